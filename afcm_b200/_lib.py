@@ -1,0 +1,138 @@
+"""ctypes binding of libafcm_b200.so -- the only way Python reaches the CUDA kernels.
+
+This is the binding a maintainer of the reference would add in place of
+torch_utils/custom_ops.get_plugin (models/networks/stylegan3/torch_utils/custom_ops.py:59-155): no JIT
+build at first call, no pybind/ATen types, just `extern "C"` entry points taking raw device pointers.
+There is deliberately NO fallback: if the library is missing or an op is called on a non-CUDA tensor
+the call raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libafcm_b200.so')
+
+OK, ERR_UNSUPPORTED, ERR_INVALID = 0, -1, -2
+F32, F16, BF16 = 0, 1, 2
+SIGN_NONE, SIGN_WRITE, SIGN_READ = 0, 1, 2
+
+_c = ctypes
+_vp, _i, _f, _i64 = _c.c_void_p, _c.c_int, _c.c_float, _c.c_int64
+_pi = _c.POINTER(_c.c_int)
+
+# name -> (restype, argtypes); mirrors include/afcm_b200.h one to one
+SIGNATURES = {
+    'afcm_version': (_i, []),
+    'afcm_last_error': (_c.c_char_p, []),
+    'afcm_device_check': (_i, []),
+    'afcm_launch_count': (_c.c_longlong, []),
+    'afcm_filtered_lrelu': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i,            # x xs y ys b skip dtype
+                                 _i, _i, _i, _i, _i, _i,                       # N C xh xw yh yw
+                                 _vp, _i, _vp, _i,                             # fu n fd n
+                                 _i, _i, _i, _i, _i, _i,                       # up down px0 px1 py0 py1
+                                 _f, _f, _f, _f, _i,                           # gain slope clamp out_scale flip
+                                 _i, _vp, _i, _i, _i, _i, _vp]),               # sign_mode signs sh swb sx sy stream
+    'afcm_filtered_lrelu_out_size': (_i, [_i] * 10 + [_pi, _pi]),
+    'afcm_filtered_lrelu_sign_size': (_i, [_i] * 4 + [_pi, _pi]),
+    'afcm_filtered_lrelu_set_tile': (_i, [_i, _i]),
+    'afcm_filtered_lrelu_act': (_i, [_vp, _i, _i64, _i, _i, _f, _f, _f, _i, _vp, _i, _i, _i, _i, _vp]),
+    'afcm_upfirdn2d': (_i, [_vp, _vp, _i, _i64, _i, _i, _i, _i, _vp, _i, _i,
+                            _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
+    'afcm_bias_act': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i64, _i64, _i, _i, _f, _f, _f, _vp]),
+    'afcm_conv2d_f32': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    'afcm_conv_weight_prep': (_i, [_vp, _i, _i, _i, _f, _i, _vp, _vp, _i, _vp, _vp]),
+    'afcm_modconv_coefs': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'afcm_conv_tc_plane_elems': (_i64, [_i, _i]),
+    'afcm_conv_tc_pack': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    'afcm_conv2d_tc': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    'afcm_fully_connected': (_i, [_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _f, _f, _i, _f, _f, _vp]),
+    'afcm_normalize_2nd_moment': (_i, [_vp, _i64, _vp, _i64, _i, _i, _f, _vp]),
+    'afcm_adaptive_avgpool': (_i, [_vp, _vp, _i64, _i, _i, _i, _i, _vp]),
+    'afcm_pad_input': (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _vp]),
+    'afcm_fourier_features': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """Loads the shared library (raises if it has not been built: `python -m afcm_b200.build`)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f'{LIB_PATH} not found: the CUDA extension is not built '
+                               f'(run `python -m afcm_b200.build`). There is no CPU fallback.')
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def last_error():
+    return lib().afcm_last_error().decode('utf-8', 'replace')
+
+
+def check(rc, allow_unsupported=False):
+    """0 -> ok; -1 -> returned to the caller when allow_unsupported (the reference's return_code < 0);
+    anything else raises RuntimeError, the analogue of the reference's TORCH_CHECK / AT_CUDA_CHECK."""
+    if rc == OK:
+        return rc
+    if rc == ERR_UNSUPPORTED and allow_unsupported:
+        return rc
+    raise RuntimeError(f'libafcm_b200 error {rc}: {last_error()}')
+
+
+def launch_count():
+    return int(lib().afcm_launch_count())
+
+
+def dtype_code(t):
+    import torch
+    return {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}[t]
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(device=None):
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('afcm_b200 ops run on CUDA tensors only (sm_100a kernels; there is no CPU fallback)')
+
+
+_host_cache = {}
+
+
+def host_array(t, dtype=np.float32):
+    """Host copy of a small constant tensor (filter taps), cached by storage pointer + version so that
+    the device->host sync happens once per filter, not per call."""
+    if t is None:
+        return None
+    key = (t.data_ptr(), t._version, tuple(t.shape), str(t.device))
+    a = _host_cache.get(key)
+    if a is None:
+        a = np.ascontiguousarray(t.detach().to('cpu', copy=True).numpy().astype(dtype, copy=False))
+        if len(_host_cache) > 4096:
+            _host_cache.clear()
+        _host_cache[key] = a
+    return a
+
+
+def np_ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def i64x4(vals):
+    return (ctypes.c_int64 * 4)(*[int(v) for v in vals])

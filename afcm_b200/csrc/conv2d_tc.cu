@@ -1,0 +1,381 @@
+// conv2d_tc.cu -- 3x3 convolution / modulated convolution as a tcgen05 + TMEM implicit GEMM (sm_100a).
+//
+// Replaces the cuDNN grouped convolution the reference reaches through modulated_conv2d
+// (models/networks/stylegan3/networks_stylegan3.py:25-64 -> torch_utils/ops/conv2d_gradfix.py:37-40)
+// and the plain encoder convolution (networks_stylegan3.py:503-505).
+//
+// Formulation (see DESIGN.md "modulated_conv2d"):
+//   * activations are pre-scaled by the modulation coefficient and packed to 16 bit in a "flat
+//     plane" layout  xp[n][ci][y*(W+2) + x]  with two zero columns at the end of every row.  A 3x3 tap
+//     (ky,kx) is then a pure shift of the flat pixel index by (ky-pad)*(W+2) + (kx-pad): horizontal
+//     taps wrap onto the zero columns, vertical taps run off the plane where TMA zero-fills.
+//   * GEMM:  D[p, o] = sum_{tap} sum_{ci} A_tap[p, ci] * B_tap[o, ci]
+//       M = 128 consecutive flat output pixels p of one sample (all of them valid outputs for pad=2)
+//       N = BN <= 256 output channels,  K = 9 taps x Ci (64 channels per pipeline stage)
+//       A_tap tile : two TMA boxes [64 ch][64 px]  -> MN-major (pixel-contiguous) SWIZZLE_128B operand
+//       B_tap tile : one TMA box   [BN o][64 ci]   -> K-major SWIZZLE_128B operand
+//       D          : fp32 accumulator in tensor memory, 2 stages x 256 columns (epilogue of tile i
+//                    overlaps the main loop of tile i+1)
+//   * warp roles: warp 0 TMA producer, warp 1 tcgen05.mma issuer (one lane), warp 2 TMEM allocator,
+//     warps 4-7 epilogue (tcgen05.ld -> demodulation scale -> coalesced NCHW fp32 stores)
+//   * persistent CTAs (one per SM), static tile striding, output-channel tiles innermost so CTAs that
+//     run concurrently share their activation tiles in L2.
+#include <cuda.h>
+#include "afcm_common.cuh"
+
+namespace afcm {
+
+constexpr int TC_BM = 128;            // pixels per tile (UMMA M)
+constexpr int TC_BK = 64;             // channels per pipeline stage
+constexpr int TC_STAGES = 4;
+constexpr int TC_THREADS = 256;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;          // 16 KB
+constexpr int TC_TMEM_COLS = 512;
+constexpr unsigned TC_SPIN_LIMIT = 1u << 27;           // watchdog: trap instead of hanging the GPU
+
+struct TcParams {
+    const float* ocoef;     // [N, Co] or null
+    float* y;               // [N, Co, OH, OW]
+    int N, Ci, Co, H, W, Wp, OH, OW, pad;
+    int BN, n_tiles, m_tiles, cblocks;     // channel tile, #channel tiles, #pixel tiles per sample, ceil(Ci/64)
+    int total_tiles;
+    unsigned idesc;
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    for (unsigned spin = 0; !done; spin++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (spin > TC_SPIN_LIMIT) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, leading / stride byte
+// offsets in 16-byte units, version 1 (Blackwell), SWIZZLE_128B layout.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// ---- the kernel --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ TcParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int b_bytes = p.BN * TC_BK * 2;
+    const int stage_bytes = TC_A_BYTES + b_bytes;
+    uint8_t* tail = smem + TC_STAGES * stage_bytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(tail);                 // [TC_STAGES]
+    uint64_t* empty = full + TC_STAGES;                                 // [TC_STAGES]
+    uint64_t* tfull = empty + TC_STAGES;                                // [2]
+    uint64_t* tempty = tfull + 2;                                       // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* s_ocoef = reinterpret_cast<float*>(tail + 128);              // [2][256]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < TC_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int kblocks = 9 * p.cblocks;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int nt = tile % p.n_tiles;
+                const int r = tile / p.n_tiles;
+                const int mt = r % p.m_tiles, n = r / p.m_tiles;
+                const int p0 = mt * TC_BM, o0 = nt * p.BN;
+                for (int kb = 0; kb < kblocks; kb++) {
+                    const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
+                    const int ky = tap / 3, kx = tap - ky * 3;
+                    const int shift = (ky - p.pad) * p.Wp + (kx - p.pad);
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * stage_bytes;
+                    mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
+                    tma_load_3d(sa, &map_a, &full[stage], p0 + shift, cb * TC_BK, n);
+                    tma_load_3d(sa + TC_A_BYTES / 2, &map_a, &full[stage], p0 + shift + 64, cb * TC_BK, n);
+                    tma_load_3d(sa + TC_A_BYTES, &map_b, &full[stage], cb * TC_BK, o0, tap);
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256);
+                for (int kb = 0; kb < kblocks; kb++) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+                    const uint32_t sb = sa + TC_A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; k++) {
+                        // A: MN-major, 16 channels = two 8-row groups of 128 B rows (SBO 1024), two 64-pixel chunks (LBO 8192)
+                        const uint64_t adesc = make_desc(sa + k * 2048, TC_A_BYTES / 2, 1024);
+                        // B: K-major, 16 channels = 32 bytes inside the 128 B swizzled row, 8-row groups 1024 B apart
+                        const uint64_t bdesc = make_desc(sb + k * 32, 16, 1024);
+                        umma_f16(tmem_d, adesc, bdesc, p.idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty[stage]);
+                    if (kb == kblocks - 1) umma_commit(&tfull[acc]);
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue =================
+        const int wq = warp & 3;
+        const int et = threadIdx.x - 128;
+        int acc = 0; uint32_t acc_phase = 0;
+        const long long ohw = (long long)p.OH * p.OW;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const int nt = tile % p.n_tiles;
+            const int r = tile / p.n_tiles;
+            const int mt = r % p.m_tiles, n = r / p.m_tiles;
+            const int o0 = nt * p.BN;
+            for (int j = et; j < p.BN; j += 128) {
+                const int o = o0 + j;
+                s_ocoef[acc * 256 + j] = (o < p.Co) ? (p.ocoef ? p.ocoef[(long long)n * p.Co + o] : 1.f) : 0.f;
+            }
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int pix = mt * TC_BM + wq * 32 + lane;
+            const int oy = pix / p.Wp, ox = pix - oy * p.Wp;
+            const bool ok = oy < p.OH && ox < p.OW;
+            float* yb = p.y + ((long long)n * p.Co + o0) * ohw + (long long)oy * p.OW + ox;
+            for (int c0 = 0; c0 < p.BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * 256 + c0), v);
+                tmem_ld_wait();
+                if (ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++)
+                        if (o0 + c0 + j < p.Co)
+                            yb[(long long)(c0 + j) * ohw] = __uint_as_float(v[j]) * s_ocoef[acc * 256 + c0 + j];
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+    }
+}
+
+// ---- activation packing -------------------------------------------------------------------------------
+template <typename TC>
+__global__ void __launch_bounds__(256)
+tc_pack_kernel(const float* __restrict__ x, const float* __restrict__ icoef, TC* __restrict__ xp,
+               long long planes, int H, int W, int Wp, long long plane_pad)
+{
+    const long long total = planes * plane_pad;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long pl = i / plane_pad;
+        const int idx = (int)(i - pl * plane_pad);
+        const int yy = idx / Wp, xx = idx - yy * Wp;
+        float v = 0.f;
+        if (yy < H && xx < W) {
+            v = x[(pl * H + yy) * W + xx];
+            if (icoef) v *= icoef[pl];
+        }
+        xp[i] = (TC)v;
+    }
+}
+
+// ---- host -----------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+static int encode_3d(CUtensorMap* map, int tc_dtype, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                     uint64_t s1_bytes, uint64_t s2_bytes, uint32_t b0, uint32_t b1)
+{
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return AFCM_ERR_UNSUPPORTED; }
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {s1_bytes, s2_bytes};
+    cuuint32_t box[3] = {b0, b1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, tc_dtype == AFCM_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return AFCM_ERR_INVALID; }
+    return AFCM_OK;
+}
+
+}  // namespace afcm
+
+using namespace afcm;
+
+extern "C" int64_t afcm_conv_tc_plane_elems(int H, int W)
+{
+    return (((int64_t)H * (W + 2)) + 7) & ~(int64_t)7;
+}
+
+extern "C" int afcm_conv_tc_pack(const float* x, const float* icoef, void* xp, int tc_dtype,
+                                 int N, int Ci, int H, int W, void* stream)
+{
+    AFCM_CHECK_ARG(x && xp && N > 0 && Ci > 0 && H > 0 && W > 0, "empty problem");
+    AFCM_CHECK_ARG(tc_dtype == AFCM_F16 || tc_dtype == AFCM_BF16, "tc dtype must be F16 or BF16");
+    const long long planes = (long long)N * Ci, plane_pad = afcm_conv_tc_plane_elems(H, W);
+    long long blocks = (planes * plane_pad + 255) / 256;
+    const long long cap = (long long)sm_count() * 32;
+    if (blocks > cap) blocks = cap;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (tc_dtype == AFCM_BF16) tc_pack_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(x, icoef, (__nv_bfloat16*)xp, planes, H, W, W + 2, plane_pad);
+    else tc_pack_kernel<__half><<<(unsigned)blocks, 256, 0, st>>>(x, icoef, (__half*)xp, planes, H, W, W + 2, plane_pad);
+    AFCM_LAUNCH_CHECK();
+    count_launch();
+    return AFCM_OK;
+}
+
+extern "C" int afcm_conv2d_tc(const void* xp, const void* w_tc, const float* ocoef, float* y, int tc_dtype,
+                              int N, int Ci, int H, int W, int Co, int pad, void* stream)
+{
+    AFCM_CHECK_ARG(xp && w_tc && y, "xp, w_tc and y must be given");
+    AFCM_CHECK_ARG(N > 0 && Ci > 0 && Co > 0 && H > 0 && W > 0, "empty problem");
+    AFCM_CHECK_ARG(tc_dtype == AFCM_F16 || tc_dtype == AFCM_BF16, "tc dtype must be F16 or BF16");
+    if (pad != 1 && pad != 2) { set_error("conv2d_tc: padding %d not supported (1 or 2)", pad); return AFCM_ERR_UNSUPPORTED; }
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.ocoef = ocoef; p.y = y;
+    p.N = N; p.Ci = Ci; p.Co = Co; p.H = H; p.W = W; p.Wp = W + 2; p.pad = pad;
+    p.OH = H + 2 * pad - 2; p.OW = W + 2 * pad - 2;
+    p.n_tiles = ceil_div(Co, 256);
+    p.BN = ((ceil_div(Co, p.n_tiles) + 31) / 32) * 32;
+    p.m_tiles = ceil_div((long long)p.OH * p.Wp, TC_BM);
+    p.cblocks = ceil_div(Ci, TC_BK);
+    const long long total = (long long)N * p.m_tiles * p.n_tiles;
+    AFCM_CHECK_ARG(total <= 0x7fffffffLL, "too many tiles");
+    p.total_tiles = (int)total;
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A/B = F16|BF16, A MN-major, B K-major, N, M
+    const unsigned fmt = tc_dtype == AFCM_BF16 ? 1u : 0u;
+    p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (0u << 16) | ((unsigned)(p.BN >> 3) << 17) | ((unsigned)(TC_BM >> 4) << 24);
+
+    const int co_pad = (Co + 15) & ~15, ci_pad = (Ci + 63) & ~63;
+    const uint64_t plane_pad = (uint64_t)afcm_conv_tc_plane_elems(H, W);
+    CUtensorMap map_a, map_b;
+    int rc = encode_3d(&map_a, tc_dtype, xp, plane_pad, (uint64_t)Ci, (uint64_t)N, plane_pad * 2, plane_pad * 2 * Ci, 64, TC_BK);
+    if (rc) return rc;
+    rc = encode_3d(&map_b, tc_dtype, w_tc, (uint64_t)ci_pad, (uint64_t)co_pad, 9, (uint64_t)ci_pad * 2, (uint64_t)ci_pad * 2 * co_pad,
+                   TC_BK, (uint32_t)p.BN);
+    if (rc) return rc;
+
+    const int smem = TC_STAGES * (TC_A_BYTES + p.BN * TC_BK * 2) + 128 + 2 * 256 * 4 + 1024;
+    AFCM_CUDA(cudaFuncSetAttribute(conv2d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int grid = sm_count();
+    if (grid > p.total_tiles) grid = p.total_tiles;
+    conv2d_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
+    AFCM_LAUNCH_CHECK();
+    count_launch();
+    return AFCM_OK;
+}

@@ -1,0 +1,116 @@
+"""conv2d_gradfix -- the convolution entry point of the reference's operator API
+(models/networks/stylegan3/torch_utils/ops/conv2d_gradfix.py:37-40, which forwards to cuDNN), served by
+the hand-written kernels of libafcm_b200: an exact-fp32 SIMT kernel (`impl='f32'`, the parity path) and
+the tcgen05/TMEM implicit GEMM with 16-bit operands and fp32 accumulation (`impl='tc'`).
+
+Module switches (process-wide, like the reference's `enabled` flag):
+    conv_impl : 'f32' | 'tc'      default implementation used by conv2d() / modulated_conv2d()
+    tc_dtype  : torch.float16 | torch.bfloat16   operand type of the tensor-core path
+"""
+import numpy as np
+import torch
+
+from ... import _lib
+
+conv_impl = 'f32'
+tc_dtype = torch.float16
+enabled = False                      # kept for API compatibility with the reference module
+weight_gradients_disabled = False
+
+_prep_cache = {}
+
+
+def set_conv_impl(impl, dtype=None):
+    global conv_impl, tc_dtype
+    assert impl in ('f32', 'tc')
+    conv_impl = impl
+    if dtype is not None:
+        assert dtype in (torch.float16, torch.bfloat16)
+        tc_dtype = dtype
+
+
+def prepare_weight(w, pre_scale=1.0, normalize=False, want_tc=False, want_wsq=False, dtype=None):
+    """Per-layer constant preparation (afcm_conv_weight_prep), cached on (storage, version): scaled /
+    RMS-normalised fp32 weights, the 16-bit tap-major copy for the tensor-core kernel and the per-(o,i)
+    squared sums used by demodulation."""
+    dtype = dtype or tc_dtype
+    key = (w.data_ptr(), w._version, tuple(w.shape), float(pre_scale), bool(normalize), str(w.device))
+    ent = _prep_cache.get(key)
+    if ent is None:
+        if len(_prep_cache) > 512:
+            _prep_cache.clear()
+        ent = _prep_cache[key] = {}
+    need_f32 = 'w_f32' not in ent
+    need_tc = want_tc and ('w_tc', dtype) not in ent
+    need_wsq = want_wsq and 'wsq' not in ent
+    if need_f32 or need_tc or need_wsq:
+        Co, Ci, kh, kw = w.shape
+        assert kh == kw
+        wc = w.detach().contiguous().float()
+        w_f32 = torch.empty_like(wc) if need_f32 else None
+        w_tc = None
+        if need_tc:
+            w_tc = torch.empty([kh * kw, (Co + 15) // 16 * 16, (Ci + 63) // 64 * 64], dtype=dtype, device=w.device)
+        wsq = torch.empty([Co, Ci], dtype=torch.float32, device=w.device) if need_wsq else None
+        _lib.check(_lib.lib().afcm_conv_weight_prep(
+            _lib.ptr(wc), Co, Ci, kh, float(pre_scale), int(bool(normalize)), _lib.ptr(w_f32), _lib.ptr(w_tc),
+            _lib.dtype_code(dtype), _lib.ptr(wsq), _lib.stream_ptr(w.device)))
+        if need_f32:
+            ent['w_f32'] = w_f32
+        if need_tc:
+            ent[('w_tc', dtype)] = w_tc
+        if need_wsq:
+            ent['wsq'] = wsq
+    return ent
+
+
+def conv2d_native(x, w, padding, icoef=None, ocoef=None, pre_scale=1.0, normalize=False, impl=None, out=None):
+    """y[n,o] = ocoef[n,o] * conv(icoef[n,i] * x[n,i], prepared(w))  -- the shared formulation of the
+    encoder conv, Conv2dLayer and modulated_conv2d (include/afcm_b200.h)."""
+    impl = impl or conv_impl
+    _lib.require_cuda(x, w)
+    L = _lib.lib()
+    N, Ci, H, W = x.shape
+    Co, Ci2, kh, kw = w.shape
+    assert Ci == Ci2 and kh == kw
+    if x.dtype != torch.float32:
+        raise RuntimeError('afcm conv2d: activations must be float32 (the reference network runs in fp32)')
+    x = x.contiguous()
+    OH, OW = H + 2 * padding - kh + 1, W + 2 * padding - kw + 1
+    y = out if out is not None else torch.empty([N, Co, OH, OW], dtype=torch.float32, device=x.device)
+    st = _lib.stream_ptr(x.device)
+    use_tc = impl == 'tc' and kh == 3 and padding in (1, 2)
+    ent = prepare_weight(w, pre_scale, normalize, want_tc=use_tc)
+    if use_tc:
+        plane = int(L.afcm_conv_tc_plane_elems(H, W))
+        xp = torch.empty([N, Ci, plane], dtype=tc_dtype, device=x.device)
+        code = _lib.dtype_code(tc_dtype)
+        _lib.check(L.afcm_conv_tc_pack(_lib.ptr(x), _lib.ptr(icoef), _lib.ptr(xp), code, N, Ci, H, W, st))
+        _lib.check(L.afcm_conv2d_tc(_lib.ptr(xp), _lib.ptr(ent[('w_tc', tc_dtype)]), _lib.ptr(ocoef), _lib.ptr(y), code,
+                                    N, Ci, H, W, Co, padding, st))
+    else:
+        _lib.check(L.afcm_conv2d_f32(_lib.ptr(x), _lib.ptr(ent['w_f32']), _lib.ptr(icoef), _lib.ptr(ocoef), _lib.ptr(y),
+                                     N, Ci, H, W, Co, kh, padding, st))
+    return y
+
+
+def conv2d(input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
+    """Drop-in for conv2d_gradfix.conv2d (reference :37-40) for the configurations the generator uses:
+    stride 1, dilation 1, groups 1, square 1x1 / 3x3 kernels, symmetric integer padding.  Forward only --
+    gradients of the convolution are the training-step row of the scope table."""
+    assert isinstance(input, torch.Tensor)
+    if isinstance(padding, (tuple, list)):
+        assert padding[0] == padding[1]
+        padding = padding[0]
+    if stride not in (1, (1, 1)) or dilation not in (1, (1, 1)) or groups != 1:
+        raise NotImplementedError('afcm conv2d supports stride=1, dilation=1, groups=1 only')
+    if torch.is_grad_enabled() and (input.requires_grad or weight.requires_grad):
+        raise NotImplementedError('afcm conv2d: backward is not implemented yet (forward-only hot path)')
+    y = conv2d_native(input, weight, int(padding))
+    if bias is not None:
+        y = y + bias.reshape(1, -1, 1, 1)
+    return y
+
+
+def conv_transpose2d(*args, **kwargs):
+    raise NotImplementedError('conv_transpose2d is not on the AFCM stylegan3 generator path')

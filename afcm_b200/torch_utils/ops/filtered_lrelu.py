@@ -1,0 +1,189 @@
+"""filtered_lrelu -- same public signature as the reference op
+(models/networks/stylegan3/torch_utils/ops/filtered_lrelu.py:56), executed by the hand-written sm_100a
+kernel behind afcm_filtered_lrelu (include/afcm_b200.h).  `impl` is accepted for compatibility and
+ignored: there is one implementation and it needs a CUDA tensor."""
+import numpy as np
+import torch
+
+from ... import _lib
+from . import upfirdn2d as _upfirdn2d
+
+
+def _get_filter_size(f):
+    if f is None:
+        return 1, 1
+    assert isinstance(f, torch.Tensor) and 1 <= f.ndim <= 2
+    return f.shape[-1], f.shape[0]  # width, height
+
+
+def _parse_padding(padding):
+    # same accepted forms as the reference (filtered_lrelu.py:42-52)
+    if isinstance(padding, (int, np.integer)):
+        padding = [padding, padding]
+    assert isinstance(padding, (list, tuple))
+    assert all(isinstance(x, (int, np.integer)) for x in padding)
+    padding = [int(x) for x in padding]
+    if len(padding) == 2:
+        px, py = padding
+        padding = [px, px, py, py]
+    px0, px1, py0, py1 = padding
+    return px0, px1, py0, py1
+
+
+def filtered_lrelu(x, fu=None, fd=None, b=None, up=1, down=1, padding=0, gain=np.sqrt(2), slope=0.2, clamp=None,
+                   flip_filter=False, impl='cuda'):
+    r"""Filtered leaky ReLU: bias, zero-insert upsample by `up`, pad, FIR `fu`, gain, leaky ReLU, clamp,
+    FIR `fd`, keep every `down`-th sample.  Arguments as in the reference (filtered_lrelu.py:85-111).
+    Supports first-order gradients w.r.t. `x` and `b` (the backward pass re-runs the op with the filters
+    swapped, reading the 2-bit sign tensor written by the forward pass, like the reference)."""
+    assert isinstance(x, torch.Tensor)
+    assert impl in ['ref', 'cuda']
+    _lib.require_cuda(x)
+    return _filtered_lrelu_cuda(up=up, down=down, padding=padding, gain=gain, slope=slope, clamp=clamp,
+                                flip_filter=flip_filter).apply(x, fu, fd, b, None, 0, 0)
+
+
+def _taps_1d(f):
+    """(host taps or None, taps) for a separable filter; None for a 2-D filter (no fused kernel)."""
+    if f is None:
+        return None, 1
+    if f.ndim == 1:
+        return _lib.host_array(f), int(f.shape[0])
+    if f.ndim == 2 and f.shape[0] == 1 and f.shape[1] == 1:
+        return _lib.host_array(f).reshape(1), 1
+    return False, 0
+
+
+def _run_fused(x, fu, fd, b, si, up, down, px0, px1, py0, py1, sx, sy, gain, slope, clamp, flip_filter, write_signs,
+               skip=None, out_scale=1.0):
+    """Calls afcm_filtered_lrelu.  Returns (y, so, return_code) like the reference plugin
+    (filtered_lrelu.cpp:16-18,208): return_code -1 means 'no fused kernel for this geometry'."""
+    L = _lib.lib()
+    fu_h, fu_n = _taps_1d(fu)
+    fd_h, fd_n = _taps_1d(fd)
+    if fu_h is False or fd_h is False or x.dtype not in (torch.float32, torch.float16):
+        return None, None, -1
+    N, C, xh, xw = x.shape
+    yh, yw = _lib._c.c_int(), _lib._c.c_int()
+    _lib.check(L.afcm_filtered_lrelu_out_size(xh, xw, up, down, fu_n, fd_n, px0, px1, py0, py1, yh, yw))
+    yh, yw = yh.value, yw.value
+    y = torch.empty([N, C, yh, yw], dtype=x.dtype, device=x.device)
+    so = None
+    mode, s, sh, swb = _lib.SIGN_NONE, None, 0, 0
+    if write_signs:
+        a, c = _lib._c.c_int(), _lib._c.c_int()
+        L.afcm_filtered_lrelu_sign_size(yh, yw, down, fd_n, a, c)
+        sh, swb = a.value, c.value
+        so = torch.empty([N, C, sh, swb], dtype=torch.uint8, device=x.device)
+        mode, s = _lib.SIGN_WRITE, so
+    elif si is not None and si.numel():
+        assert si.is_contiguous() and si.dtype == torch.uint8 and si.ndim == 4
+        mode, s, sh, swb = _lib.SIGN_READ, si, si.shape[2], si.shape[3]
+    if b is not None:
+        b = b.contiguous()
+    if skip is not None:
+        assert skip.shape == y.shape and skip.dtype == y.dtype
+        skip = skip.contiguous()
+    rc = L.afcm_filtered_lrelu(
+        _lib.ptr(x), _lib.i64x4(x.stride()), _lib.ptr(y), _lib.i64x4(y.stride()), _lib.ptr(b), _lib.ptr(skip),
+        _lib.dtype_code(x.dtype), N, C, xh, xw, yh, yw,
+        _lib.np_ptr(fu_h), fu_n, _lib.np_ptr(fd_h), fd_n, up, down, px0, px1, py0, py1,
+        gain, slope, clamp, out_scale, int(bool(flip_filter)), mode, _lib.ptr(s), sh, swb, int(sx), int(sy),
+        _lib.stream_ptr(x.device))
+    _lib.check(rc, allow_unsupported=True)
+    if rc != 0:
+        return None, None, rc
+    return y, so, 0
+
+
+def _act_(y, si, sx, sy, gain, slope, clamp, write_signs):
+    """In-place activation step of the generic composition (reference: filtered_lrelu_act_)."""
+    L = _lib.lib()
+    assert y.is_contiguous()
+    N, C, h, w = y.shape
+    so = None
+    mode, s, sh, swb = _lib.SIGN_NONE, None, 0, 0
+    if write_signs:
+        swb = ((w + 15) & ~15) >> 2
+        sh = h
+        so = torch.empty([N, C, sh, swb], dtype=torch.uint8, device=y.device)
+        mode, s = _lib.SIGN_WRITE, so
+    elif si is not None and si.numel():
+        mode, s, sh, swb = _lib.SIGN_READ, si, si.shape[2], si.shape[3]
+    _lib.check(L.afcm_filtered_lrelu_act(_lib.ptr(y), _lib.dtype_code(y.dtype), N * C, h, w, gain, slope, clamp,
+                                         mode, _lib.ptr(s), sh, swb, int(sx), int(sy), _lib.stream_ptr(y.device)))
+    return so
+
+
+_filtered_lrelu_cuda_cache = dict()
+
+
+def _filtered_lrelu_cuda(up=1, down=1, padding=0, gain=np.sqrt(2), slope=0.2, clamp=None, flip_filter=False):
+    assert isinstance(up, (int, np.integer)) and up >= 1
+    assert isinstance(down, (int, np.integer)) and down >= 1
+    up, down = int(up), int(down)
+    px0, px1, py0, py1 = _parse_padding(padding)
+    assert gain == float(gain) and gain > 0
+    gain = float(gain)
+    assert slope == float(slope) and slope >= 0
+    slope = float(slope)
+    assert clamp is None or (clamp == float(clamp) and clamp >= 0)
+    clamp = float(clamp if clamp is not None else 'inf')
+
+    key = (up, down, px0, px1, py0, py1, gain, slope, clamp, flip_filter)
+    if key in _filtered_lrelu_cuda_cache:
+        return _filtered_lrelu_cuda_cache[key]
+
+    class FilteredLReluCuda(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, fu, fd, b, si, sx, sy):
+            assert isinstance(x, torch.Tensor) and x.ndim == 4
+            _lib.require_cuda(x, fu, fd, b)
+            if b is not None:
+                assert b.dtype == x.dtype and b.ndim == 1 and b.shape[0] == x.shape[1]
+            write_signs = (si is None or si.numel() == 0) and (x.requires_grad or (b is not None and b.requires_grad))
+            y, so, rc = _run_fused(x, fu, fd, b, si, up, down, px0, px1, py0, py1, sx, sy, gain, slope, clamp,
+                                   flip_filter, write_signs)
+            if rc < 0:
+                # Generic composition, same as the reference's fallback (filtered_lrelu.py:223-229):
+                # bias, upfirdn2d(up), in-place activation with sign handling, upfirdn2d(down).
+                y = x if b is None else x + b.reshape(1, -1, 1, 1)
+                y = _upfirdn2d.upfirdn2d(y, fu, up=up, padding=[px0, px1, py0, py1], gain=up ** 2,
+                                         flip_filter=flip_filter).contiguous()
+                if y is x:
+                    y = y.clone()
+                so = _act_(y, si, sx, sy, gain, slope, clamp, write_signs)
+                y = _upfirdn2d.upfirdn2d(y, fd, down=down, flip_filter=flip_filter)
+            ctx.save_for_backward(fu, fd, (si if (si is not None and si.numel()) else so))
+            ctx.x_shape = x.shape
+            ctx.y_shape = y.shape
+            ctx.s_ofs = sx, sy
+            ctx.has_b = b is not None
+            return y
+
+        @staticmethod
+        def backward(ctx, dy):
+            fu, fd, si = ctx.saved_tensors
+            _, _, xh, xw = ctx.x_shape
+            _, _, yh, yw = ctx.y_shape
+            sx, sy = ctx.s_ofs
+            dx = None
+            db = None
+            fuw, fuh = _get_filter_size(fu)
+            fdw, fdh = _get_filter_size(fd)
+            if ctx.needs_input_grad[0] or ctx.needs_input_grad[3]:
+                # reference: filtered_lrelu.py:252-263
+                pp = [(fuw - 1) + (fdw - 1) - px0, xw * up - yw * down + px0 - (up - 1),
+                      (fuh - 1) + (fdh - 1) - py0, xh * up - yh * down + py0 - (up - 1)]
+                gg = gain * (up ** 2) / (down ** 2)
+                ff = (not flip_filter)
+                sx = sx - (fuw - 1) + px0
+                sy = sy - (fuh - 1) + py0
+                dx = _filtered_lrelu_cuda(up=down, down=up, padding=pp, gain=gg, slope=slope, clamp=None,
+                                          flip_filter=ff).apply(dy, fd, fu, None, si, sx, sy)
+            if ctx.needs_input_grad[3] and ctx.has_b:
+                db = dx.sum([0, 2, 3])
+            return dx, None, None, db, None, None, None
+
+    _filtered_lrelu_cuda_cache[key] = FilteredLReluCuda
+    return FilteredLReluCuda

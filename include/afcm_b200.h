@@ -1,0 +1,187 @@
+/*
+ * afcm_b200.h -- C ABI of libafcm_b200.so, the B200 (sm_100a) implementation of the AFCM generator
+ * forward hot path.  Plain pointers and sizes only: no torch / ATen types cross this boundary.
+ *
+ * Each entry point replaces one native interface of the reference (paths relative to the
+ * reference repo; OPS = models/networks/stylegan3/torch_utils/ops, NET =
+ * models/networks/stylegan3/networks_stylegan3.py).  INTEGRATION.md shows the binding a reference
+ * maintainer would add (ctypes, as used by afcm_b200/_lib.py).
+ *
+ * Conventions
+ *   - every function returns int: 0 = ok, AFCM_ERR_UNSUPPORTED (-1) = no kernel for these arguments
+ *     (same meaning as the reference's return code -1, OPS/filtered_lrelu.cpp:52-56: the caller may
+ *     use the generic composition), AFCM_ERR_INVALID (-2) = bad arguments (the reference raises
+ *     TORCH_CHECK), > 0 = a cudaError_t.  afcm_last_error() returns a thread-local message.
+ *   - all data pointers are DEVICE pointers unless the name ends in _host.
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued, never synchronised.
+ *   - tensors are NCHW; dtype codes AFCM_F32 / AFCM_F16 / AFCM_BF16.  Filter taps are HOST arrays:
+ *     they are layer constants and travel in the kernel-parameter constant bank (the reference
+ *     staged them through a global buffer + __constant__ copy on every call,
+ *     OPS/filtered_lrelu.cu:87-117, which made the op unsafe on concurrent streams).
+ *   - no entry point allocates device memory; the caller (PyTorch in this repo) owns every buffer.
+ */
+#ifndef AFCM_B200_H
+#define AFCM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AFCM_OK               0
+#define AFCM_ERR_UNSUPPORTED (-1)
+#define AFCM_ERR_INVALID     (-2)
+
+#define AFCM_F32  0
+#define AFCM_F16  1
+#define AFCM_BF16 2
+
+/* sign-tensor modes of afcm_filtered_lrelu (OPS/filtered_lrelu.cpp:83-96) */
+#define AFCM_SIGN_NONE  0
+#define AFCM_SIGN_WRITE 1
+#define AFCM_SIGN_READ  2
+
+/* ---------------------------------------------------------------------------------------------- */
+/* library                                                                                         */
+
+int         afcm_version(void);                 /* ABI version, currently 1 */
+const char* afcm_last_error(void);              /* message of the last failing call on this thread */
+int         afcm_device_check(void);            /* 0 iff the current device is sm_100 (B200)        */
+long long   afcm_launch_count(void);            /* kernels launched by this library so far          */
+
+/* ---------------------------------------------------------------------------------------------- */
+/* filtered_lrelu -- replaces filtered_lrelu_plugin.filtered_lrelu (OPS/filtered_lrelu.cpp:16-209)   */
+/*
+ * y = down_fir(clamp(lrelu((up_fir(zero_insert(x + b)) ) * gain)))   (OPS/filtered_lrelu.py:59-80)
+ *
+ * x [N,C,xh,xw] with element strides xs[4] = {n,c,h,w};  y [N,C,yh,yw] with strides ys[4];
+ * yh/yw must equal afcm_filtered_lrelu_out_size().  b: [C] or NULL.  skip: optional tensor with y's
+ * shape and strides that is added to the result (fuses NET:376-377), out_scale multiplies it
+ * (fuses NET:699-700); pass NULL / 1.0f for the plain op.
+ * fu_host/fd_host: separable 1-D taps (NULL + taps 1 = identity).  Supported fused geometries:
+ *   (up,fu,down,fd) in {(2,12,2,12), (2,12,4,24), (4,24,2,12)}  and  (1,1,1,1);
+ * anything else returns AFCM_ERR_UNSUPPORTED and the caller composes afcm_upfirdn2d +
+ * afcm_filtered_lrelu_act + afcm_upfirdn2d exactly like OPS/filtered_lrelu.py:223-229.
+ * sign_mode WRITE: `signs` [N,C,sh,swb] uint8 is written (2 bits / up-sampled element: 1 = negative,
+ * 2 = clamped; sh, swb from afcm_filtered_lrelu_sign_size()).  READ: `signs` is applied at element
+ * offset (sx,sy) instead of lrelu/clamp (the backward pass, OPS/filtered_lrelu.py:252-266).
+ */
+int afcm_filtered_lrelu(const void* x, const int64_t* xs, void* y, const int64_t* ys,
+                        const void* b, const void* skip, int dtype,
+                        int N, int C, int xh, int xw, int yh, int yw,
+                        const float* fu_host, int fu_taps, const float* fd_host, int fd_taps,
+                        int up, int down, int px0, int px1, int py0, int py1,
+                        float gain, float slope, float clamp, float out_scale, int flip_filter,
+                        int sign_mode, void* signs, int sign_h, int sign_wb, int sx, int sy,
+                        void* stream);
+
+int afcm_filtered_lrelu_out_size(int xh, int xw, int up, int down, int fu_taps, int fd_taps,
+                                 int px0, int px1, int py0, int py1, int* yh, int* yw);
+int afcm_filtered_lrelu_sign_size(int yh, int yw, int down, int fd_taps, int* sh, int* swb);
+
+/* Tile override for tuning (0,0 = automatic).  Process-global, not part of the stable ABI. */
+int afcm_filtered_lrelu_set_tile(int tow, int toh);
+
+/* filtered_lrelu_act_ -- replaces filtered_lrelu_plugin.filtered_lrelu_act_ (OPS/filtered_lrelu.cpp:213-290):
+ * in-place gain / lrelu / clamp with optional sign write or read on a dense [planes,h,w] tensor.     */
+int afcm_filtered_lrelu_act(void* x, int dtype, int64_t planes, int h, int w,
+                            float gain, float slope, float clamp,
+                            int sign_mode, void* signs, int sign_h, int sign_wb, int sx, int sy,
+                            void* stream);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* upfirdn2d -- replaces upfirdn2d_plugin.upfirdn2d (OPS/upfirdn2d.cpp:16-98)                        */
+/* x [planes,xh,xw] dense, y [planes,yh,yw] dense, f_host [fh][fw] dense 2-D taps (a separable filter */
+/* is two calls, as in OPS/upfirdn2d.py:241-245).                                                    */
+int afcm_upfirdn2d(const void* x, void* y, int dtype, int64_t planes, int xh, int xw, int yh, int yw,
+                   const float* f_host, int fh, int fw,
+                   int upx, int upy, int downx, int downy, int px0, int px1, int py0, int py1,
+                   int flip_filter, float gain, void* stream);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* bias_act -- replaces bias_act_plugin.bias_act (OPS/bias_act.cpp:32-90)                            */
+/* grad 0: y = clamp(act(x + b) * gain).  grad 1: dx from dy (= x argument), xref, yref.  grad 2:    */
+/* second-order term from dy-of-dy (= x), xref, yref, dy.  b indexes (i / step_b) % size_b.          */
+int afcm_bias_act(const void* x, const void* b, const void* xref, const void* yref, const void* dy,
+                  void* y, int dtype, int64_t n, int64_t step_b, int64_t size_b,
+                  int grad, int act, float alpha, float gain, float clamp, void* stream);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* convolution / modulated convolution -- replace modulated_conv2d (NET:25-64), the encoder conv    */
+/* (NET:503-505) and Conv2dLayer's conv (models/networks/CoModGAN/layers.py:157) which the reference */
+/* routes to cuDNN through conv2d_gradfix.conv2d (OPS/conv2d_gradfix.py:37-40).                       */
+/*
+ * Shared formulation:  y[n,o] = ocoef[n,o] * sum_{i,ky,kx} w[o,i,ky,kx] * (icoef[n,i] * x[n,i])
+ * (stride 1, zero padding `pad`, correlation).  For modulated_conv2d icoef = normalised style *
+ * input_gain and ocoef = demodulation coefficient (both from afcm_modconv_coefs), which is
+ * algebraically the reference's per-sample weight w*s*d*g without materialising [N,O,I,k,k].
+ * icoef / ocoef may be NULL (= 1).
+ */
+
+/* exact-fp32 SIMT path (parity path, |err| ~ 1e-6 relative). */
+int afcm_conv2d_f32(const float* x, const float* w, const float* icoef, const float* ocoef, float* y,
+                    int N, int Ci, int H, int W, int Co, int ksize, int pad, void* stream);
+
+/* Per-layer weight preparation.  w [Co,Ci,k,k] fp32 (as stored in the reference state_dict).
+ * pre_scale: multiply every weight (encoder: 1/sqrt(Ci*k*k), NET:464,503).  normalize != 0: divide each
+ * output channel by its RMS (NET:42).  Writes any of (NULL = skip):
+ *   w_f32  [Co,Ci,k,k]        prepared weights for afcm_conv2d_f32
+ *   w_tc   [k*k,Co_pad,Ci_pad] 16-bit (tc_dtype AFCM_F16/AFCM_BF16) tap-major K-major tile source for the
+ *                              tcgen05 kernel, zero padded (Co_pad = roundup(Co,16), Ci_pad = roundup(Ci,64))
+ *   wsq    [Co,Ci]             sum over taps of the prepared weight squared (demodulation GEMV input) */
+int afcm_conv_weight_prep(const float* w, int Co, int Ci, int ksize, float pre_scale, int normalize,
+                          float* w_f32, void* w_tc, int tc_dtype, float* wsq, void* stream);
+
+/* Modulation coefficients (NET:41-57).  styles [N,Ci]; demodulate != 0: s_hat = s * rsqrt(mean(s^2)) over
+ * the whole [N,Ci] batch, ocoef[n,o] = rsqrt(sum_i wsq[o,i] * s_hat[n,i]^2 + 1e-8); else s_hat = s,
+ * ocoef = 1.  icoef[n,i] = s_hat[n,i] * input_gain (input_gain: device scalar pointer or NULL). */
+int afcm_modconv_coefs(const float* styles, const float* wsq, const float* input_gain,
+                       float* icoef, float* ocoef, int N, int Ci, int Co, int demodulate, void* stream);
+
+/* tcgen05 / TMEM implicit-GEMM path (16-bit operands, fp32 accumulation in tensor memory).
+ * Step 1: pack activations into the conv-ready layout  xp [N,Ci,plane_pad] 16-bit, where each plane is
+ * H rows of pitch W+2 (two trailing zeros per row, so horizontal taps wrap onto zeros) and plane_pad =
+ * afcm_conv_tc_plane_elems(H,W).  icoef is folded here (modulation on the activation side).
+ * Step 2: afcm_conv2d_tc runs the GEMM  D[pixel, o] = sum_{tap,i} A_tap[pixel,i] * B_tap[o,i]  with
+ * M = 128 flat pixels, N = up to 256 output channels per CTA, TMA-fed, and writes fp32 NCHW
+ * y [N,Co,H+2*pad-2,W+2*pad-2] scaled by ocoef.  ksize must be 3, pad 1 or 2. */
+int64_t afcm_conv_tc_plane_elems(int H, int W);
+int afcm_conv_tc_pack(const float* x, const float* icoef, void* xp, int tc_dtype,
+                      int N, int Ci, int H, int W, void* stream);
+int afcm_conv2d_tc(const void* xp, const void* w_tc, const float* ocoef, float* y, int tc_dtype,
+                   int N, int Ci, int H, int W, int Co, int pad, void* stream);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* small fused kernels                                                                              */
+
+/* FullyConnectedLayer.forward (NET:89-101): y[n,o] = act(sum_i x[n,i] * w[o,i] * weight_gain + b[o] *
+ * bias_gain) * act_gain.  x row stride ldx (elements) lets the caller feed a concatenation view. */
+int afcm_fully_connected(const float* x, int64_t ldx, const float* w, const float* b, float* y, int64_t ldy,
+                         int N, int in_features, int out_features,
+                         float weight_gain, float bias_gain, int act, float alpha, float act_gain,
+                         void* stream);
+
+/* normalize_2nd_moment of MappingNetwork (NET:142,146): y = x * rsqrt(mean(x^2, dim=1) + eps). */
+int afcm_normalize_2nd_moment(const float* x, int64_t ldx, float* y, int64_t ldy, int N, int F, float eps,
+                              void* stream);
+
+/* AdaptiveAvgPool2d((oh,ow)) on [planes,H,W] (NET:636,683). */
+int afcm_adaptive_avgpool(const float* x, float* y, int64_t planes, int H, int W, int oh, int ow, void* stream);
+
+/* F.pad(img, margin) of NET:669, optionally fused with the uint8 -> [-1,1] input normalisation
+ * (data/augment/transforms.py:604-616): when lut_host != NULL, x is uint8 and lut_host[256] holds the
+ * float32 value of every code (computed on the host in float64 exactly like the reference transform). */
+int afcm_pad_input(const void* x, float* y, const float* lut_host, int64_t planes, int H, int W, int margin,
+                   void* stream);
+
+/* SynthesisInput Fourier features (NET:198-243), API parity only (AFCM never instantiates it).
+ * t [N,4] = affine(w); freqs [C,2]; phases [C]; weight [C,C]; y [N,C,size,size]. */
+int afcm_fourier_features(const float* t, const float* freqs, const float* phases, const float* weight,
+                          const float* transform3x3, float* y, int N, int C, int size_h, int size_w,
+                          float sampling_rate, float bandwidth, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AFCM_B200_H */

@@ -1,0 +1,229 @@
+"""GPU parity tests (run on the B200 box with -m gpu): every operator goes through the C-ABI library
+and is compared with (a) golden vectors produced by the reference's `_ref` path and (b) the CPU oracle
+on fresh seeded inputs.  Tolerance: max|a-b| / max|b|, 1e-4 for the fp32 path as
+the north star states (measured errors are ~1e-6)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import afcm_oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4          # north-star bound for the fp32 path
+TIGHT = 1e-5        # what we actually expect
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available()
+    from afcm_b200 import _lib
+    assert _lib.lib().afcm_device_check() == 0, _lib.last_error()
+    return torch.device('cuda:0')
+
+
+def _t(a, dev):
+    return None if a is None else torch.as_tensor(np.asarray(a), device=dev)
+
+
+def _flr_cases(g):
+    for name in g['flrelu.names']:
+        k = 'flrelu.' + str(name)
+        c = g[k + '.cfg']
+        fu, fd = g[k + '.fu'], g[k + '.fd']
+        yield (str(name), k, int(c[0]), int(c[1]), [int(v) for v in c[2:6]], float(c[6]), float(c[7]),
+               (None if c[8] < 0 else float(c[8])), (fu if fu.size else None), (fd if fd.size else None))
+
+
+def test_filtered_lrelu_golden(dev, golden_ops):
+    from afcm_b200.torch_utils.ops import filtered_lrelu
+    g = golden_ops
+    for name, k, up, dn, pad, gain, slope, clamp, fu, fd in _flr_cases(g):
+        x, b = _t(g[k + '.x'], dev), _t(g[k + '.b'], dev)
+        y = filtered_lrelu.filtered_lrelu(x, _t(fu, dev), _t(fd, dev), b, up, dn, pad, gain, slope, clamp)
+        assert rel_err(y.cpu().numpy(), g[k + '.y']) < TIGHT, name
+        yf = filtered_lrelu.filtered_lrelu(x, _t(fu, dev), _t(fd, dev), b, up, dn, pad, gain, slope, clamp, flip_filter=True)
+        assert rel_err(yf.cpu().numpy(), g[k + '.yflip']) < TIGHT, name
+
+
+def test_filtered_lrelu_backward_golden(dev, golden_ops):
+    from afcm_b200.torch_utils.ops import filtered_lrelu
+    g = golden_ops
+    for name, k, up, dn, pad, gain, slope, clamp, fu, fd in _flr_cases(g):
+        x = _t(g[k + '.x'], dev).requires_grad_(True)
+        b = _t(g[k + '.b'], dev).requires_grad_(True)
+        y = filtered_lrelu.filtered_lrelu(x, _t(fu, dev), _t(fd, dev), b, up, dn, pad, gain, slope, clamp)
+        (y * _t(g[k + '.r'], dev)).sum().backward()
+        assert rel_err(y.detach().cpu().numpy(), g[k + '.y']) < TIGHT, name
+        assert rel_err(x.grad.cpu().numpy(), g[k + '.dx']) < 2e-5, name
+        assert rel_err(b.grad.cpu().numpy(), g[k + '.db']) < 1e-4, name
+
+
+def test_filtered_lrelu_signs_match_oracle(dev, golden_ops):
+    from afcm_b200.torch_utils.ops.filtered_lrelu import _run_fused
+    g = golden_ops
+    for name, k, up, dn, pad, gain, slope, clamp, fu, fd in _flr_cases(g):
+        if fu is None or fd is None:
+            continue
+        x, b = _t(g[k + '.x'], dev), _t(g[k + '.b'], dev)
+        cl = float('inf') if clamp is None else clamp
+        y, so, rc = _run_fused(x, _t(fu, dev), _t(fd, dev), b, None, up, dn, *pad, 0, 0, gain, slope, cl, False, True)
+        assert rc == 0
+        yo, so_o, pre = orc.filtered_lrelu(g[k + '.x'], fu, fd, g[k + '.b'], up, dn, pad, gain, slope, clamp,
+                                           write_signs=True, return_preact=True)
+        sz = orc.filtered_lrelu_sizes(x.shape[2], x.shape[3], up, dn, len(fu), len(fd), pad)
+        sw = sz['OW'] * dn - (dn - 1) + len(fd) - 1
+        unpack = lambda s: np.stack([(s >> (2 * j)) & 3 for j in range(4)], -1).reshape(*s.shape[:3], -1)[..., :sw]
+        a, bb = unpack(so.cpu().numpy()), unpack(so_o)
+        pre = pre[:, :, :sz['SH'], :sw]
+        act = np.where(pre < 0, pre * slope, pre)
+        safe = ((np.abs(pre) > 1e-5) | (pre == 0)) & ((np.abs(np.abs(act) - cl) > 1e-4 * max(cl, 1)) if np.isfinite(cl) else True)
+        assert (a[safe] == bb[safe]).all(), name
+
+
+@pytest.mark.parametrize('geom', ['u2d2', 'u2d4', 'u4d2'])
+def test_filtered_lrelu_random_vs_oracle(dev, golden_ops, geom):
+    """Fresh seeded inputs at AFCM plane sizes (ragged tiles, several tile shapes, strided input)."""
+    from afcm_b200.torch_utils.ops import filtered_lrelu
+    from afcm_b200 import _lib
+    g = golden_ops
+    k = 'flrelu.' + geom
+    c = g[k + '.cfg']
+    up, dn, pad = int(c[0]), int(c[1]), [int(v) for v in c[2:6]]
+    fu, fd = g[k + '.fu'], g[k + '.fd']
+    rng = np.random.default_rng(3)
+    size = {'u2d2': 86, 'u2d4': 150, 'u4d2': 54}[geom]
+    x = rng.standard_normal((2, 3, size, size)).astype(np.float32) * 2
+    b = rng.standard_normal(3).astype(np.float32)
+    yo = orc.filtered_lrelu(x, fu, fd, b, up, dn, pad, np.sqrt(2), 0.2, 1.0)
+    try:
+        for tile in [(0, 0), (16, 8), (40, 24), (64, 32)]:
+            _lib.lib().afcm_filtered_lrelu_set_tile(*tile)
+            y = filtered_lrelu.filtered_lrelu(_t(x, dev), _t(fu, dev), _t(fd, dev), _t(b, dev), up, dn, pad, np.sqrt(2), 0.2, 1.0)
+            assert rel_err(y.cpu().numpy(), yo) < TIGHT, (geom, tile)
+    finally:
+        _lib.lib().afcm_filtered_lrelu_set_tile(0, 0)
+    # non-contiguous input (strides are honoured like in the reference, filtered_lrelu.cpp:127-134)
+    xt = _t(np.ascontiguousarray(x.transpose(0, 1, 3, 2)), dev).transpose(2, 3)
+    y = filtered_lrelu.filtered_lrelu(xt, _t(fu, dev), _t(fd, dev), _t(b, dev), up, dn, pad, np.sqrt(2), 0.2, 1.0)
+    assert rel_err(y.cpu().numpy(), yo) < TIGHT
+    # fp16 storage, fp32 math
+    yh = filtered_lrelu.filtered_lrelu(_t(x, dev).half(), _t(fu, dev), _t(fd, dev), _t(b, dev).half(), up, dn, pad, np.sqrt(2), 0.2, 1.0)
+    assert yh.dtype == torch.float16 and rel_err(yh.float().cpu().numpy(), yo) < 5e-3
+
+
+def test_upfirdn2d_golden(dev, golden_ops):
+    from afcm_b200.torch_utils.ops import upfirdn2d
+    g = golden_ops
+    for name in g['upfirdn.names']:
+        k = 'upfirdn.' + str(name)
+        c = g[k + '.cfg']
+        f = g[k + '.f']; f = _t(f, dev) if f.size else None
+        x = _t(g[k + '.x'], dev).requires_grad_(True)
+        y = upfirdn2d.upfirdn2d(x, f, up=[int(c[0]), int(c[1])], down=[int(c[2]), int(c[3])],
+                                padding=[int(v) for v in c[4:8]], flip_filter=bool(c[8]), gain=float(c[9]))
+        assert rel_err(y.detach().cpu().numpy(), g[k + '.y']) < TIGHT, name
+        # adjointness of the backward op: <upfirdn(x), r> == <x, upfirdn^T(r)>
+        r = torch.randn_like(y)
+        (y * r).sum().backward()
+        x2 = torch.randn_like(x)
+        y2 = upfirdn2d.upfirdn2d(x2, f, up=[int(c[0]), int(c[1])], down=[int(c[2]), int(c[3])],
+                                 padding=[int(v) for v in c[4:8]], flip_filter=bool(c[8]), gain=float(c[9]))
+        lhs, rhs = float((y2 * r).sum()), float((x2 * x.grad).sum())
+        assert abs(lhs - rhs) < 1e-3 * max(1.0, abs(lhs)), name
+
+
+def test_upfirdn2d_wrappers(dev):
+    from afcm_b200.torch_utils.ops import upfirdn2d
+    x = torch.randn(2, 3, 16, 20, device=dev)
+    f = upfirdn2d.setup_filter([1, 3, 3, 1], device=dev)
+    assert upfirdn2d.filter2d(x, f).shape == x.shape
+    assert upfirdn2d.upsample2d(x, f).shape == (2, 3, 32, 40)
+    assert upfirdn2d.downsample2d(x, f).shape == (2, 3, 8, 10)
+    xo = orc.upfirdn2d(x.cpu().numpy(), f.cpu().numpy(), up=2, padding=[2, 1, 2, 1], gain=4)
+    assert rel_err(upfirdn2d.upsample2d(x, f).cpu().numpy(), xo) < TIGHT
+
+
+@pytest.mark.parametrize('act', list(orc.ACT_IDX))
+def test_bias_act_golden(dev, golden_ops, act):
+    from afcm_b200.torch_utils.ops import bias_act
+    g = golden_ops
+    for tag, clamp in (('n', None), ('c', 0.7)):
+        x = _t(g['bias_act.x'], dev).requires_grad_(True)
+        y = bias_act.bias_act(x, _t(g['bias_act.b'], dev), act=act, clamp=clamp)
+        assert rel_err(y.detach().cpu().numpy(), g[f'bias_act.{act}.{tag}.y']) < TIGHT, (act, tag)
+        y.backward(torch.full_like(y, 0.5))
+        assert rel_err(x.grad.cpu().numpy(), g[f'bias_act.{act}.{tag}.dx']) < 5e-5, (act, tag)
+    y2 = bias_act.bias_act(_t(g['bias_act.x2'], dev), _t(g['bias_act.b2'], dev), act='lrelu')
+    assert rel_err(y2.cpu().numpy(), g['bias_act.y2']) < TIGHT
+
+
+def test_bias_act_second_order(dev):
+    """d/dx of the first-order gradient against torch autograd on the same formula."""
+    from afcm_b200.torch_utils.ops import bias_act
+    x = torch.randn(4, 6, 5, device=dev, dtype=torch.float32).requires_grad_(True)
+    b = torch.randn(6, device=dev).requires_grad_(True)
+    for act, fn in (('tanh', torch.tanh), ('sigmoid', torch.sigmoid), ('softplus', torch.nn.functional.softplus)):
+        y = bias_act.bias_act(x, b, act=act)
+        gx, = torch.autograd.grad(y.sum(), x, create_graph=True)
+        ggx, = torch.autograd.grad((gx * gx).sum(), x)
+        xr = x.detach().clone().requires_grad_(True)
+        yr = fn(xr + b.detach().reshape(1, -1, 1))
+        gr, = torch.autograd.grad(yr.sum(), xr, create_graph=True)
+        ggr, = torch.autograd.grad((gr * gr).sum(), xr)
+        assert rel_err(ggx.cpu().numpy(), ggr.cpu().numpy()) < 1e-4, act
+
+
+def test_modulated_conv2d_golden_fp32(dev, golden_ops):
+    from afcm_b200.networks_stylegan3 import modulated_conv2d
+    g = golden_ops
+    for name in ('demod3', 'torgb1', 'demod3b'):
+        t = 'modconv.' + name
+        demod, pad, ig = int(g[t + '.cfg'][0]), int(g[t + '.cfg'][1]), float(g[t + '.cfg'][2])
+        y = modulated_conv2d(_t(g[t + '.x'], dev), _t(g[t + '.w'], dev), _t(g[t + '.s'], dev), bool(demod), pad,
+                             torch.tensor(ig, device=dev), impl='f32')
+        assert rel_err(y.cpu().numpy(), g[t + '.y']) < TIGHT, name
+
+
+@pytest.mark.parametrize('shape', [(2, 5, 7, 9, 11, 3, 2), (1, 64, 91, 38, 38, 3, 2), (3, 17, 70, 20, 33, 3, 1),
+                                   (2, 64, 1, 24, 24, 1, 0), (1, 130, 66, 17, 16, 3, 2)])
+def test_conv2d_f32_vs_oracle(dev, shape):
+    from afcm_b200.torch_utils.ops import conv2d_gradfix
+    N, Ci, Co, H, W, k, pad = shape
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((N, Ci, H, W)).astype(np.float32)
+    w = rng.standard_normal((Co, Ci, k, k)).astype(np.float32)
+    y = conv2d_gradfix.conv2d_native(_t(x, dev), _t(w, dev), pad, impl='f32')
+    yo = torch.nn.functional.conv2d(torch.as_tensor(x), torch.as_tensor(w), padding=pad).numpy()
+    assert rel_err(y.cpu().numpy(), yo) < TIGHT
+
+
+def test_fully_connected_mapping_fourier(dev, golden_ops):
+    from afcm_b200 import networks_stylegan3 as net
+    g = golden_ops
+    y = net._fc_native(_t(g['fc.x'], dev), _t(g['fc.w'], dev), _t(g['fc.b'], dev), 0.01 / np.sqrt(37), 0.01, 'lrelu')
+    assert rel_err(y.cpu().numpy(), g['fc.y']) < TIGHT
+    y = net._fc_native(_t(g['fc.x'], dev), _t(g['fc2.w'], dev), _t(g['fc2.b'], dev), 1 / np.sqrt(37), 1.0, 'linear')
+    assert rel_err(y.cpu().numpy(), g['fc2.y']) < TIGHT
+    mp = net.MappingNetwork(z_dim=48, c_dim=1, w_dim=40, num_ws=6, num_layers=3)
+    mp.load_state_dict({k[len('map.P.'):]: torch.as_tensor(g[k]) for k in g.files if k.startswith('map.P.')})
+    ws = mp.to(dev)(_t(g['map.z'], dev), _t(g['map.c'], dev))
+    assert rel_err(ws.cpu().numpy(), g['map.ws']) < TIGHT
+    si = net.SynthesisInput(w_dim=40, channels=12, size=20, sampling_rate=16, bandwidth=2)
+    si.load_state_dict({k[len('synin.P.'):]: torch.as_tensor(g[k]) for k in g.files if k.startswith('synin.P.')})
+    y = si.to(dev)(_t(g['synin.w'], dev))
+    assert rel_err(y.cpu().numpy(), g['synin.y']) < 5e-5
+
+
+def test_pool_and_pad(dev):
+    from afcm_b200 import _lib
+    x = torch.randn(3, 5, 36, 36, device=dev)
+    y = torch.empty(3, 5, 4, 4, device=dev)
+    _lib.check(_lib.lib().afcm_adaptive_avgpool(_lib.ptr(x), _lib.ptr(y), 15, 36, 36, 4, 4, _lib.stream_ptr(dev)))
+    assert rel_err(y.cpu().numpy(), torch.nn.functional.adaptive_avg_pool2d(x, (4, 4)).cpu().numpy()) < TIGHT
+    u8 = torch.randint(0, 256, (2, 4, 16, 16), dtype=torch.uint8, device=dev)
+    lut = np.clip(2 * ((np.arange(256, dtype=np.float64) - 0) / 255) - 1, -1, 1).astype(np.float32)
+    out = torch.empty(2, 4, 36, 36, device=dev)
+    _lib.check(_lib.lib().afcm_pad_input(_lib.ptr(u8), _lib.ptr(out), _lib.np_ptr(lut), 8, 16, 16, 10, _lib.stream_ptr(dev)))
+    ref = torch.nn.functional.pad(torch.as_tensor(lut)[u8.cpu().long()], [10] * 4)
+    assert torch.equal(out.cpu(), ref)

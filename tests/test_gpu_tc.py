@@ -1,0 +1,94 @@
+"""tcgen05 / TMEM implicit-GEMM convolution: parity against the exact-fp32 kernel and the reference
+golden vectors within the stated 16-bit tolerance (operands rounded to fp16/bf16, fp32 accumulation)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+# operands carry 11 (fp16) / 8 (bf16) significant bits; K up to 4608 products accumulate in fp32
+TC_TOL = {torch.float16: 2e-3, torch.bfloat16: 1.5e-2}
+
+
+@pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize('shape', [
+    # N, Ci, Co, H, W, pad
+    (1, 64, 64, 14, 14, 2),        # single k-block per tap, single tile
+    (2, 128, 96, 36, 36, 2),       # AFCM 36x36 plane, two channel blocks
+    (1, 4, 64, 52, 52, 2),         # enc0-like: Ci << 64 (TMA zero-fills the channel tail)
+    (2, 91, 181, 30, 22, 2),       # odd channel counts on both sides, rectangular plane
+    (1, 362, 512, 38, 38, 2),      # Co tiled as 2 x 256, Ci tail
+    (2, 512, 362, 20, 20, 2),      # Co tiled as 2 x 192
+    (2, 96, 80, 36, 36, 1),        # pad 1 (e_16x16): garbage columns are skipped on store
+    (3, 48, 45, 52, 52, 2),        # tiny-generator shapes
+])
+def test_conv2d_tc_matches_fp32(shape, dtype):
+    from afcm_b200.torch_utils.ops import conv2d_gradfix
+    N, Ci, Co, H, W, pad = shape
+    dev = torch.device('cuda:0')
+    g = torch.Generator(device='cpu').manual_seed(17)
+    x = torch.randn(N, Ci, H, W, generator=g).to(dev)
+    w = torch.randn(Co, Ci, 3, 3, generator=g).to(dev)
+    icoef = (torch.rand(N, Ci, generator=g) + 0.5).to(dev)
+    ocoef = (torch.rand(N, Co, generator=g) + 0.5).to(dev)
+    scale = 1.0 / np.sqrt(Ci * 9)
+    conv2d_gradfix.set_conv_impl('f32', dtype)
+    ref = conv2d_gradfix.conv2d_native(x, w, pad, icoef=icoef, ocoef=ocoef, pre_scale=scale, impl='f32')
+    got = conv2d_gradfix.conv2d_native(x, w, pad, icoef=icoef, ocoef=ocoef, pre_scale=scale, impl='tc')
+    torch.cuda.synchronize()
+    assert got.shape == ref.shape
+    assert torch.isfinite(got).all()
+    assert rel_err(got.cpu().numpy(), ref.cpu().numpy()) < TC_TOL[dtype]
+    conv2d_gradfix.set_conv_impl('f32', torch.float16)
+
+
+def test_conv2d_tc_exact_on_representable_inputs():
+    """With inputs exactly representable in fp16 and small integer products the tensor-core result must
+    be bit-identical to the fp32 kernel: proves descriptor / layout correctness, not just 'close'."""
+    from afcm_b200.torch_utils.ops import conv2d_gradfix
+    dev = torch.device('cuda:0')
+    g = torch.Generator(device='cpu').manual_seed(3)
+    N, Ci, Co, H, W = 2, 192, 160, 36, 36
+    x = torch.randint(-4, 5, (N, Ci, H, W), generator=g).float().to(dev)
+    w = torch.randint(-2, 3, (Co, Ci, 3, 3), generator=g).float().to(dev)
+    ref = conv2d_gradfix.conv2d_native(x, w, 2, impl='f32')
+    got = conv2d_gradfix.conv2d_native(x, w, 2, impl='tc')
+    assert torch.equal(ref, got)
+
+
+def test_modulated_conv2d_golden_tc(golden_ops):
+    from afcm_b200.networks_stylegan3 import modulated_conv2d
+    dev = torch.device('cuda:0')
+    g = golden_ops
+    for name in ('demod3', 'demod3b'):
+        t = 'modconv.' + name
+        demod, pad, ig = int(g[t + '.cfg'][0]), int(g[t + '.cfg'][1]), float(g[t + '.cfg'][2])
+        y = modulated_conv2d(torch.as_tensor(g[t + '.x'], device=dev), torch.as_tensor(g[t + '.w'], device=dev),
+                             torch.as_tensor(g[t + '.s'], device=dev), bool(demod), pad, torch.tensor(ig, device=dev), impl='tc')
+        assert rel_err(y.cpu().numpy(), g[t + '.y']) < 2e-3, name
+
+
+def test_full_generator_tc(golden_full):
+    """Whole generator on the tensor-core path vs the reference fp32 output: stated tolerance
+    PSNR >= 50 dB (peak = max|y_ref|) and max-abs error <= 1% of max|y_ref| with fp16 operands."""
+    from afcm_b200.networks_stylegan3 import afcm_generator
+    from afcm_b200.torch_utils.ops import conv2d_gradfix
+    dev = torch.device('cuda:0')
+    g = golden_full
+    G = afcm_generator(seed=0, device=dev)
+    x = (torch.as_tensor(g['x_u8']).float() * (2.0 / 255.0) - 1.0).clamp(-1, 1).to(dev)
+    conv2d_gradfix.set_conv_impl('tc', torch.float16)
+    try:
+        with torch.no_grad():
+            y = G(torch.as_tensor(g['z'], device=dev), torch.as_tensor(g['c'], device=dev), x, noise_mode='const')
+    finally:
+        conv2d_gradfix.set_conv_impl('f32', torch.float16)
+    ref = g['y']
+    err = y.cpu().numpy() - ref
+    peak = np.abs(ref).max()
+    psnr = 10 * np.log10(peak ** 2 / np.mean(err ** 2))
+    print(f'tc fp16: psnr {psnr:.1f} dB, max-abs/peak {np.abs(err).max() / peak:.2e}')
+    assert psnr >= 50.0
+    assert np.abs(err).max() / peak <= 1e-2

@@ -1,0 +1,118 @@
+"""Per-layer timing of the two heavy operators at the AFCM geometries -- a development
+tool, not the bench contract.  CUDA-event timing on the launching stream, L2 flushed between iterations.
+
+    python tools/layer_bench.py --batch 8 --ops flrelu,conv_tc,conv_f32
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from afcm_b200 import _lib  # noqa: E402
+from afcm_b200.networks_stylegan3 import afcm_generator  # noqa: E402
+from afcm_b200.torch_utils.ops import conv2d_gradfix  # noqa: E402
+from afcm_b200.torch_utils.ops.filtered_lrelu import _run_fused  # noqa: E402
+
+
+def time_cuda(fn, iters=5, warmup=2, flush=None):
+    for _ in range(warmup):
+        fn()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--batch', type=int, default=8)
+    ap.add_argument('--ops', default='flrelu,conv_tc')
+    ap.add_argument('--json', default='')
+    ap.add_argument('--tile', default='')
+    args = ap.parse_args()
+    ops = args.ops.split(',')
+    dev = torch.device('cuda:0')
+    peaks = {}
+    pk = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'MEASURED_PEAKS.json')
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    hbm = peaks.get('hbm_gbs', 6650.0); tf = peaks.get('bf16_tflops', 1590.0)
+    G = afcm_generator(seed=0, device=dev)
+    S = G.synthesis
+    layers = [('enc%d' % i, getattr(S, 'encoder_%d' % i)) for i in range(S.num_layers)] + \
+             [(n, getattr(S, n)) for n in S.layer_names]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    B = args.batch
+    if args.tile:
+        tw, th = [int(v) for v in args.tile.split('x')]
+        _lib.lib().afcm_filtered_lrelu_set_tile(tw, th)
+    rows = []
+    tot = dict(flrelu_ms=0.0, flrelu_bytes=0.0, conv_tc_ms=0.0, pack_ms=0.0, conv_f32_ms=0.0, flops=0.0)
+    for name, L in layers:
+        cin, cout = L.in_channels, L.out_channels
+        H = int(L.in_size[0]); k = L.conv_kernel; Hc = H + k - 1; out = int(L.out_size[0])
+        row = dict(layer=name, cin=cin, cout=cout, H=H, Hc=Hc, out=out, up=L.up_factor, down=L.down_factor)
+        if 'flrelu' in ops:
+            x = torch.randn(B, cout, Hc, Hc, device=dev)
+            b = torch.randn(cout, device=dev)
+            px0, px1, py0, py1 = L.padding
+            gain, slope = (1.0, 1.0) if getattr(L, 'is_torgb', False) else (float(np.sqrt(2)), 0.2)
+            fn = lambda: _run_fused(x, L.up_filter, L.down_filter, b, None, L.up_factor, L.down_factor, px0, px1, py0, py1,
+                                    0, 0, gain, slope, 256.0, False, False)
+            ms = time_cuda(fn, flush=flush)
+            nbytes = 4.0 * B * cout * (Hc * Hc + out * out)
+            row.update(flrelu_ms=ms, flrelu_gbs=nbytes / ms / 1e6, flrelu_frac=nbytes / ms / 1e6 / hbm)
+            tot['flrelu_ms'] += ms; tot['flrelu_bytes'] += nbytes
+            del x
+        flops = 2.0 * B * cout * cin * k * k * Hc * Hc
+        tot['flops'] += flops
+        if k == 3 and ('conv_tc' in ops or 'conv_f32' in ops):
+            x = torch.randn(B, cin, H, H, device=dev)
+            w = L.weight.detach()
+            if 'conv_tc' in ops:
+                Lb = _lib.lib()
+                ent = conv2d_gradfix.prepare_weight(w, 1.0, False, want_tc=True)
+                plane = int(Lb.afcm_conv_tc_plane_elems(H, H))
+                xp = torch.empty(B, cin, plane, dtype=torch.float16, device=dev)
+                y = torch.empty(B, cout, Hc, Hc, device=dev)
+                st = _lib.stream_ptr(dev)
+                pack = lambda: _lib.check(Lb.afcm_conv_tc_pack(_lib.ptr(x), None, _lib.ptr(xp), 1, B, cin, H, H, st))
+                gemm = lambda: _lib.check(Lb.afcm_conv2d_tc(_lib.ptr(xp), _lib.ptr(ent[('w_tc', torch.float16)]), None,
+                                                            _lib.ptr(y), 1, B, cin, H, H, cout, 2, st))
+                pms = time_cuda(pack, flush=flush); gms = time_cuda(gemm, flush=flush)
+                row.update(pack_ms=pms, conv_tc_ms=gms, conv_tc_tflops=flops / gms / 1e9, conv_tc_frac=flops / gms / 1e9 / tf)
+                tot['conv_tc_ms'] += gms; tot['pack_ms'] += pms
+                del xp, y
+            if 'conv_f32' in ops:
+                fms = time_cuda(lambda: conv2d_gradfix.conv2d_native(x, w, 2, impl='f32'), iters=2, warmup=1)
+                row.update(conv_f32_ms=fms, conv_f32_tflops=flops / fms / 1e9)
+                tot['conv_f32_ms'] += fms
+            del x
+        rows.append(row)
+        print(json.dumps(row))
+    summ = dict(batch=B, **tot)
+    if tot['flrelu_ms']:
+        summ['flrelu_gbs'] = tot['flrelu_bytes'] / tot['flrelu_ms'] / 1e6
+        summ['flrelu_frac_of_measured_hbm'] = summ['flrelu_gbs'] / hbm
+        summ['flrelu_ms_per_slice'] = tot['flrelu_ms'] / B
+    if tot['conv_tc_ms']:
+        summ['conv_tc_tflops'] = tot['flops'] / tot['conv_tc_ms'] / 1e9
+        summ['conv_tc_frac_of_measured_bf16'] = summ['conv_tc_tflops'] / tf
+        summ['conv_tc_ms_per_slice'] = tot['conv_tc_ms'] / B
+    print('SUMMARY', json.dumps(summ))
+    if args.json:
+        json.dump(dict(rows=rows, summary=summ), open(args.json, 'w'), indent=1)
+
+
+if __name__ == '__main__':
+    main()
