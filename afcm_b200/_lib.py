@@ -44,9 +44,10 @@ SIGNATURES = {
     'afcm_conv2d_f32': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'afcm_conv_weight_prep': (_i, [_vp, _i, _i, _i, _f, _i, _vp, _vp, _i, _vp, _vp]),
     'afcm_modconv_coefs': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
-    'afcm_conv_tc_plane_elems': (_i64, [_i, _i]),
+    'afcm_conv_tc_plane_elems': (_i64, [_i, _i, _i]),
     'afcm_conv_tc_pack': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'afcm_conv2d_tc': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    'afcm_conv_tc_debug_buffer': (_vp, [_i]),
     'afcm_fully_connected': (_i, [_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _f, _f, _i, _f, _f, _vp]),
     'afcm_normalize_2nd_moment': (_i, [_vp, _i64, _vp, _i64, _i, _i, _f, _vp]),
     'afcm_adaptive_avgpool': (_i, [_vp, _vp, _i64, _i, _i, _i, _i, _vp]),
@@ -116,17 +117,23 @@ _host_cache = {}
 
 
 def host_array(t, dtype=np.float32):
-    """Host copy of a small constant tensor (filter taps), cached by storage pointer + version so that
-    the device->host sync happens once per filter, not per call."""
+    """Host copy of a small constant tensor (filter taps), cached per tensor OBJECT (weak reference +
+    version counter) so that the device->host sync happens once per filter, not per call.  Keying on the
+    storage address alone would be wrong: the caching allocator hands freed addresses to new tensors."""
+    import weakref
     if t is None:
         return None
-    key = (t.data_ptr(), t._version, tuple(t.shape), str(t.device))
-    a = _host_cache.get(key)
-    if a is None:
-        a = np.ascontiguousarray(t.detach().to('cpu', copy=True).numpy().astype(dtype, copy=False))
-        if len(_host_cache) > 4096:
+    key = id(t)
+    ent = _host_cache.get(key)
+    if ent is not None and ent[0]() is t and ent[1] == t._version:
+        return ent[2]
+    a = np.ascontiguousarray(t.detach().to('cpu', copy=True).numpy().astype(dtype, copy=False))
+    if len(_host_cache) > 1024:
+        for k in [k for k, v in _host_cache.items() if v[0]() is None]:
+            del _host_cache[k]
+        if len(_host_cache) > 1024:
             _host_cache.clear()
-        _host_cache[key] = a
+    _host_cache[key] = (weakref.ref(t), t._version, a)
     return a
 
 

@@ -5,14 +5,17 @@
 // and the plain encoder convolution (networks_stylegan3.py:503-505).
 //
 // Formulation (see DESIGN.md "modulated_conv2d"):
-//   * activations are pre-scaled by the modulation coefficient and packed to 16 bit in a "flat
-//     plane" layout  xp[n][ci][y*(W+2) + x]  with two zero columns at the end of every row.  A 3x3 tap
-//     (ky,kx) is then a pure shift of the flat pixel index by (ky-pad)*(W+2) + (kx-pad): horizontal
-//     taps wrap onto the zero columns, vertical taps run off the plane where TMA zero-fills.
+//   * activations are pre-scaled by the modulation coefficient and packed to 16 bit in a channel-
+//     innermost "flat plane" layout  xp[n][y*(W+2) + x][ci]  (ci padded to a multiple of 8) with two
+//     zero pixels at the end of every row.  A 3x3 tap (ky,kx) is then a pure shift of the flat pixel
+//     index by (ky-pad)*(W+2) + (kx-pad): horizontal taps wrap onto the zero pixels, vertical taps run
+//     off the plane where TMA zero-fills.  The shift sits on an OUTER tensor-map dimension because TMA
+//     requires the innermost start to be 16-byte aligned (measured: an unaligned pixel-innermost box
+//     raises an illegal-instruction fault).
 //   * GEMM:  D[p, o] = sum_{tap} sum_{ci} A_tap[p, ci] * B_tap[o, ci]
 //       M = 128 consecutive flat output pixels p of one sample (all of them valid outputs for pad=2)
 //       N = BN <= 256 output channels,  K = 9 taps x Ci (64 channels per pipeline stage)
-//       A_tap tile : two TMA boxes [64 ch][64 px]  -> MN-major (pixel-contiguous) SWIZZLE_128B operand
+//       A_tap tile : one TMA box   [128 px][64 ci] -> K-major SWIZZLE_128B operand
 //       B_tap tile : one TMA box   [BN o][64 ci]   -> K-major SWIZZLE_128B operand
 //       D          : fp32 accumulator in tensor memory, 2 stages x 256 columns (epilogue of tile i
 //                    overlaps the main loop of tile i+1)
@@ -31,7 +34,7 @@ constexpr int TC_STAGES = 4;
 constexpr int TC_THREADS = 256;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;          // 16 KB
 constexpr int TC_TMEM_COLS = 512;
-constexpr unsigned TC_SPIN_LIMIT = 1u << 27;           // watchdog: trap instead of hanging the GPU
+constexpr long long TC_WATCHDOG_CYCLES = 4000000000LL; // ~2 s: trap instead of hanging the GPU
 
 struct TcParams {
     const float* ocoef;     // [N, Co] or null
@@ -40,6 +43,8 @@ struct TcParams {
     int BN, n_tiles, m_tiles, cblocks;     // channel tile, #channel tiles, #pixel tiles per sample, ceil(Ci/64)
     int total_tiles;
     unsigned idesc;
+    unsigned* dbg;          // mapped host memory for progress markers (AFCM_TC_DEBUG), or null
+    int dbg_mode;           // debug bisection switches (see afcm_conv_tc_debug_buffer)
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------
@@ -57,18 +62,30 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned* dbg = nullptr, unsigned code = 0)
 {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
+    long long t0 = 0;
     for (unsigned spin = 0; !done; spin++) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-        if (spin > TC_SPIN_LIMIT) __trap();
+        if (!done && (spin & 1023) == 1023) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > TC_WATCHDOG_CYCLES) {
+                if (dbg) { dbg[48 + (code >> 8)] = code | 0x80000000u; __threadfence_system(); }
+                __trap();
+            }
+        }
     }
+}
+__device__ __forceinline__ void dbg_mark(unsigned* dbg, int slot, unsigned v)
+{
+    if (dbg) { dbg[slot] = v; __threadfence_system(); }
 }
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2)
 {
@@ -154,6 +171,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { dbg_mark(p.dbg, 5, tmem_base); dbg_mark(p.dbg, 6, 0xC0DE0001u); }
 
     const int kblocks = 9 * p.cblocks;
 
@@ -166,50 +184,65 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 const int r = tile / p.n_tiles;
                 const int mt = r % p.m_tiles, n = r / p.m_tiles;
                 const int p0 = mt * TC_BM, o0 = nt * p.BN;
-                for (int kb = 0; kb < kblocks; kb++) {
+                for (int kb = 0; kb < ((p.dbg_mode & 8) ? min(kblocks, TC_STAGES) : kblocks); kb++) {
                     const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
                     const int ky = tap / 3, kx = tap - ky * 3;
                     const int shift = (ky - p.pad) * p.Wp + (kx - p.pad);
-                    mbar_wait(&empty[stage], phase ^ 1);
+                    dbg_mark(p.dbg, 10, (unsigned)kb + 1);
+                    mbar_wait(&empty[stage], phase ^ 1, p.dbg, 0x100u | (unsigned)stage);
+                    dbg_mark(p.dbg, 11, (unsigned)kb + 1);
                     uint8_t* sa = smem + stage * stage_bytes;
-                    mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
-                    tma_load_3d(sa, &map_a, &full[stage], p0 + shift, cb * TC_BK, n);
-                    tma_load_3d(sa + TC_A_BYTES / 2, &map_a, &full[stage], p0 + shift + 64, cb * TC_BK, n);
-                    tma_load_3d(sa + TC_A_BYTES, &map_b, &full[stage], cb * TC_BK, o0, tap);
+                    uint32_t bytes = (uint32_t)stage_bytes;
+                    if (p.dbg_mode & 1) bytes -= TC_A_BYTES;
+                    if (p.dbg_mode & 2) bytes -= (uint32_t)b_bytes;
+                    const int pa = (p.dbg_mode & 4) ? p0 : p0 + shift;
+                    mbar_expect_tx(&full[stage], bytes);
+                    dbg_mark(p.dbg, 12, (unsigned)kb + 1);
+                    if (!(p.dbg_mode & 1)) {
+                        tma_load_3d(sa, &map_a, &full[stage], cb * TC_BK, pa, n);
+                        dbg_mark(p.dbg, 13, (unsigned)kb + 1);
+                    }
+                    if (!(p.dbg_mode & 2)) {
+                        tma_load_3d(sa + TC_A_BYTES, &map_b, &full[stage], cb * TC_BK, o0, tap);
+                        dbg_mark(p.dbg, 15, (unsigned)kb + 1);
+                    }
+                    if (blockIdx.x == 0) dbg_mark(p.dbg, 0, (unsigned)(kb + 1) | ((unsigned)tile << 16));
                     if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        if (lane == 0 && !(p.dbg_mode & 8)) {
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                mbar_wait(&tempty[acc], acc_phase ^ 1, p.dbg, 0x200u | (unsigned)acc);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256);
                 for (int kb = 0; kb < kblocks; kb++) {
-                    mbar_wait(&full[stage], phase);
+                    mbar_wait(&full[stage], phase, p.dbg, 0x300u | (unsigned)stage);
                     tc_fence_after();
+                    if (blockIdx.x == 0) dbg_mark(p.dbg, 1, (unsigned)(kb + 1) | ((unsigned)tile << 16));
                     const uint32_t sa = smem_u32(smem + stage * stage_bytes);
                     const uint32_t sb = sa + TC_A_BYTES;
 #pragma unroll
                     for (int k = 0; k < TC_BK / 16; k++) {
-                        // A: MN-major, 16 channels = two 8-row groups of 128 B rows (SBO 1024), two 64-pixel chunks (LBO 8192)
-                        const uint64_t adesc = make_desc(sa + k * 2048, TC_A_BYTES / 2, 1024);
-                        // B: K-major, 16 channels = 32 bytes inside the 128 B swizzled row, 8-row groups 1024 B apart
+                        // A and B are both K-major SWIZZLE_128B tiles of 128-byte rows: one UMMA_K step of 16
+                        // channels = 32 bytes inside the swizzled row, 8-row groups 1024 B apart (SBO)
+                        const uint64_t adesc = make_desc(sa + k * 32, 16, 1024);
                         const uint64_t bdesc = make_desc(sb + k * 32, 16, 1024);
                         umma_f16(tmem_d, adesc, bdesc, p.idesc, (kb | k) != 0);
                     }
                     umma_commit(&empty[stage]);
                     if (kb == kblocks - 1) umma_commit(&tfull[acc]);
+                    if (blockIdx.x == 0) dbg_mark(p.dbg, 2, (unsigned)(kb + 1) | ((unsigned)tile << 16));
                     if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && !(p.dbg_mode & 8)) {
         // ================= epilogue =================
         const int wq = warp & 3;
         const int et = threadIdx.x - 128;
@@ -224,8 +257,9 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 const int o = o0 + j;
                 s_ocoef[acc * 256 + j] = (o < p.Co) ? (p.ocoef ? p.ocoef[(long long)n * p.Co + o] : 1.f) : 0.f;
             }
-            mbar_wait(&tfull[acc], acc_phase);
+            mbar_wait(&tfull[acc], acc_phase, p.dbg, 0x400u | (unsigned)acc);
             tc_fence_after();
+            if (blockIdx.x == 0 && et == 0) dbg_mark(p.dbg, 3, (unsigned)tile + 1);
             asm volatile("bar.sync 1, 128;" ::: "memory");
             const int pix = mt * TC_BM + wq * 32 + lane;
             const int oy = pix / p.Wp, ox = pix - oy * p.Wp;
@@ -245,6 +279,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (blockIdx.x == 0 && et == 0) dbg_mark(p.dbg, 4, (unsigned)tile + 1);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -258,23 +293,44 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
 }
 
-// ---- activation packing -------------------------------------------------------------------------------
+// ---- activation packing: fp32 NCHW -> 16-bit [n][flat pixel][channel], modulation folded in ------------
+// One CTA transposes a tile of 64 flat pixels x 64 channels through shared memory: coalesced reads along
+// x, 16-byte coalesced writes along the channel axis.
 template <typename TC>
 __global__ void __launch_bounds__(256)
 tc_pack_kernel(const float* __restrict__ x, const float* __restrict__ icoef, TC* __restrict__ xp,
-               long long planes, int H, int W, int Wp, long long plane_pad)
+               int Ci, int c_pad, int H, int W, int Wp, int rows)
 {
-    const long long total = planes * plane_pad;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long pl = i / plane_pad;
-        const int idx = (int)(i - pl * plane_pad);
-        const int yy = idx / Wp, xx = idx - yy * Wp;
+    __shared__ float tile[64][65];
+    const int n = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
+    const int tid = threadIdx.x;
+    const int px = tid & 63, cq = tid >> 6;                 // read: 64 pixels x 4 channels per pass
+    const int p = p0 + px;
+    const int yy = p / Wp, xx = p - yy * Wp;
+    const bool pix_ok = p < rows && xx < W;
+#pragma unroll 4
+    for (int j = 0; j < 16; j++) {
+        const int c = c0 + cq * 16 + j;
         float v = 0.f;
-        if (yy < H && xx < W) {
-            v = x[(pl * H + yy) * W + xx];
-            if (icoef) v *= icoef[pl];
+        if (pix_ok && c < Ci) {
+            v = x[(((long long)n * Ci + c) * H + yy) * W + xx];
+            if (icoef) v *= icoef[n * Ci + c];
         }
-        xp[i] = (TC)v;
+        tile[cq * 16 + j][px] = v;
+    }
+    __syncthreads();
+    // write: thread -> (pixel, group of 8 channels) = one 16-byte store
+    const int g8 = tid & 7;
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const int pw = (tid >> 3) + 32 * j;
+        const int pp = p0 + pw, cc = c0 + g8 * 8;
+        if (pp < rows && cc < c_pad) {
+            alignas(16) TC v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = (TC)tile[g8 * 8 + k][pw];
+            *reinterpret_cast<uint4*>(xp + ((long long)n * rows + pp) * c_pad + cc) = *reinterpret_cast<const uint4*>(v);
+        }
     }
 }
 
@@ -312,13 +368,31 @@ static int encode_3d(CUtensorMap* map, int tc_dtype, const void* base, uint64_t 
     return AFCM_OK;
 }
 
+static unsigned* g_dbg_host = nullptr;
+static unsigned* g_dbg_dev = nullptr;
+static int g_dbg_mode = 0;
+
 }  // namespace afcm
 
 using namespace afcm;
 
-extern "C" int64_t afcm_conv_tc_plane_elems(int H, int W)
+// Debug aid (not part of the stable ABI): enables progress markers written by the tcgen05 kernel into
+// mapped host memory, readable even after a failed launch.  Returns the host pointer (64 words).
+extern "C" void* afcm_conv_tc_debug_buffer(int enable)
 {
-    return (((int64_t)H * (W + 2)) + 7) & ~(int64_t)7;
+    g_dbg_mode = enable >> 8;
+    if (!(enable & 1)) { g_dbg_dev = nullptr; return g_dbg_host; }
+    if (!g_dbg_host) {
+        if (cudaHostAlloc((void**)&g_dbg_host, 64 * sizeof(unsigned), cudaHostAllocMapped) != cudaSuccess) return nullptr;
+        memset(g_dbg_host, 0, 64 * sizeof(unsigned));
+    }
+    if (cudaHostGetDevicePointer((void**)&g_dbg_dev, g_dbg_host, 0) != cudaSuccess) { g_dbg_dev = nullptr; return nullptr; }
+    return g_dbg_host;
+}
+
+extern "C" int64_t afcm_conv_tc_plane_elems(int H, int W, int Ci)
+{
+    return (int64_t)H * (W + 2) * ((Ci + 7) & ~7);           // [H*(W+2) flat pixels][Ci padded to 8]
 }
 
 extern "C" int afcm_conv_tc_pack(const float* x, const float* icoef, void* xp, int tc_dtype,
@@ -326,13 +400,12 @@ extern "C" int afcm_conv_tc_pack(const float* x, const float* icoef, void* xp, i
 {
     AFCM_CHECK_ARG(x && xp && N > 0 && Ci > 0 && H > 0 && W > 0, "empty problem");
     AFCM_CHECK_ARG(tc_dtype == AFCM_F16 || tc_dtype == AFCM_BF16, "tc dtype must be F16 or BF16");
-    const long long planes = (long long)N * Ci, plane_pad = afcm_conv_tc_plane_elems(H, W);
-    long long blocks = (planes * plane_pad + 255) / 256;
-    const long long cap = (long long)sm_count() * 32;
-    if (blocks > cap) blocks = cap;
+    AFCM_CHECK_ARG(N <= 65535, "batch too large");
+    const int Wp = W + 2, rows = H * Wp, c_pad = (Ci + 7) & ~7;
+    dim3 grid(ceil_div(rows, 64), ceil_div(c_pad, 64), N);
     cudaStream_t st = (cudaStream_t)stream;
-    if (tc_dtype == AFCM_BF16) tc_pack_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(x, icoef, (__nv_bfloat16*)xp, planes, H, W, W + 2, plane_pad);
-    else tc_pack_kernel<__half><<<(unsigned)blocks, 256, 0, st>>>(x, icoef, (__half*)xp, planes, H, W, W + 2, plane_pad);
+    if (tc_dtype == AFCM_BF16) tc_pack_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, icoef, (__nv_bfloat16*)xp, Ci, c_pad, H, W, Wp, rows);
+    else tc_pack_kernel<__half><<<grid, 256, 0, st>>>(x, icoef, (__half*)xp, Ci, c_pad, H, W, Wp, rows);
     AFCM_LAUNCH_CHECK();
     count_launch();
     return AFCM_OK;
@@ -347,7 +420,7 @@ extern "C" int afcm_conv2d_tc(const void* xp, const void* w_tc, const float* oco
     if (pad != 1 && pad != 2) { set_error("conv2d_tc: padding %d not supported (1 or 2)", pad); return AFCM_ERR_UNSUPPORTED; }
     TcParams p;
     memset(&p, 0, sizeof(p));
-    p.ocoef = ocoef; p.y = y;
+    p.ocoef = ocoef; p.y = y; p.dbg = g_dbg_dev; p.dbg_mode = g_dbg_mode;
     p.N = N; p.Ci = Ci; p.Co = Co; p.H = H; p.W = W; p.Wp = W + 2; p.pad = pad;
     p.OH = H + 2 * pad - 2; p.OW = W + 2 * pad - 2;
     p.n_tiles = ceil_div(Co, 256);
@@ -357,14 +430,14 @@ extern "C" int afcm_conv2d_tc(const void* xp, const void* w_tc, const float* oco
     const long long total = (long long)N * p.m_tiles * p.n_tiles;
     AFCM_CHECK_ARG(total <= 0x7fffffffLL, "too many tiles");
     p.total_tiles = (int)total;
-    // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A/B = F16|BF16, A MN-major, B K-major, N, M
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A/B = F16|BF16, A and B K-major, N, M
     const unsigned fmt = tc_dtype == AFCM_BF16 ? 1u : 0u;
-    p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (0u << 16) | ((unsigned)(p.BN >> 3) << 17) | ((unsigned)(TC_BM >> 4) << 24);
+    p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (0u << 15) | (0u << 16) | ((unsigned)(p.BN >> 3) << 17) | ((unsigned)(TC_BM >> 4) << 24);
 
     const int co_pad = (Co + 15) & ~15, ci_pad = (Ci + 63) & ~63;
-    const uint64_t plane_pad = (uint64_t)afcm_conv_tc_plane_elems(H, W);
+    const uint64_t c_pad = (uint64_t)((Ci + 7) & ~7), rows = (uint64_t)H * p.Wp;
     CUtensorMap map_a, map_b;
-    int rc = encode_3d(&map_a, tc_dtype, xp, plane_pad, (uint64_t)Ci, (uint64_t)N, plane_pad * 2, plane_pad * 2 * Ci, 64, TC_BK);
+    int rc = encode_3d(&map_a, tc_dtype, xp, c_pad, rows, (uint64_t)N, c_pad * 2, rows * c_pad * 2, TC_BK, TC_BM);
     if (rc) return rc;
     rc = encode_3d(&map_b, tc_dtype, w_tc, (uint64_t)ci_pad, (uint64_t)co_pad, 9, (uint64_t)ci_pad * 2, (uint64_t)ci_pad * 2 * co_pad,
                    TC_BK, (uint32_t)p.BN);

@@ -74,7 +74,11 @@ def _bias_act_cuda(dim=1, act='linear', alpha=None, gain=None, clamp=None):
             if act != 'linear' or gain != 1 or clamp >= 0 or b is not None:
                 y = _native(x, b, None, None, None, 0, dim, spec, alpha, gain, clamp)
             need_x = 'x' in spec.ref or spec.has_2nd_grad
-            ctx.save_for_backward(x if need_x else None, b if need_x else None, y if 'y' in spec.ref else None)
+            # The reference plugin saves y only for activations whose derivative is expressed through it; for
+            # 'linear' with a clamp it therefore never gates the gradient (bias_act.py:151-154), unlike its own
+            # `_ref` path.  The `_ref` semantics are the oracle here, so y is also kept whenever a clamp is active.
+            need_y = 'y' in spec.ref or (clamp >= 0 and 'x' not in spec.ref)
+            ctx.save_for_backward(x if need_x else None, b if need_x else None, y if need_y else None)
             ctx.has_b = b is not None
             return y
 

@@ -33,13 +33,19 @@ def prepare_weight(w, pre_scale=1.0, normalize=False, want_tc=False, want_wsq=Fa
     """Per-layer constant preparation (afcm_conv_weight_prep), cached on (storage, version): scaled /
     RMS-normalised fp32 weights, the 16-bit tap-major copy for the tensor-core kernel and the per-(o,i)
     squared sums used by demodulation."""
+    import weakref
     dtype = dtype or tc_dtype
-    key = (w.data_ptr(), w._version, tuple(w.shape), float(pre_scale), bool(normalize), str(w.device))
+    key = (id(w), float(pre_scale), bool(normalize))
     ent = _prep_cache.get(key)
+    if ent is not None and (ent['_ref']() is not w or ent['_version'] != w._version):
+        ent = None                      # address / id reuse or in-place update (optimizer step): re-prepare
     if ent is None:
         if len(_prep_cache) > 512:
-            _prep_cache.clear()
-        ent = _prep_cache[key] = {}
+            for k in [k for k, v in _prep_cache.items() if v['_ref']() is None]:
+                del _prep_cache[k]
+            if len(_prep_cache) > 512:
+                _prep_cache.clear()
+        ent = _prep_cache[key] = {'_ref': weakref.ref(w), '_version': w._version}
     need_f32 = 'w_f32' not in ent
     need_tc = want_tc and ('w_tc', dtype) not in ent
     need_wsq = want_wsq and 'wsq' not in ent
@@ -82,8 +88,8 @@ def conv2d_native(x, w, padding, icoef=None, ocoef=None, pre_scale=1.0, normaliz
     use_tc = impl == 'tc' and kh == 3 and padding in (1, 2)
     ent = prepare_weight(w, pre_scale, normalize, want_tc=use_tc)
     if use_tc:
-        plane = int(L.afcm_conv_tc_plane_elems(H, W))
-        xp = torch.empty([N, Ci, plane], dtype=tc_dtype, device=x.device)
+        plane = int(L.afcm_conv_tc_plane_elems(H, W, Ci))
+        xp = torch.empty([N, plane], dtype=tc_dtype, device=x.device)
         code = _lib.dtype_code(tc_dtype)
         _lib.check(L.afcm_conv_tc_pack(_lib.ptr(x), _lib.ptr(icoef), _lib.ptr(xp), code, N, Ci, H, W, st))
         _lib.check(L.afcm_conv2d_tc(_lib.ptr(xp), _lib.ptr(ent[('w_tc', tc_dtype)]), _lib.ptr(ocoef), _lib.ptr(y), code,

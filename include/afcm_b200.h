@@ -140,17 +140,21 @@ int afcm_modconv_coefs(const float* styles, const float* wsq, const float* input
                        float* icoef, float* ocoef, int N, int Ci, int Co, int demodulate, void* stream);
 
 /* tcgen05 / TMEM implicit-GEMM path (16-bit operands, fp32 accumulation in tensor memory).
- * Step 1: pack activations into the conv-ready layout  xp [N,Ci,plane_pad] 16-bit, where each plane is
- * H rows of pitch W+2 (two trailing zeros per row, so horizontal taps wrap onto zeros) and plane_pad =
- * afcm_conv_tc_plane_elems(H,W).  icoef is folded here (modulation on the activation side).
+ * Step 1: pack activations into the conv-ready layout  xp [N, H*(W+2), Ci_pad8] 16-bit: channel-innermost
+ * flat planes of row pitch W+2 (two trailing zero pixels per row, so horizontal taps wrap onto zeros;
+ * vertical taps fall off the plane where TMA zero-fills); afcm_conv_tc_plane_elems(H,W,Ci) elements per
+ * sample.  icoef is folded here (modulation on the activation side).
  * Step 2: afcm_conv2d_tc runs the GEMM  D[pixel, o] = sum_{tap,i} A_tap[pixel,i] * B_tap[o,i]  with
  * M = 128 flat pixels, N = up to 256 output channels per CTA, TMA-fed, and writes fp32 NCHW
  * y [N,Co,H+2*pad-2,W+2*pad-2] scaled by ocoef.  ksize must be 3, pad 1 or 2. */
-int64_t afcm_conv_tc_plane_elems(int H, int W);
+int64_t afcm_conv_tc_plane_elems(int H, int W, int Ci);
 int afcm_conv_tc_pack(const float* x, const float* icoef, void* xp, int tc_dtype,
                       int N, int Ci, int H, int W, void* stream);
 int afcm_conv2d_tc(const void* xp, const void* w_tc, const float* ocoef, float* y, int tc_dtype,
                    int N, int Ci, int H, int W, int Co, int pad, void* stream);
+
+/* Debug aid, not part of the stable ABI: progress markers of the tcgen05 kernel in mapped host memory. */
+void* afcm_conv_tc_debug_buffer(int enable);
 
 /* ---------------------------------------------------------------------------------------------- */
 /* small fused kernels                                                                              */

@@ -53,7 +53,7 @@ def test_version_and_size_helpers(lib):
     sh, swb = ctypes.c_int(), ctypes.c_int()
     lib.afcm_filtered_lrelu_sign_size(276, 276, 2, 12, sh, swb)
     assert (sh.value, swb.value) == (276 * 2 - 1 + 11, ((276 * 2 - 1 + 11 + 15) // 16 * 16) // 4)
-    assert lib.afcm_conv_tc_plane_elems(36, 36) == (36 * 38 + 7) // 8 * 8
+    assert lib.afcm_conv_tc_plane_elems(36, 36, 362) == 36 * 38 * 368
     # invalid arguments are reported through the status code + message, never by crashing
     assert lib.afcm_filtered_lrelu_out_size(4, 4, 2, 2, 12, 12, 0, 0, 0, 0, yh, yw) == -2
     assert b'upsampled buffer' in lib.afcm_last_error()

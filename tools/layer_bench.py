@@ -82,8 +82,8 @@ def main():
             if 'conv_tc' in ops:
                 Lb = _lib.lib()
                 ent = conv2d_gradfix.prepare_weight(w, 1.0, False, want_tc=True)
-                plane = int(Lb.afcm_conv_tc_plane_elems(H, H))
-                xp = torch.empty(B, cin, plane, dtype=torch.float16, device=dev)
+                plane = int(Lb.afcm_conv_tc_plane_elems(H, H, cin))
+                xp = torch.empty(B, plane, dtype=torch.float16, device=dev)
                 y = torch.empty(B, cout, Hc, Hc, device=dev)
                 st = _lib.stream_ptr(dev)
                 pack = lambda: _lib.check(Lb.afcm_conv_tc_pack(_lib.ptr(x), None, _lib.ptr(xp), 1, B, cin, H, H, st))
