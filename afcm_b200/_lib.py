@@ -143,3 +143,42 @@ def np_ptr(a):
 
 def i64x4(vals):
     return (ctypes.c_int64 * 4)(*[int(v) for v in vals])
+
+
+# ----------------------------------------------------------------------------------------------------
+# Per-kernel timing used by bench.py's roofline leg: CUDA events on the launching stream around each
+# heavy kernel launch.  Off (None) unless bench.py turns it on; the product path is unaffected.
+_prof = None
+
+
+def profile_begin():
+    global _prof
+    _prof = []
+
+
+def profile_end():
+    """-> {kernel name: dict(ms, work, launches)}; synchronises."""
+    global _prof
+    import torch
+    torch.cuda.synchronize()
+    rec, _prof = _prof, None
+    out = {}
+    for name, work, a, b in rec or []:
+        d = out.setdefault(name, dict(ms=0.0, work=0.0, launches=0))
+        d['ms'] += a.elapsed_time(b)
+        d['work'] += work
+        d['launches'] += 1
+    return out
+
+
+def timed(name, work, fn):
+    """Runs fn(); when profiling is on, brackets it with CUDA events on the current stream."""
+    if _prof is None:
+        return fn()
+    import torch
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    r = fn()
+    b.record()
+    _prof.append((name, float(work), a, b))
+    return r

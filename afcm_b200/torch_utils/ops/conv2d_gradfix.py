@@ -91,9 +91,12 @@ def conv2d_native(x, w, padding, icoef=None, ocoef=None, pre_scale=1.0, normaliz
         plane = int(L.afcm_conv_tc_plane_elems(H, W, Ci))
         xp = torch.empty([N, plane], dtype=tc_dtype, device=x.device)
         code = _lib.dtype_code(tc_dtype)
-        _lib.check(L.afcm_conv_tc_pack(_lib.ptr(x), _lib.ptr(icoef), _lib.ptr(xp), code, N, Ci, H, W, st))
-        _lib.check(L.afcm_conv2d_tc(_lib.ptr(xp), _lib.ptr(ent[('w_tc', tc_dtype)]), _lib.ptr(ocoef), _lib.ptr(y), code,
-                                    N, Ci, H, W, Co, padding, st))
+        flops = 2.0 * N * Co * Ci * kh * kw * OH * OW
+        _lib.timed('conv_tc_pack', 4.0 * x.numel() + 2.0 * xp.numel(), lambda: _lib.check(
+            L.afcm_conv_tc_pack(_lib.ptr(x), _lib.ptr(icoef), _lib.ptr(xp), code, N, Ci, H, W, st)))
+        _lib.timed('conv2d_tc', flops, lambda: _lib.check(
+            L.afcm_conv2d_tc(_lib.ptr(xp), _lib.ptr(ent[('w_tc', tc_dtype)]), _lib.ptr(ocoef), _lib.ptr(y), code,
+                             N, Ci, H, W, Co, padding, st)))
     else:
         _lib.check(L.afcm_conv2d_f32(_lib.ptr(x), _lib.ptr(ent['w_f32']), _lib.ptr(icoef), _lib.ptr(ocoef), _lib.ptr(y),
                                      N, Ci, H, W, Co, kh, padding, st))

@@ -84,12 +84,14 @@ def _run_fused(x, fu, fd, b, si, up, down, px0, px1, py0, py1, sx, sy, gain, slo
     if skip is not None:
         assert skip.shape == y.shape and skip.dtype == y.dtype
         skip = skip.contiguous()
-    rc = L.afcm_filtered_lrelu(
+    # algorithmic bytes: x read once + y written once (+ the skip read when fused)
+    nbytes = x.element_size() * (x.numel() + y.numel() * (2 if skip is not None else 1))
+    rc = _lib.timed('filtered_lrelu', nbytes, lambda: L.afcm_filtered_lrelu(
         _lib.ptr(x), _lib.i64x4(x.stride()), _lib.ptr(y), _lib.i64x4(y.stride()), _lib.ptr(b), _lib.ptr(skip),
         _lib.dtype_code(x.dtype), N, C, xh, xw, yh, yw,
         _lib.np_ptr(fu_h), fu_n, _lib.np_ptr(fd_h), fd_n, up, down, px0, px1, py0, py1,
         gain, slope, clamp, out_scale, int(bool(flip_filter)), mode, _lib.ptr(s), sh, swb, int(sx), int(sy),
-        _lib.stream_ptr(x.device))
+        _lib.stream_ptr(x.device)))
     _lib.check(rc, allow_unsupported=True)
     if rc != 0:
         return None, None, rc

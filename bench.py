@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""bench.py -- AFCM generator forward throughput (slices/s @256^2) on B200, per the driver contract.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one generator forward (mapping + 14 encoder layers + co-modulation code + 15 synthesis
+layers) over one batch of synthetic slices: BASELINE.json configs[1], "IXI T1->T2 synthesis generator
+forward, synthetic 256x256 slices, batch 64, 1x B200".  For N > 1 every rank runs its own batch of 64
+slices (weak scaling, slice-sharded, no data-path collective -- SURVEY.md 8(e)).
+
+Own arm (default): every kernel on the path is hand-written sm_100a code reached through
+libafcm_b200.so; convolutions run on the tcgen05/TMEM implicit GEMM with fp16 operands and fp32
+accumulation.  `value` = slices/s with inputs resident in HBM; `e2e` = the same through the public
+generator call with pinned HOST buffers (H2D of cond_img/z/c and D2H of the result inside the timed
+region).  `roofline` is the dominant kernel (the implicit-GEMM convolution, tensor bound); `rooflines`
+adds filtered_lrelu against the measured HBM copy bandwidth.  `cpu_baseline` is the oracle port of the
+reference's CPU `_ref` path on this box's host cores (rank 0, N=1 only, bounded sample).
+
+Reference arm (--impl reference): times that CPU port alone with all host threads, one slice per step.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'generator_slices_per_sec_256x256'
+UNIT = 'slices/s'
+WORKLOAD = 'IXI T1->T2 synthesis generator forward, synthetic 256x256 slices, batch 64 per GPU'
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d['hbm_gbs']), tf_burst=float(d['bf16_tflops']),
+                    tf_sustained=float(d.get('bf16_tflops_sustained', d['bf16_tflops'])), source='measured')
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source='fallback')
+
+
+def synthetic_inputs(batch, seed=0):
+    """uint8-quantised slices mapped to [-1,1] like data/augment/transforms.py:604-616 of the reference;
+    4-slice stacks; fractional slice position c; z ~ N(0,1)."""
+    import numpy as np
+    import torch
+    rng = np.random.RandomState(seed)
+    v = rng.randint(0, 256, size=(batch, 4, 256, 256)).astype(np.float64)
+    x = np.clip(2.0 * v / 255.0 - 1.0, -1, 1).astype(np.float32)
+    g = torch.Generator().manual_seed(seed)
+    z = torch.randn(batch, 512, generator=g)
+    c = torch.zeros(batch, 1)
+    return z, c, torch.from_numpy(x)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons during the timed region (NVML, falls back to nvidia-smi)."""
+
+    def __init__(self, index, period=0.1):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.sm_max = [], set(), None
+        self._halt = threading.Event()
+        self._h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._h = None
+
+    NAMES = {0x1: 'gpu_idle', 0x2: 'applications_clocks_setting', 0x4: 'sw_power_cap', 0x8: 'hw_slowdown',
+             0x10: 'sync_boost', 0x20: 'sw_thermal_slowdown', 0x40: 'hw_thermal_slowdown',
+             0x80: 'hw_power_brake_slowdown', 0x100: 'display_clock_setting'}
+
+    def _sample(self):
+        if self._h is not None:
+            nv = self._nv
+            self.samples.append(int(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+            try:
+                fn = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                r = int(fn(self._h))
+                for bit, name in self.NAMES.items():
+                    if r & bit and name != 'gpu_idle':
+                        self.reasons.add(name)
+            except Exception:
+                pass
+        else:
+            import subprocess
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=clocks.sm,clocks.max.sm,'
+                                      'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+                                      'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap',
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                f = [t.strip() for t in out.strip().split(',')]
+                self.samples.append(int(f[0])); self.sm_max = int(f[1])
+                for name, val in zip(['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'], f[2:]):
+                    if val.lower().startswith('active'):
+                        self.reasons.add(name)
+            except Exception:
+                pass
+
+    def run(self):
+        while not self._halt.is_set():
+            self._sample()
+            self._halt.wait(self.period)
+
+    def finish(self):
+        self._halt.set()
+        self.join(timeout=5)
+        import statistics
+        return dict(sm_mhz=(statistics.median(self.samples) if self.samples else None), sm_max_mhz=self.sm_max,
+                    reasons=sorted(self.reasons), samples=len(self.samples))
+
+
+def cpu_reference_slices_per_sec(steps, warmup, seed=0):
+    """The oracle's torch-CPU restatement of the reference `_ref` generator forward (oracle/afcm_oracle.py
+    generator_forward), all host threads, ONE slice per step.  Returns (slices/s, ms/step, cores, sample)."""
+    import torch
+    from oracle import afcm_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    P = orc.init_params(seed=0)
+    z, c, x = synthetic_inputs(1, seed)
+    for _ in range(warmup):
+        orc.generator_forward(P, z, c, x)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.generator_forward(P, z, c, x)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return 1.0 / dt, dt * 1e3, cores, f'{steps} timed + {warmup} warm-up forwards of 1 slice (batch 1) of the same workload'
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    sps, ms, cores, sample = cpu_reference_slices_per_sec(args.steps, args.warmup)
+    line = dict(metric=METRIC, value=sps, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
+                data='synthetic', impl='reference',
+                config=dict(workload=WORKLOAD, batch_per_step=1,
+                            note='CPU port of the reference _ref path (the reference is Python; its own CPU ops are '
+                                 'torch conv2d/matmul, which the port calls too)'),
+                cpu_baseline=dict(value=sps, unit=UNIT, cores=cores, kind='port', sample=sample),
+                e2e=dict(value=sps, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world):
+    import torch
+    import torch.distributed as dist
+    from afcm_b200 import _lib
+    from afcm_b200.networks_stylegan3 import afcm_generator
+    from afcm_b200.torch_utils.ops import conv2d_gradfix
+
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    _lib.check(_lib.lib().afcm_device_check())
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B = args.batch
+    conv2d_gradfix.set_conv_impl('tc', torch.float16)
+    G = afcm_generator(seed=0, device=dev)
+    z, c, x = synthetic_inputs(B, seed=rank)
+    hz, hc, hx = z.pin_memory(), c.pin_memory(), x.pin_memory()
+    hy = torch.empty([B, 1, 256, 256], dtype=torch.float32).pin_memory()
+    dz, dc, dx = hz.to(dev), hc.to(dev), hx.to(dev)
+
+    def step_resident():
+        with torch.no_grad():
+            return G(dz, dc, dx, noise_mode='const')
+
+    def step_e2e():
+        with torch.no_grad():
+            y = G(hz.to(dev, non_blocking=True), hc.to(dev, non_blocking=True), hx.to(dev, non_blocking=True),
+                  noise_mode='const')
+            hy.copy_(y, non_blocking=True)
+
+    def timed_region(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local)
+    sampler.start()
+    n0 = _lib.launch_count()
+    ms_total = timed_region(step_resident, args.steps)
+    launches = _lib.launch_count() - n0
+    clocks = sampler.finish()
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed_region(step_e2e, args.steps)
+
+    # per-kernel roofline leg: same step, CUDA events around each heavy launch
+    _lib.profile_begin()
+    for _ in range(min(args.steps, 3)):
+        step_resident()
+    prof = _lib.profile_end()
+    peaks = load_peaks()
+
+    slices = float(B * world * args.steps)
+    value = slices / (ms_total * 1e-3)
+    e2e = slices / (ms_e2e * 1e-3)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    def roof(name, bound):
+        d = prof.get(name)
+        if not d or d['ms'] <= 0:
+            return None
+        if bound == 'tensor':
+            ach = d['work'] / d['ms'] / 1e9          # TFLOP/s
+            peak, unit = peaks['tf_sustained'], 'TFLOP/s'
+        else:
+            ach = d['work'] / d['ms'] / 1e6          # GB/s
+            peak, unit = peaks['hbm'], 'GB/s'
+        return dict(kernel=name, bound=bound, achieved=ach, peak=peak, unit=unit, frac=ach / peak, traffic=None,
+                    peak_source=peaks['source'] + (' (sustained bf16 cuBLAS)' if bound == 'tensor' else ' (copy)'),
+                    launches_per_step=d['launches'] // max(min(args.steps, 3), 1),
+                    ms_per_step=d['ms'] / max(min(args.steps, 3), 1),
+                    work_per_launch=d['work'] / max(d['launches'], 1))
+
+    r_conv = roof('conv2d_tc', 'tensor')
+    r_flr = roof('filtered_lrelu', 'hbm')
+    r_pack = roof('conv_tc_pack', 'hbm')
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                ms_per_step=ms_total / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype='f16 operands / f32 accumulate (conv), f32 elsewhere', data='synthetic',
+                config=dict(workload=WORKLOAD, batch_per_gpu=B, global_batch=B * world, resolution=256,
+                            sharding='slices across ranks, no data-path collective',
+                            l2='working set per step (>5 GB of activations) exceeds the 126 MB L2; no explicit flush'),
+                clocks=clocks, gpu_launches=int(launches),
+                e2e=dict(value=e2e, unit=UNIT, h2d_bytes_per_step=int(hz.nbytes + hc.nbytes + hx.nbytes),
+                         d2h_bytes_per_step=int(hy.nbytes), ms_per_step=ms_e2e / args.steps),
+                roofline=r_conv, rooflines=dict(conv2d_tc=r_conv, filtered_lrelu=r_flr, conv_tc_pack=r_pack))
+    if world == 1 and not args.no_cpu_baseline:
+        sps, ms, cores, sample = cpu_reference_slices_per_sec(1, 1)
+        line['cpu_baseline'] = dict(value=sps, unit=UNIT, cores=cores, kind='port', sample=sample)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=64)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    if args.impl == 'reference':
+        run_reference(args, rank)
+    else:
+        run_ours(args, rank, world)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,17 @@
+#!/bin/bash
+# Round-1 measurement session: parity tests, smoke, bench line, per-layer timings, ncu launch list and
+# full captures of the two heavy kernels.  Everything lands in gpurun_out/.
+mkdir -p gpurun_out
+S=gpurun_out/summary.txt; : > $S
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/t_gpu.log 2>&1; echo "pytest_gpu rc=$?" >> $S
+timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> $S
+timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?" >> $S
+timeout 600 python tools/layer_bench.py --batch 16 --ops flrelu,conv_tc --json gpurun_out/lb.json > gpurun_out/lb.log 2>&1; echo "layer_bench rc=$?" >> $S
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; echo "ncu_launches rc=$?" >> $S
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv2d_tc_kernel -s 40 -c 3 -o gpurun_out/prof_conv -f \
+    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --batch 16 > gpurun_out/ncu_conv.log 2>&1; echo "ncu_conv rc=$?" >> $S
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:flr_fused -s 40 -c 4 -o gpurun_out/prof_flr -f \
+    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --batch 16 > gpurun_out/ncu_flr.log 2>&1; echo "ncu_flr rc=$?" >> $S
+cat $S; tail -5 gpurun_out/t_gpu.log; tail -2 gpurun_out/smoke.log; cat gpurun_out/bench.log; tail -3 gpurun_out/bench.err; tail -2 gpurun_out/lb.log

@@ -1,0 +1,76 @@
+"""Turns gpurun_out/launches.csv (ncu --metrics gpu__time_duration.sum) and *.ncu-rep captures into the
+small text summaries committed under profiles/.
+
+    python tools/summarize_profiles.py launches gpurun_out/launches.csv profiles/r01_launches_<tag>.txt
+    python tools/summarize_profiles.py rep gpurun_out/prof_conv.ncu-rep profiles/r01_ncu_<tag>.txt
+"""
+import csv
+import re
+import subprocess
+import sys
+from collections import OrderedDict
+
+KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'dram__throughput.avg.pct_of_peak_sustained_elapsed',
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'lts__t_bytes.sum', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_tensor.sum',
+        'sm__pipe_tensor_op_hmma_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active', 'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed.sum', 'smsp__inst_executed.avg.per_cycle_active', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'launch__registers_per_thread', 'launch__shared_mem_per_block_dynamic', 'launch__shared_mem_per_block_static',
+        'launch__grid_size', 'launch__block_size', 'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem',
+        'launch__waves_per_multiprocessor', 'sm__cycles_elapsed.avg', 'smsp__cycles_active.avg',
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct',
+        'smsp__warp_issue_stalled_barrier_per_warp_active.pct', 'smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct',
+        'smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct', 'smsp__warp_issue_stalled_mio_throttle_per_warp_active.pct',
+        'smsp__warp_issue_stalled_wait_per_warp_active.pct', 'smsp__warp_issue_stalled_not_selected_per_warp_active.pct',
+        'smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct']
+
+
+def short(name):
+    name = re.sub(r'\(.*', '', name)
+    return name.replace('afcm::', '')
+
+
+def launches(src, dst):
+    rows = []
+    with open(src) as f:
+        lines = [l for l in f if l.startswith('"')]
+    for r in csv.DictReader(lines):
+        if r.get('Metric Name') == 'gpu__time_duration.sum':
+            rows.append((short(r['Kernel Name']), float(r['Metric Value'].replace(',', '')), r['Grid Size'], r['Block Size']))
+    agg = OrderedDict()
+    for k, ns, *_ in rows:
+        a = agg.setdefault(k, [0, 0.0])
+        a[0] += 1; a[1] += ns
+    total = sum(a[1] for a in agg.values())
+    with open(dst, 'w') as f:
+        f.write(f'# per-kernel totals over {len(rows)} launches (ncu gpu__time_duration.sum, --clock-control none; cold-cache, serialised:\n')
+        f.write('# compare SHARES, not absolutes)\n')
+        f.write(f'{"kernel":60s} {"launches":>8s} {"total_ms":>10s} {"avg_us":>9s} {"share":>7s}\n')
+        for k, (n, ns) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f'{k:60s} {n:8d} {ns / 1e6:10.3f} {ns / n / 1e3:9.2f} {ns / total:7.3f}\n')
+        f.write(f'{"TOTAL":60s} {len(rows):8d} {total / 1e6:10.3f}\n\n# launch list (id, kernel, us, grid, block)\n')
+        for i, (k, ns, g, b) in enumerate(rows):
+            f.write(f'{i:5d} {k:60s} {ns / 1e3:10.2f} {g:>16s} {b:>14s}\n')
+    print(open(dst).read().split('# launch list')[0])
+
+
+def rep(src, dst):
+    out = subprocess.run(['ncu', '-i', src, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    lines = [l for l in out.splitlines() if l.startswith('"')]
+    rd = list(csv.reader(lines))
+    hdr, units, data = rd[0], rd[1], rd[2:]
+    with open(dst, 'w') as f:
+        f.write(f'# ncu --set full --clock-control none capture: {src}\n')
+        for row in data:
+            d = dict(zip(hdr, row))
+            f.write(f'\n== {short(d["Kernel Name"])}  grid {d.get("Grid Size")} block {d.get("Block Size")}\n')
+            for k in KEYS:
+                if k in d:
+                    f.write(f'  {k:80s} {d[k]:>18s} {units[hdr.index(k)]}\n')
+    print(open(dst).read())
+
+
+if __name__ == '__main__':
+    {'launches': launches, 'rep': rep}[sys.argv[1]](sys.argv[2], sys.argv[3])
