@@ -1,30 +1,39 @@
 // flr_tc.cu -- filtered_lrelu on the tensor cores (sm_100a): the four separable FIR passes of
 // bias -> up-FIR -> gain/leaky-ReLU/clamp -> down-FIR (reference: models/networks/stylegan3/torch_utils/
 // ops/filtered_lrelu.py:121-153, filtered_lrelu.cu:139-1099) evaluated as a chain of small banded-Toeplitz
-// matrix products with mma.sync.m16n8k16 (fp16 operands, fp32 accumulation), entirely in registers.
+// matrix products with mma.sync.m16n8k16 (fp16 operands), entirely in registers.
 //
 // Why: the op does 17-46 FLOP per algorithmic byte, above the FP32-SIMT ridge of B200, so a CUDA-core
-// kernel cannot approach the HBM roofline.  Here the MACs run on the tensor pipe
-// and the FP32 pipe only does the nonlinearity.
+// kernel cannot approach the HBM roofline.  Here the MACs run on the tensor pipe,
+// the nonlinearity on the (otherwise idle) FMA pipe as packed half2 arithmetic, and the ALU pipe only
+// sees address arithmetic and the input conversion.
 //
 // Algorithm (one warp = one strip of 16 output columns, streamed top to bottom):
 //   in[y][x]  --(1) R1[j,y] = sum_x Tu_x[j,x] in[y,x]      const A, data B (global -> regs)
-//             --(2) R2[v,j] = sum_y Tu_y[v,y] R1[j,y]      const A, B = C-fragments of (1)   (transposing reuse)
-//             --    gain (folded into Tu_y), leaky ReLU in fp32, clamp by saturating fp16 conversion
-//             --(4) R3[k,v] = sum_j Td_x[k,j] R2[v,j]      const A, B = C-fragments of (2)
-//             --(5) R4[k,w] = sum_v R3[k,v] Td_y[w,v]      A = C-fragments of (4), const B
-//   j,v = up-sampled coordinates, k,w = output coordinates.  The m16n8 accumulator layout of one product
-//   is exactly the B (or A) operand layout of the next, so no shared memory, shuffles or block barriers
-//   are needed between passes; the Toeplitz operands are shift invariant, so each thread keeps a handful
-//   of constant fragments (the FIR taps) in registers for the whole strip.  The polyphase structure of
-//   the zero-insertion is folded into Tu (only every UP-th column of a row is non-zero).
+//             --(2) R2[v,j] = sum_y Tu_y[v,y] R1[j,y]      const A, B = D-fragments of (1)   (transposing reuse)
+//             --    leaky ReLU + clamp on half2 (see act2 below)
+//             --(4) R3[k,v] = sum_j Td_x[k,j] R2[v,j]      const A, B = D-fragments of (2)
+//             --(5) R4[k,w] = sum_v R3[k,v] Td_y[w,v]      A = D-fragments of (4), const B, fp32 accumulate
+//   j,v = up-sampled coordinates, k,w = output coordinates.  Products (1), (2) and (4) use the f16
+//   accumulator form of the instruction: its m16n8 result layout (two packed half2 registers) IS the B
+//   (or A) operand layout of the next product, so there is no conversion, shared memory, shuffle or block
+//   barrier between passes.  The Toeplitz operands are shift invariant, so each thread keeps a handful of
+//   constant fragments (the FIR taps) in registers for the whole strip.  The polyphase structure of the
+//   zero-insertion is folded into Tu (only every UP-th column of a row is non-zero).
 //   Index conventions (s = phase shift, delta = input alignment, origins) are modelled in
 //   tools/flr_tc_model.py and pinned against the oracle by tests/test_flr_tc_model.py.
 //
-// Numerics: operands (activations, intermediates, taps) are rounded to fp16, sums are fp32.  Measured
-// against the fp32 oracle: max error ~5e-4 of max|y| per call (tests/test_gpu_flr_tc.py states the bound).
-// This is the "tensor-core path with stated tolerance" of the north star; afcm_filtered_lrelu remains the
-// exact-fp32 path.
+// Activation: with u = x*gain/clamp (the scale is folded into the Tu_y taps),
+//       clamp(lrelu(x*gain), +-clamp) / clamp = sat(u) - sat(-slope*u),      sat(.) = clamp to [0,1]
+//   which is three half2 instructions on the FMA pipe (HMUL2.SAT x2, HADD2) for two samples, both clamps
+//   included; `clamp` is folded back into the Td_x taps.  Without a clamp (or with one too large for the
+//   fp16 range of u) the kernel uses max(u, slope*u) and an explicit min/max.
+//
+// Numerics: operands (activations, intermediates, taps) are rounded to fp16; sums are fp32 inside the
+// tensor core and rounded once per product (product (4) rounds after each of its K chunks), the last
+// product accumulates in fp32.  Measured against the fp32 oracle: see tests/test_gpu_flr_tc.py for the
+// stated bound (2e-3 of max|y| per call).  This is the "tensor-core path with stated tolerance" of the north
+// star; afcm_filtered_lrelu remains the exact-fp32 path.
 #include <cuda_fp16.h>
 #include "afcm_common.cuh"
 
@@ -34,17 +43,19 @@ constexpr int FTC_WARPS = 4;
 constexpr int FTC_TAB = 192;          // tap tables: index t + 64, zero padded
 constexpr int FTC_TAB_OFS = 64;
 
+enum { FTC_ACT_SAT = 0, FTC_ACT_MINMAX = 1 };
+
 struct FlrTcParams {
     const void* x; void* y; const float* b; const void* skip;
-    long long xs_n, xs_c, xs_h, ys_n, ys_c, ys_h;        // element strides, innermost stride 1
+    long long xs_n, xs_c, ys_n, ys_c;                    // element strides, innermost stride 1
+    int xs_h, ys_h;                                      // row strides (host-checked to fit 32 bits)
     int C, xh, xw, yh, yw;
     int strips, segs, seg_wblocks;                        // 16-column strips, row segments of 8*seg_wblocks rows
     long long total_warps;
     int ix0, iy0, iy_step;                                // input origin: col = strip*IXS + ix0, row = seg*iy_step + iy0
     int sx, sy, dx;
-    int slope_gt1;
-    float slope, out_scale, sat_scale;                    // sat_scale: R2 is scaled so that clamp == fp16 max (or 1)
-    float kux[24], kuy[24], kdx[24], kdy[24];             // correlation-form taps (kuy carries gain*sat_scale, kdx 1/sat_scale)
+    float slope, out_scale, act_clamp;                    // act_clamp: clamp in the units of R2 (MINMAX mode)
+    float kux[24], kuy[24], kdx[24], kdy[24];             // correlation-form taps (kuy, kdx carry gain and the clamp scale)
 };
 
 template <int U, int D> struct FtcGeo {
@@ -62,32 +73,83 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi)
     __half2 h = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);
 }
-// saturating conversion: |v| >= 65504 -> +-65504 (implements the clamp, see sat_scale)
-__device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi)
+// D = A * B, f16 result (two packed half2 registers: rows g / g+8, columns 2t, 2t+1)
+__device__ __forceinline__ void mma_h(uint32_t (&d)[2], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    const uint32_t z = 0u;
+    asm("mma.sync.aligned.m16n8k16.row.col.f16.f16.f16.f16 {%0,%1}, {%2,%3,%4,%5}, {%6,%7}, {%8,%8};"
+        : "=r"(d[0]), "=r"(d[1])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "r"(z));
+}
+// D += A * B, f16 accumulator
+__device__ __forceinline__ void mma_h_acc(uint32_t (&d)[2], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    asm("mma.sync.aligned.m16n8k16.row.col.f16.f16.f16.f16 {%0,%1}, {%2,%3,%4,%5}, {%6,%7}, {%0,%1};"
+        : "+r"(d[0]), "+r"(d[1])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// D += A * B, fp32 accumulator
+__device__ __forceinline__ void mma_f(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t h2_mul_sat(uint32_t a, uint32_t b)
 {
     uint32_t r;
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    asm("mul.rn.sat.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
     return r;
 }
-__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+__device__ __forceinline__ uint32_t h2_sub(uint32_t a, uint32_t b)
 {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    uint32_t r;
+    asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ uint32_t h2_mul(uint32_t a, uint32_t b)
+{
+    uint32_t r;
+    asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ uint32_t h2_max(uint32_t a, uint32_t b)
+{
+    uint32_t r;
+    asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ uint32_t h2_min(uint32_t a, uint32_t b)
+{
+    uint32_t r;
+    asm("min.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
 }
 
-template <int U, int D, typename TIN, typename TOUT>
+template <typename T> struct Pair;
+template <> struct Pair<float> { typedef float2 type; };
+template <> struct Pair<__half> { typedef uint32_t type; };
+
+template <int U, int D, typename TIN, typename TOUT, int ACT>
 struct FtcWarp {
     using Geo = FtcGeo<U, D>;
+    using RawT = typename Pair<TIN>::type;
     // constant fragments (the FIR taps)
     uint32_t a1[Geo::NPH][4], a2[Geo::NPH][4], a4[Geo::KC4][4], b5[Geo::NB5][2];
+    uint32_t h_one, h_nslope, h_slope, h_cl, h_ncl, h_bias;
     const FlrTcParams& p;
     int g, t;
     // strip state
-    const TIN* xp; TOUT* yp; const TOUT* kp;
+    const TIN* xg;               // plane base + g rows
+    const TIN* xc0;              // xg + first column pair of the strip (interior strips: chunk c at +8c)
+    TOUT* yt;                    // plane base + (w0 + 2t) rows + k0 + g
+    long long kofs;              // skip - y (elements), valid when has_skip
+    bool has_skip;
     float bias;
-    int ix, iy, k0, w0, nwb;
-    unsigned colmask;            // bit 2c / 2c+1: column validity of the two elements of chunk c
+    int iy, k0, w0, nwb;
+    int coff[Geo::NC];           // element offset of the chunk's column pair inside a row (clamped into the row)
+    unsigned cmask;              // bit c: the chunk's column pair is inside the plane
+    bool cols_all;               // every lane of the warp has every chunk inside the plane
 
     __device__ FtcWarp(const FlrTcParams& p_, int lane) : p(p_), g(lane >> 2), t(lane & 3) {}
 
@@ -126,6 +188,11 @@ struct FtcWarp {
                 b5[q][r] = pack_h2(tdy[e], tdy[e + 1]);
             }
         }
+        h_one = pack_h2(1.f, 1.f);
+        h_nslope = pack_h2(-p.slope, -p.slope);
+        h_slope = pack_h2(p.slope, p.slope);
+        h_cl = pack_h2(p.act_clamp, p.act_clamp);
+        h_ncl = pack_h2(-p.act_clamp, -p.act_clamp);
     }
 
     __device__ void begin_strip(long long wid)
@@ -135,72 +202,92 @@ struct FtcWarp {
         const int seg = (int)(r % p.segs);
         const long long plane = r / p.segs;
         const int n = (int)(plane / p.C), c = (int)(plane - (long long)n * p.C);
-        xp = (const TIN*)p.x + n * p.xs_n + c * p.xs_c;
-        yp = (TOUT*)p.y + n * p.ys_n + c * p.ys_c;
-        kp = p.skip ? (const TOUT*)p.skip + n * p.ys_n + c * p.ys_c : nullptr;
+        xg = (const TIN*)p.x + n * p.xs_n + c * p.xs_c + (long long)g * p.xs_h;
+        has_skip = p.skip != nullptr;
+        kofs = has_skip ? (const TOUT*)p.skip - (const TOUT*)p.y : 0;
         bias = p.b ? p.b[c] : 0.f;
-        ix = strip * Geo::IXS + p.ix0;
+        h_bias = pack_h2(bias, bias);
+        const int ix = strip * Geo::IXS + p.ix0;
         iy = seg * p.iy_step + p.iy0;
         k0 = strip * 16;
         w0 = seg * p.seg_wblocks * 8;
+        yt = (TOUT*)p.y + n * p.ys_n + c * p.ys_c + (long long)(w0 + 2 * t) * p.ys_h + k0 + g;
+        xc0 = xg + (ix + 2 * t);
         const int rows_left = p.yh - w0;
         nwb = (rows_left + 7) >> 3;
         if (nwb > p.seg_wblocks) nwb = p.seg_wblocks;
-        colmask = 0;
+        cmask = 0;
+        // ix and xw are even (host-checked), so a column pair is either inside or outside the plane as a whole
 #pragma unroll
         for (int c8 = 0; c8 < Geo::NC; c8++) {
             const int col = ix + 8 * c8 + 2 * t;
-            if (col >= 0 && col < p.xw) colmask |= 1u << (2 * c8);
-            if (col + 1 >= 0 && col + 1 < p.xw) colmask |= 2u << (2 * c8);
+            const bool ok = col >= 0 && col < p.xw;
+            if (ok) cmask |= 1u << c8;
+            coff[c8] = ok ? col : 0;
         }
+        cols_all = __all_sync(0xffffffffu, cmask == (1u << Geo::NC) - 1u);
     }
 
-    // raw loads of one block of 8 input rows (this thread: row g, NC column pairs)
-    __device__ __forceinline__ void load_raw(int yb, float2 (&raw)[Geo::NC]) const
+    // ---- input: issue the loads of one block of 8 input rows (this thread: row g, NC column pairs).
+    // Addresses are clamped into the plane, so the loads are unconditional; convert() zeroes what was outside.
+    __device__ __forceinline__ void fetch(int yb, RawT (&raw)[Geo::NC]) const
     {
-        const int row = iy + 8 * yb + g;
-        const bool rok = row >= 0 && row < p.xh;
-        const TIN* rp = xp + (long long)row * p.xs_h + ix + 2 * t;
+        const int row0 = iy + 8 * yb;
+        if (cols_all && row0 >= 0 && row0 + 8 <= p.xh) {                // warp-uniform: interior block
+            const TIN* rp = xc0 + (long long)row0 * p.xs_h;
 #pragma unroll
-        for (int c8 = 0; c8 < Geo::NC; c8++) {
-            const unsigned m = rok ? (colmask >> (2 * c8)) & 3u : 0u;
-            float2 v = make_float2(0.f, 0.f);
-            const TIN* q = rp + 8 * c8;
-            if (sizeof(TIN) == 4) {
-                if (m == 3u && ((reinterpret_cast<uintptr_t>(q) & 7) == 0)) {
-                    v = *reinterpret_cast<const float2*>(q);
-                } else {
-                    if (m & 1u) v.x = (float)q[0];
-                    if (m & 2u) v.y = (float)q[1];
-                }
-            } else {
-                if (m == 3u && ((reinterpret_cast<uintptr_t>(q) & 3) == 0)) {
-                    v = __half22float2(*reinterpret_cast<const __half2*>(q));
-                } else {
-                    if (m & 1u) v.x = (float)q[0];
-                    if (m & 2u) v.y = (float)q[1];
-                }
-            }
-            if (m & 1u) v.x += bias;
-            if (m & 2u) v.y += bias;
-            raw[c8] = v;
+            for (int c8 = 0; c8 < Geo::NC; c8++) raw[c8] = *reinterpret_cast<const RawT*>(rp + 8 * c8);
+        } else {
+            const int row = max(-g, min(row0, p.xh - 1 - g));           // row + g clamped into [0, xh)
+            const TIN* rp = xg + (long long)row * p.xs_h;
+#pragma unroll
+            for (int c8 = 0; c8 < Geo::NC; c8++) raw[c8] = *reinterpret_cast<const RawT*>(rp + coff[c8]);
+        }
+    }
+    __device__ __forceinline__ uint32_t cvt_pair(const float2& v) const { return pack_h2(v.x + bias, v.y + bias); }
+    __device__ __forceinline__ uint32_t cvt_pair(const uint32_t& v) const
+    {
+        uint32_t r;
+        asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(h_bias));
+        return r;
+    }
+    __device__ __forceinline__ void convert(int yb, const RawT (&raw)[Geo::NC], uint32_t (&in)[Geo::NC]) const
+    {
+        const int row0 = iy + 8 * yb;
+        if (cols_all && row0 >= 0 && row0 + 8 <= p.xh) {                // warp-uniform: interior block
+#pragma unroll
+            for (int c8 = 0; c8 < Geo::NC; c8++) in[c8] = cvt_pair(raw[c8]);
+        } else {
+            const int row = row0 + g;
+            const unsigned m = (row >= 0 && row < p.xh) ? cmask : 0u;
+#pragma unroll
+            for (int c8 = 0; c8 < Geo::NC; c8++) in[c8] = ((m >> c8) & 1u) ? cvt_pair(raw[c8]) : 0u;
         }
     }
 
     // (1) horizontal up-FIR of one block of 8 input rows: r1[nb] = B-fragment half for column block nb of R2
-    __device__ __forceinline__ void step1(const float2 (&raw)[Geo::NC], uint32_t (&r1)[Geo::NJ8]) const
+    __device__ __forceinline__ void step1(const uint32_t (&in)[Geo::NC], uint32_t (&r1)[Geo::NJ8]) const
     {
-        uint32_t in[Geo::NC];
-#pragma unroll
-        for (int c8 = 0; c8 < Geo::NC; c8++) in[c8] = pack_h2(raw[c8].x, raw[c8].y);
 #pragma unroll
         for (int b = 0; b < Geo::KC4; b++) {
             const int w = (U == 2) ? b : (b >> 1);          // first input chunk of the window
             const int ph = (U == 2) ? 0 : (b & 1);
-            float c[4] = {0.f, 0.f, 0.f, 0.f};
-            mma16816(c, a1[ph], in[w], in[w + 1]);
-            r1[2 * b] = pack_h2(c[0], c[1]);
-            r1[2 * b + 1] = pack_h2(c[2], c[3]);
+            uint32_t d[2];
+            mma_h(d, a1[ph], in[w], in[w + 1]);
+            r1[2 * b] = d[0];
+            r1[2 * b + 1] = d[1];
+        }
+    }
+
+    // leaky ReLU + clamp of two packed samples (see the header)
+    __device__ __forceinline__ uint32_t act2(uint32_t u) const
+    {
+        if (ACT == FTC_ACT_SAT) {
+            return h2_sub(h2_mul_sat(u, h_one), h2_mul_sat(u, h_nslope));
+        } else {
+            const uint32_t s = h2_mul(u, h_slope);
+            const uint32_t v = p.slope > 1.f ? h2_min(u, s) : h2_max(u, s);
+            return h2_max(h2_min(v, h_cl), h_ncl);
         }
     }
 
@@ -208,43 +295,52 @@ struct FtcWarp {
     __device__ __forceinline__ void vblock(const uint32_t (&ra)[Geo::NJ8], const uint32_t (&rb)[Geo::NJ8], int ph,
                                            uint32_t (&a5)[4]) const
     {
-        float c3[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        uint32_t c0[2], c1[2];
 #pragma unroll
         for (int kc = 0; kc < Geo::KC4; kc++) {
             uint32_t p2[2][2];
 #pragma unroll
             for (int q = 0; q < 2; q++) {
                 const int nb = 2 * kc + q;
-                float c[4] = {0.f, 0.f, 0.f, 0.f};
-                mma16816(c, a2[ph], ra[nb], rb[nb]);
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const float s = c[i] * p.slope;
-                    c[i] = p.slope_gt1 ? fminf(c[i], s) : fmaxf(c[i], s);
-                }
-                p2[q][0] = pack_h2_sat(c[0], c[1]);
-                p2[q][1] = pack_h2_sat(c[2], c[3]);
+                uint32_t d[2];
+                mma_h(d, a2[ph], ra[nb], rb[nb]);
+                p2[q][0] = act2(d[0]);
+                p2[q][1] = act2(d[1]);
             }
-            mma16816(c3[0], a4[kc], p2[0][0], p2[1][0]);
-            mma16816(c3[1], a4[kc], p2[0][1], p2[1][1]);
+            if (kc == 0) {
+                mma_h(c0, a4[kc], p2[0][0], p2[1][0]);
+                mma_h(c1, a4[kc], p2[0][1], p2[1][1]);
+            } else {
+                mma_h_acc(c0, a4[kc], p2[0][0], p2[1][0]);
+                mma_h_acc(c1, a4[kc], p2[0][1], p2[1][1]);
+            }
         }
-        a5[0] = pack_h2(c3[0][0], c3[0][1]);
-        a5[1] = pack_h2(c3[0][2], c3[0][3]);
-        a5[2] = pack_h2(c3[1][0], c3[1][1]);
-        a5[3] = pack_h2(c3[1][2], c3[1][3]);
+        a5[0] = c0[0]; a5[1] = c0[1]; a5[2] = c1[0]; a5[3] = c1[1];
     }
 
     __device__ __forceinline__ void store(int wb, const float (&c)[4]) const
     {
-        const int y0 = w0 + 8 * wb + 2 * t;
+        TOUT* q0 = yt + (long long)(8 * wb) * p.ys_h;                   // (row 2t, col g) of this block
+        TOUT* q1 = q0 + p.ys_h;
+        float v[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int yy = y0 + (i & 1), xx = k0 + g + (i >> 1) * 8;
-            if (yy < p.yh && xx < p.yw) {
-                const long long o = (long long)yy * p.ys_h + xx;
-                float v = c[i];
-                if (kp) v += (float)kp[o];
-                yp[o] = (TOUT)(v * p.out_scale);
+        for (int i = 0; i < 4; i++) v[i] = c[i];
+        if (w0 + 8 * wb + 8 <= p.yh && k0 + 16 <= p.yw) {               // warp-uniform: interior block
+            if (has_skip) {
+                v[0] += (float)q0[kofs]; v[1] += (float)q1[kofs]; v[2] += (float)q0[kofs + 8]; v[3] += (float)q1[kofs + 8];
+            }
+            q0[0] = (TOUT)(v[0] * p.out_scale); q1[0] = (TOUT)(v[1] * p.out_scale);
+            q0[8] = (TOUT)(v[2] * p.out_scale); q1[8] = (TOUT)(v[3] * p.out_scale);
+        } else {
+            const int y0 = w0 + 8 * wb + 2 * t;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int yy = y0 + (i & 1), xx = k0 + g + (i >> 1) * 8;
+                if (yy < p.yh && xx < p.yw) {
+                    TOUT* q = ((i & 1) ? q1 : q0) + (i >> 1) * 8;
+                    if (has_skip) v[i] += (float)q[kofs];
+                    *q = (TOUT)(v[i] * p.out_scale);
+                }
             }
         }
     }
@@ -253,48 +349,61 @@ struct FtcWarp {
     __device__ __forceinline__ void wblock2(int wb, const uint32_t (&c0)[4], const uint32_t (&c1)[4]) const
     {
         float c[4] = {0.f, 0.f, 0.f, 0.f};
-        mma16816(c, c0, b5[0][0], b5[0][1]);
-        mma16816(c, c1, b5[1][0], b5[1][1]);
+        mma_f(c, c0, b5[0][0], b5[0][1]);
+        mma_f(c, c1, b5[1][0], b5[1][1]);
         store(wb, c);
     }
     __device__ __forceinline__ void wblock4(int wb, const uint32_t (&c0)[4], const uint32_t (&c1)[4], const uint32_t (&c2)[4],
                                             const uint32_t (&c3)[4]) const
     {
         float c[4] = {0.f, 0.f, 0.f, 0.f};
-        mma16816(c, c0, b5[0][0], b5[0][1]);
-        mma16816(c, c1, b5[1][0], b5[1][1]);
-        mma16816(c, c2, b5[Geo::NB5 - 2][0], b5[Geo::NB5 - 2][1]);
-        mma16816(c, c3, b5[Geo::NB5 - 1][0], b5[Geo::NB5 - 1][1]);
+        mma_f(c, c0, b5[0][0], b5[0][1]);
+        mma_f(c, c1, b5[1][0], b5[1][1]);
+        mma_f(c, c2, b5[Geo::NB5 - 2][0], b5[Geo::NB5 - 2][1]);
+        mma_f(c, c3, b5[Geo::NB5 - 1][0], b5[Geo::NB5 - 1][1]);
         store(wb, c);
     }
 
     __device__ void run()
     {
-        float2 raw[Geo::NC];
+        RawT raw[Geo::NC];
+        uint32_t in[Geo::NC];
         if (U == 2 && D == 2) {
-            // iteration it: input block it -> R1[it]; v-block it-1 from R1[it-1], R1[it]; w-block it-2 from chunks it-2, it-1
-            uint32_t r1p[Geo::NJ8], r1c[Geo::NJ8], a5p[4], a5c[4];
-            const int iters = nwb + 2;
-            load_raw(0, raw);
-            for (int it = 0; it < iters; it++) {
-                step1(raw, r1c);
-                if (it + 1 < iters) load_raw(it + 1, raw);
-                if (it >= 1) vblock(r1p, r1c, 0, a5c);
-                if (it >= 2) wblock2(it - 2, a5p, a5c);
-#pragma unroll
-                for (int i = 0; i < Geo::NJ8; i++) r1p[i] = r1c[i];
-#pragma unroll
-                for (int i = 0; i < 4; i++) a5p[i] = a5c[i];
+            // iteration it: input block it -> R1[it]; v-block it-1 from R1[it-1], R1[it]; w-block it-2 from chunks it-2, it-1.
+            // Unrolled by two so that the "previous" buffers alternate instead of being copied.
+            uint32_t r1a[Geo::NJ8], r1b[Geo::NJ8], a5a[4], a5b[4];
+            const int iters = nwb + 2;                                  // >= 3
+            fetch(0, raw);
+            convert(0, raw, in); step1(in, r1a);
+            fetch(1, raw);
+            convert(1, raw, in); step1(in, r1b);
+            fetch(2, raw);
+            vblock(r1a, r1b, 0, a5b);
+            int it = 2;
+            for (; it + 1 < iters; it += 2) {
+                convert(it, raw, in); step1(in, r1a);
+                fetch(it + 1, raw);
+                vblock(r1b, r1a, 0, a5a);
+                wblock2(it - 2, a5b, a5a);
+                convert(it + 1, raw, in); step1(in, r1b);
+                fetch(it + 2, raw);
+                vblock(r1a, r1b, 0, a5b);
+                wblock2(it - 1, a5a, a5b);
+            }
+            if (it < iters) {
+                convert(it, raw, in); step1(in, r1a);
+                vblock(r1b, r1a, 0, a5a);
+                wblock2(it - 2, a5b, a5a);
             }
         } else if (U == 4 && D == 2) {
             // iteration it: input block it; v-blocks 2it-2, 2it-1 (two phases) from R1[it-1], R1[it];
             // w-block 2it-3 from chunks (2it-3, 2it-2), w-block 2it-2 from chunks (2it-2, 2it-1)
             uint32_t r1p[Geo::NJ8], r1c[Geo::NJ8], a5l[4], a5a[4], a5b[4];
             const int iters = (nwb + 2) / 2 + 1;
-            load_raw(0, raw);
+            fetch(0, raw);
             for (int it = 0; it < iters; it++) {
-                step1(raw, r1c);
-                if (it + 1 < iters) load_raw(it + 1, raw);
+                convert(it, raw, in); step1(in, r1c);
+                fetch(it + 1, raw);
                 if (it >= 1) {
                     vblock(r1p, r1c, 0, a5a);
                     vblock(r1p, r1c, Geo::NPH - 1, a5b);
@@ -311,12 +420,13 @@ struct FtcWarp {
             // v-block 2it from R1[2it], R1[2it+1]; w-block it-2 from chunks 2it-4 .. 2it-1
             uint32_t r1l[Geo::NJ8], r1a[Geo::NJ8], r1b[Geo::NJ8], q0[4], q1[4], q2[4], qa[4], qb[4];
             const int iters = nwb + 2;
+            fetch(0, raw);
             for (int it = 0; it < iters; it++) {
-                load_raw(2 * it, raw);
-                step1(raw, r1a);
-                load_raw(2 * it + 1, raw);
-                step1(raw, r1b);
+                convert(2 * it, raw, in); step1(in, r1a);
+                fetch(2 * it + 1, raw);
                 if (it >= 1) vblock(r1l, r1a, 0, qa);
+                convert(2 * it + 1, raw, in); step1(in, r1b);
+                fetch(2 * it + 2, raw);
                 vblock(r1a, r1b, 0, qb);
                 if (it >= 2) wblock4(it - 2, q0, q1, q2, qa);
 #pragma unroll
@@ -328,7 +438,7 @@ struct FtcWarp {
     }
 };
 
-template <int U, int D, typename TIN, typename TOUT>
+template <int U, int D, typename TIN, typename TOUT, int ACT>
 __global__ void __launch_bounds__(FTC_WARPS * 32)
 flr_tc_kernel(const __grid_constant__ FlrTcParams p)
 {
@@ -343,7 +453,7 @@ flr_tc_kernel(const __grid_constant__ FlrTcParams p)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long wid = (long long)blockIdx.x * FTC_WARPS + warp;
     if (wid >= p.total_warps) return;
-    FtcWarp<U, D, TIN, TOUT> w(p, lane);
+    FtcWarp<U, D, TIN, TOUT, ACT> w(p, lane);
     w.load_consts(tab);
     w.begin_strip(wid);
     w.run();
@@ -351,7 +461,7 @@ flr_tc_kernel(const __grid_constant__ FlrTcParams p)
 
 static int floor_mod(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
 
-template <int U, int D, typename TIN, typename TOUT>
+template <int U, int D, typename TIN, typename TOUT, int ACT>
 static int launch_tc(FlrTcParams& p, int N, cudaStream_t st)
 {
     p.strips = ceil_div(p.yw, 16);
@@ -369,19 +479,26 @@ static int launch_tc(FlrTcParams& p, int N, cudaStream_t st)
     p.total_warps = planes * p.strips * p.segs;
     const long long blocks = (p.total_warps + FTC_WARPS - 1) / FTC_WARPS;
     if (blocks > 0x7fffffffLL) { set_error("filtered_lrelu_tc: too many strips"); return AFCM_ERR_INVALID; }
-    flr_tc_kernel<U, D, TIN, TOUT><<<(unsigned)blocks, FTC_WARPS * 32, 0, st>>>(p);
+    flr_tc_kernel<U, D, TIN, TOUT, ACT><<<(unsigned)blocks, FTC_WARPS * 32, 0, st>>>(p);
     AFCM_LAUNCH_CHECK();
     count_launch();
     return AFCM_OK;
 }
 
-template <typename TIN, typename TOUT>
-static int dispatch_tc(FlrTcParams& p, int N, int up, int down, cudaStream_t st)
+template <typename TIN, typename TOUT, int ACT>
+static int dispatch_geo(FlrTcParams& p, int N, int up, int down, cudaStream_t st)
 {
-    if (up == 2 && down == 2) return launch_tc<2, 2, TIN, TOUT>(p, N, st);
-    if (up == 4 && down == 2) return launch_tc<4, 2, TIN, TOUT>(p, N, st);
-    if (up == 2 && down == 4) return launch_tc<2, 4, TIN, TOUT>(p, N, st);
+    if (up == 2 && down == 2) return launch_tc<2, 2, TIN, TOUT, ACT>(p, N, st);
+    if (up == 4 && down == 2) return launch_tc<4, 2, TIN, TOUT, ACT>(p, N, st);
+    if (up == 2 && down == 4) return launch_tc<2, 4, TIN, TOUT, ACT>(p, N, st);
     return AFCM_ERR_UNSUPPORTED;
+}
+
+template <typename TIN, typename TOUT>
+static int dispatch_act(FlrTcParams& p, int N, int up, int down, int act, cudaStream_t st)
+{
+    if (act == FTC_ACT_SAT) return dispatch_geo<TIN, TOUT, FTC_ACT_SAT>(p, N, up, down, st);
+    return dispatch_geo<TIN, TOUT, FTC_ACT_MINMAX>(p, N, up, down, st);
 }
 
 }  // namespace afcm
@@ -411,36 +528,47 @@ extern "C" int afcm_filtered_lrelu_tc(const void* x, const int64_t* xs, int x_dt
                   up, fu_taps, down, fd_taps);
         return AFCM_ERR_UNSUPPORTED;
     }
+    // the input is read as aligned column pairs (one 8- or 4-byte load per pair)
+    const uintptr_t pair_bytes = x_dtype == AFCM_F32 ? 8 : 4;
+    if ((xw & 1) || (xs[0] & 1) || (xs[1] & 1) || (xs[2] & 1) || ((uintptr_t)x % pair_bytes) != 0) {
+        set_error("filtered_lrelu_tc: x must have an even width, even strides and a pair-aligned base address");
+        return AFCM_ERR_UNSUPPORTED;
+    }
+    AFCM_CHECK_ARG(xs[2] >= 0 && xs[2] < (1ll << 28) && ys[2] >= 0 && ys[2] < (1ll << 28), "row strides out of range");
     FlrTcParams p;
     memset(&p, 0, sizeof(p));
     p.x = x; p.y = y; p.b = b; p.skip = skip;
-    p.xs_n = xs[0]; p.xs_c = xs[1]; p.xs_h = xs[2];
-    p.ys_n = ys[0]; p.ys_c = ys[1]; p.ys_h = ys[2];
+    p.xs_n = xs[0]; p.xs_c = xs[1]; p.xs_h = (int)xs[2];
+    p.ys_n = ys[0]; p.ys_c = ys[1]; p.ys_h = (int)ys[2];
     p.C = C; p.xh = xh; p.xw = xw; p.yh = yh; p.yw = yw;
     // phase shift s: the strip's first up-sampled sample is a multiple of `up` away from the padding origin;
-    // delta: one extra input column in front so that the fp32 pair loads are 8-byte aligned.
+    // delta: one extra input column in front so that the column pairs are aligned.
     p.sx = floor_mod(-px0, up);
     p.sy = floor_mod(-py0, up);
     int bx = (-p.sx - px0) / up;            // exact
     p.dx = (bx & 1) ? 1 : 0;
     p.ix0 = bx - p.dx;
     p.iy0 = (-p.sy - py0) / up;
-    p.slope = slope; p.slope_gt1 = slope > 1.f; p.out_scale = out_scale;
+    p.slope = slope; p.out_scale = out_scale;
+    // activation scale: R2 is computed in units of `clamp` when the sat() form applies
     const bool finite_clamp = clamp > 0.f && clamp < 3.0e38f;
-    p.sat_scale = finite_clamp ? 65504.f / clamp : 1.f;
+    int act = FTC_ACT_MINMAX;
+    float u_scale = 1.f;                    // R2 = x * gain * u_scale
+    if (finite_clamp && clamp <= 1024.f && clamp >= 1.f / 1024.f) { act = FTC_ACT_SAT; u_scale = 1.f / clamp; }
+    p.act_clamp = finite_clamp ? fminf(clamp, 65504.f) : 65504.f;
     for (int t = 0; t < fu_taps; t++) {
         const float f = fu_host[flip_filter ? t : fu_taps - 1 - t] * (float)up;
         p.kux[t] = f;
-        p.kuy[t] = f * gain * p.sat_scale;
+        p.kuy[t] = f * gain * u_scale;
     }
     for (int t = 0; t < fd_taps; t++) {
         const float f = fd_host[flip_filter ? t : fd_taps - 1 - t];
-        p.kdx[t] = f / p.sat_scale;
+        p.kdx[t] = f / u_scale;
         p.kdy[t] = f;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (x_dtype == AFCM_F32 && y_dtype == AFCM_F32) return dispatch_tc<float, float>(p, N, up, down, st);
-    if (x_dtype == AFCM_F32 && y_dtype == AFCM_F16) return dispatch_tc<float, __half>(p, N, up, down, st);
-    if (x_dtype == AFCM_F16 && y_dtype == AFCM_F32) return dispatch_tc<__half, float>(p, N, up, down, st);
-    return dispatch_tc<__half, __half>(p, N, up, down, st);
+    if (x_dtype == AFCM_F32 && y_dtype == AFCM_F32) return dispatch_act<float, float>(p, N, up, down, act, st);
+    if (x_dtype == AFCM_F32 && y_dtype == AFCM_F16) return dispatch_act<float, __half>(p, N, up, down, act, st);
+    if (x_dtype == AFCM_F16 && y_dtype == AFCM_F32) return dispatch_act<__half, float>(p, N, up, down, act, st);
+    return dispatch_act<__half, __half>(p, N, up, down, act, st);
 }

@@ -98,6 +98,46 @@ def _run_fused(x, fu, fd, b, si, up, down, px0, px1, py0, py1, sx, sy, gain, slo
     return y, so, 0
 
 
+def filtered_lrelu_tc(x, fu, fd, b=None, up=1, down=1, padding=0, gain=np.sqrt(2), slope=0.2, clamp=None,
+                      flip_filter=False, skip=None, out_scale=1.0, out_dtype=None, out=None):
+    """Tensor-core forward of filtered_lrelu (afcm_filtered_lrelu_tc, csrc/flr_tc.cu): same arguments and
+    result as filtered_lrelu() up to fp16 operand rounding (max |err| <= 2e-3 * max|y|).  Inference only (no
+    autograd, no sign tensor).  `skip` is added to the result and `out_scale` multiplies it (NET:376-377,
+    NET:699-700 fused); x may be float32 or float16, `out_dtype` selects the result type.  Returns None when
+    the geometry has no tensor-core kernel (the caller then uses filtered_lrelu())."""
+    _lib.require_cuda(x, fu, fd, b, skip)
+    L = _lib.lib()
+    px0, px1, py0, py1 = _parse_padding(padding)
+    fu_h, fu_n = _taps_1d(fu)
+    fd_h, fd_n = _taps_1d(fd)
+    if fu_h is False or fd_h is False or fu_h is None or fd_h is None:
+        return None
+    if x.dtype not in (torch.float32, torch.float16) or x.stride(3) != 1:
+        return None
+    if not ((up, down) in ((2, 2), (4, 2), (2, 4)) and fu_n == 6 * up and fd_n == 6 * down):
+        return None
+    out_dtype = out_dtype or x.dtype
+    N, C, xh, xw = x.shape
+    yh, yw = _lib._c.c_int(), _lib._c.c_int()
+    _lib.check(L.afcm_filtered_lrelu_out_size(xh, xw, up, down, fu_n, fd_n, px0, px1, py0, py1, yh, yw))
+    yh, yw = yh.value, yw.value
+    y = out if out is not None else torch.empty([N, C, yh, yw], dtype=out_dtype, device=x.device)
+    assert y.shape == (N, C, yh, yw) and y.dtype == out_dtype and y.stride(3) == 1
+    if b is not None:
+        b = b.detach().float().contiguous()
+    if skip is not None:
+        assert skip.shape == y.shape and skip.dtype == y.dtype and skip.stride() == y.stride()
+    clamp = float(clamp) if clamp is not None else float('inf')
+    nbytes = x.element_size() * x.numel() + y.element_size() * y.numel() * (2 if skip is not None else 1)
+    rc = _lib.timed('filtered_lrelu', nbytes, lambda: L.afcm_filtered_lrelu_tc(
+        _lib.ptr(x), _lib.i64x4(x.stride()), _lib.dtype_code(x.dtype), _lib.ptr(y), _lib.i64x4(y.stride()),
+        _lib.dtype_code(y.dtype), _lib.ptr(b), _lib.ptr(skip), N, C, xh, xw, yh, yw,
+        _lib.np_ptr(fu_h), fu_n, _lib.np_ptr(fd_h), fd_n, up, down, px0, px1, py0, py1,
+        float(gain), float(slope), clamp, float(out_scale), int(bool(flip_filter)), _lib.stream_ptr(x.device)))
+    _lib.check(rc, allow_unsupported=True)
+    return y if rc == 0 else None
+
+
 def _act_(y, si, sx, sy, gain, slope, clamp, write_signs):
     """In-place activation step of the generic composition (reference: filtered_lrelu_act_)."""
     L = _lib.lib()

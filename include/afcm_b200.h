@@ -83,6 +83,21 @@ int afcm_filtered_lrelu_sign_size(int yh, int yw, int down, int fd_taps, int* sh
 /* Tile override for tuning (0,0 = automatic).  Process-global, not part of the stable ABI. */
 int afcm_filtered_lrelu_set_tile(int tow, int toh);
 
+/* Tensor-core variant of afcm_filtered_lrelu (forward, no sign tensor): the four separable FIR passes run as
+ * banded-Toeplitz products on mma.sync (fp16 operands, fp32 accumulation) chained in registers
+ * (afcm_b200/csrc/flr_tc.cu).  Same semantics and argument meaning as afcm_filtered_lrelu; differences:
+ * x and y may have different dtypes (x_dtype / y_dtype in {AFCM_F32, AFCM_F16}); `b` is always float32;
+ * `skip` has y's dtype and strides; innermost strides must be 1.  Geometries: (up,down) in {(2,2),(4,2),(2,4)}
+ * with 6*up / 6*down taps; anything else returns AFCM_ERR_UNSUPPORTED.  Results differ from the fp32 op by the
+ * fp16 rounding of operands: max |err| <= 2e-3 * max|y| per call (tests/test_gpu_flr_tc.py). */
+int afcm_filtered_lrelu_tc(const void* x, const int64_t* xs, int x_dtype, void* y, const int64_t* ys, int y_dtype,
+                           const float* b, const void* skip,
+                           int N, int C, int xh, int xw, int yh, int yw,
+                           const float* fu_host, int fu_taps, const float* fd_host, int fd_taps,
+                           int up, int down, int px0, int px1, int py0, int py1,
+                           float gain, float slope, float clamp, float out_scale, int flip_filter,
+                           void* stream);
+
 /* filtered_lrelu_act_ -- replaces filtered_lrelu_plugin.filtered_lrelu_act_ (OPS/filtered_lrelu.cpp:213-290):
  * in-place gain / lrelu / clamp with optional sign write or read on a dense [planes,h,w] tensor.     */
 int afcm_filtered_lrelu_act(void* x, int dtype, int64_t planes, int h, int w,

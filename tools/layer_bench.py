@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from afcm_b200 import _lib  # noqa: E402
 from afcm_b200.networks_stylegan3 import afcm_generator  # noqa: E402
 from afcm_b200.torch_utils.ops import conv2d_gradfix  # noqa: E402
-from afcm_b200.torch_utils.ops.filtered_lrelu import _run_fused  # noqa: E402
+from afcm_b200.torch_utils.ops.filtered_lrelu import _run_fused, filtered_lrelu_tc  # noqa: E402
 
 
 def time_cuda(fn, iters=5, warmup=2, flush=None):
@@ -74,6 +74,19 @@ def main():
             row.update(flrelu_ms=ms, flrelu_gbs=nbytes / ms / 1e6, flrelu_frac=nbytes / ms / 1e6 / hbm)
             tot['flrelu_ms'] += ms; tot['flrelu_bytes'] += nbytes
             del x
+        if 'flrelu_tc' in ops and k == 3:
+            x = torch.randn(B, cout, Hc, Hc, device=dev)
+            b = torch.randn(cout, device=dev)
+            out_dt = torch.float16 if 'f16out' in ops else torch.float32
+            if 'f16in' in ops:
+                x = x.half()
+            fn = lambda: filtered_lrelu_tc(x, L.up_filter, L.down_filter, b, up=L.up_factor, down=L.down_factor,
+                                           padding=L.padding, gain=float(np.sqrt(2)), slope=0.2, clamp=256.0, out_dtype=out_dt)
+            ms = time_cuda(fn, flush=flush)
+            nbytes = 4.0 * B * cout * (Hc * Hc + out * out)
+            row.update(flrelu_tc_ms=ms, flrelu_tc_gbs=nbytes / ms / 1e6, flrelu_tc_frac=nbytes / ms / 1e6 / hbm)
+            tot['flrelu_tc_ms'] = tot.get('flrelu_tc_ms', 0.0) + ms; tot['flrelu_tc_bytes'] = tot.get('flrelu_tc_bytes', 0.0) + nbytes
+            del x
         flops = 2.0 * B * cout * cin * k * k * Hc * Hc
         tot['flops'] += flops
         if k == 3 and ('conv_tc' in ops or 'conv_f32' in ops):
@@ -105,6 +118,10 @@ def main():
         summ['flrelu_gbs'] = tot['flrelu_bytes'] / tot['flrelu_ms'] / 1e6
         summ['flrelu_frac_of_measured_hbm'] = summ['flrelu_gbs'] / hbm
         summ['flrelu_ms_per_slice'] = tot['flrelu_ms'] / B
+    if tot.get('flrelu_tc_ms'):
+        summ['flrelu_tc_gbs'] = tot['flrelu_tc_bytes'] / tot['flrelu_tc_ms'] / 1e6
+        summ['flrelu_tc_frac_of_measured_hbm'] = summ['flrelu_tc_gbs'] / hbm
+        summ['flrelu_tc_ms_per_slice'] = tot['flrelu_tc_ms'] / B
     if tot['conv_tc_ms']:
         summ['conv_tc_tflops'] = tot['flops'] / tot['conv_tc_ms'] / 1e9
         summ['conv_tc_frac_of_measured_bf16'] = summ['conv_tc_tflops'] / tf
