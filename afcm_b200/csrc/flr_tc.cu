@@ -42,6 +42,8 @@ namespace afcm {
 constexpr int FTC_WARPS = 4;
 constexpr int FTC_TAB = 192;          // tap tables: index t + 64, zero padded
 constexpr int FTC_TAB_OFS = 64;
+constexpr int FTC_STAGES = 4;         // per-warp shared-memory ring of input row blocks (cp.async)
+constexpr int FTC_PD = 3;             // prefetch distance in row blocks
 
 enum { FTC_ACT_SAT = 0, FTC_ACT_MINMAX = 1 };
 
@@ -126,6 +128,16 @@ __device__ __forceinline__ uint32_t h2_min(uint32_t a, uint32_t b)
     return r;
 }
 
+// 8- or 4-byte asynchronous global -> shared copy; src_bytes == 0 zero-fills without reading
+template <int BYTES>
+__device__ __forceinline__ void cp_async(uint32_t dst, const void* src, int src_bytes)
+{
+    if (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <typename T> struct Pair;
 template <> struct Pair<float> { typedef float2 type; };
 template <> struct Pair<__half> { typedef uint32_t type; };
@@ -140,16 +152,19 @@ struct FtcWarp {
     const FlrTcParams& p;
     int g, t;
     // strip state
-    const TIN* xg;               // plane base + g rows
-    const TIN* xc0;              // xg + first column pair of the strip (interior strips: chunk c at +8c)
+    const TIN* xc0;              // plane base + g rows + first column pair of the strip (chunk c at +8c)
+    uint32_t ring;               // shared-memory address of this lane's slot in stage 0, chunk 0
+    int ix;                      // first input column of the strip
     TOUT* yt;                    // plane base + (w0 + 2t) rows + k0 + g
     long long kofs;              // skip - y (elements), valid when has_skip
     bool has_skip;
     float bias;
     int iy, k0, w0, nwb;
-    int coff[Geo::NC];           // element offset of the chunk's column pair inside a row (clamped into the row)
-    unsigned cmask;              // bit c: the chunk's column pair is inside the plane
-    bool cols_all;               // every lane of the warp has every chunk inside the plane
+    bool interior;               // every input column this strip reads and every output column it writes exists
+    static constexpr int RAW_BYTES = (int)sizeof(RawT);
+    static constexpr int CHUNK_BYTES = 32 * RAW_BYTES;               // one chunk of one row block, all lanes
+    static constexpr int STAGE_BYTES = Geo::NC * CHUNK_BYTES;
+    static constexpr int WARP_RING_BYTES = FTC_STAGES * STAGE_BYTES;
 
     __device__ FtcWarp(const FlrTcParams& p_, int lane) : p(p_), g(lane >> 2), t(lane & 3) {}
 
@@ -202,12 +217,12 @@ struct FtcWarp {
         const int seg = (int)(r % p.segs);
         const long long plane = r / p.segs;
         const int n = (int)(plane / p.C), c = (int)(plane - (long long)n * p.C);
-        xg = (const TIN*)p.x + n * p.xs_n + c * p.xs_c + (long long)g * p.xs_h;
+        const TIN* xg = (const TIN*)p.x + n * p.xs_n + c * p.xs_c + (long long)g * p.xs_h;
         has_skip = p.skip != nullptr;
         kofs = has_skip ? (const TOUT*)p.skip - (const TOUT*)p.y : 0;
         bias = p.b ? p.b[c] : 0.f;
         h_bias = pack_h2(bias, bias);
-        const int ix = strip * Geo::IXS + p.ix0;
+        ix = strip * Geo::IXS + p.ix0;
         iy = seg * p.iy_step + p.iy0;
         k0 = strip * 16;
         w0 = seg * p.seg_wblocks * 8;
@@ -216,33 +231,45 @@ struct FtcWarp {
         const int rows_left = p.yh - w0;
         nwb = (rows_left + 7) >> 3;
         if (nwb > p.seg_wblocks) nwb = p.seg_wblocks;
-        cmask = 0;
         // ix and xw are even (host-checked), so a column pair is either inside or outside the plane as a whole
+        interior = __all_sync(0xffffffffu, col_mask() == (1u << Geo::NC) - 1u) && k0 + 16 <= p.yw;
+    }
+
+    // bit c: this lane's column pair of chunk c lies inside the plane
+    __device__ __forceinline__ unsigned col_mask() const
+    {
+        unsigned m = 0;
 #pragma unroll
         for (int c8 = 0; c8 < Geo::NC; c8++) {
             const int col = ix + 8 * c8 + 2 * t;
-            const bool ok = col >= 0 && col < p.xw;
-            if (ok) cmask |= 1u << c8;
-            coff[c8] = ok ? col : 0;
+            if (col >= 0 && col < p.xw) m |= 1u << c8;
         }
-        cols_all = __all_sync(0xffffffffu, cmask == (1u << Geo::NC) - 1u);
+        return m;
     }
 
-    // ---- input: issue the loads of one block of 8 input rows (this thread: row g, NC column pairs).
-    // Addresses are clamped into the plane, so the loads are unconditional; convert() zeroes what was outside.
-    __device__ __forceinline__ void fetch(int yb, RawT (&raw)[Geo::NC]) const
+    // ---- input: issue the asynchronous copies of one block of 8 input rows into the ring (this thread: row g,
+    // NC column pairs).  EDGE: rows / columns outside the plane are zero-filled (src size 0, address clamped).
+    template <bool EDGE>
+    __device__ __forceinline__ void fetch(int yb) const
     {
         const int row0 = iy + 8 * yb;
-        if (cols_all && row0 >= 0 && row0 + 8 <= p.xh) {                // warp-uniform: interior block
-            const TIN* rp = xc0 + (long long)row0 * p.xs_h;
+        const uint32_t dst = ring + (uint32_t)((yb & (FTC_STAGES - 1)) * STAGE_BYTES);
+        if (!EDGE) {
+            const TIN* rp = xc0 + row0 * p.xs_h;
 #pragma unroll
-            for (int c8 = 0; c8 < Geo::NC; c8++) raw[c8] = *reinterpret_cast<const RawT*>(rp + 8 * c8);
+            for (int c8 = 0; c8 < Geo::NC; c8++) cp_async<RAW_BYTES>(dst + c8 * CHUNK_BYTES, rp + 8 * c8, RAW_BYTES);
         } else {
-            const int row = max(-g, min(row0, p.xh - 1 - g));           // row + g clamped into [0, xh)
-            const TIN* rp = xg + (long long)row * p.xs_h;
+            const int row = row0 + g;
+            const bool rok = row >= 0 && row < p.xh;
+            const TIN* rp = xc0 + (rok ? row0 : -g) * p.xs_h - (ix + 2 * t);          // start of a valid row
 #pragma unroll
-            for (int c8 = 0; c8 < Geo::NC; c8++) raw[c8] = *reinterpret_cast<const RawT*>(rp + coff[c8]);
+            for (int c8 = 0; c8 < Geo::NC; c8++) {
+                const int col = ix + 8 * c8 + 2 * t;
+                const bool ok = rok && col >= 0 && col < p.xw;
+                cp_async<RAW_BYTES>(dst + c8 * CHUNK_BYTES, rp + (ok ? col : 0), ok ? RAW_BYTES : 0);
+            }
         }
+        cp_async_commit();
     }
     __device__ __forceinline__ uint32_t cvt_pair(const float2& v) const { return pack_h2(v.x + bias, v.y + bias); }
     __device__ __forceinline__ uint32_t cvt_pair(const uint32_t& v) const
@@ -251,15 +278,32 @@ struct FtcWarp {
         asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(h_bias));
         return r;
     }
-    __device__ __forceinline__ void convert(int yb, const RawT (&raw)[Geo::NC], uint32_t (&in)[Geo::NC]) const
+    // wait until row block yb has landed (at most FTC_PD - 1 younger groups may still be in flight), read this
+    // lane's pairs back, add the bias and round to fp16.  EDGE: pairs outside the plane stay zero (no bias there).
+    template <bool EDGE>
+    __device__ __forceinline__ void convert(int yb, uint32_t (&in)[Geo::NC]) const
     {
-        const int row0 = iy + 8 * yb;
-        if (cols_all && row0 >= 0 && row0 + 8 <= p.xh) {                // warp-uniform: interior block
+        cp_async_wait<FTC_PD - 1>();
+        const uint32_t src = ring + (uint32_t)((yb & (FTC_STAGES - 1)) * STAGE_BYTES);
+        RawT raw[Geo::NC];
+#pragma unroll
+        for (int c8 = 0; c8 < Geo::NC; c8++) {
+            if (RAW_BYTES == 8) {
+                float2 v;
+                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(src + c8 * CHUNK_BYTES) : "memory");
+                raw[c8] = *reinterpret_cast<RawT*>(&v);
+            } else {
+                uint32_t v;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(src + c8 * CHUNK_BYTES) : "memory");
+                raw[c8] = *reinterpret_cast<RawT*>(&v);
+            }
+        }
+        if (!EDGE) {
 #pragma unroll
             for (int c8 = 0; c8 < Geo::NC; c8++) in[c8] = cvt_pair(raw[c8]);
         } else {
-            const int row = row0 + g;
-            const unsigned m = (row >= 0 && row < p.xh) ? cmask : 0u;
+            const int row = iy + 8 * yb + g;
+            const unsigned m = (row >= 0 && row < p.xh) ? col_mask() : 0u;
 #pragma unroll
             for (int c8 = 0; c8 < Geo::NC; c8++) in[c8] = ((m >> c8) & 1u) ? cvt_pair(raw[c8]) : 0u;
         }
@@ -318,19 +362,22 @@ struct FtcWarp {
         a5[0] = c0[0]; a5[1] = c0[1]; a5[2] = c1[0]; a5[3] = c1[1];
     }
 
+    // out_scale is folded into the Td_y taps; a skip tensor is added as skip * out_scale
+    template <bool EDGE>
     __device__ __forceinline__ void store(int wb, const float (&c)[4]) const
     {
-        TOUT* q0 = yt + (long long)(8 * wb) * p.ys_h;                   // (row 2t, col g) of this block
-        TOUT* q1 = q0 + p.ys_h;
+        const int o = 8 * wb * p.ys_h;
+        TOUT* q0 = yt + o;                                              // (row 2t, col g) of this block
+        TOUT* q1 = yt + (o + p.ys_h);
         float v[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) v[i] = c[i];
-        if (w0 + 8 * wb + 8 <= p.yh && k0 + 16 <= p.yw) {               // warp-uniform: interior block
+        if (!EDGE) {
             if (has_skip) {
-                v[0] += (float)q0[kofs]; v[1] += (float)q1[kofs]; v[2] += (float)q0[kofs + 8]; v[3] += (float)q1[kofs + 8];
+                v[0] += (float)q0[kofs] * p.out_scale; v[1] += (float)q1[kofs] * p.out_scale;
+                v[2] += (float)q0[kofs + 8] * p.out_scale; v[3] += (float)q1[kofs + 8] * p.out_scale;
             }
-            q0[0] = (TOUT)(v[0] * p.out_scale); q1[0] = (TOUT)(v[1] * p.out_scale);
-            q0[8] = (TOUT)(v[2] * p.out_scale); q1[8] = (TOUT)(v[3] * p.out_scale);
+            q0[0] = (TOUT)v[0]; q1[0] = (TOUT)v[1]; q0[8] = (TOUT)v[2]; q1[8] = (TOUT)v[3];
         } else {
             const int y0 = w0 + 8 * wb + 2 * t;
 #pragma unroll
@@ -338,21 +385,23 @@ struct FtcWarp {
                 const int yy = y0 + (i & 1), xx = k0 + g + (i >> 1) * 8;
                 if (yy < p.yh && xx < p.yw) {
                     TOUT* q = ((i & 1) ? q1 : q0) + (i >> 1) * 8;
-                    if (has_skip) v[i] += (float)q[kofs];
-                    *q = (TOUT)(v[i] * p.out_scale);
+                    if (has_skip) v[i] += (float)q[kofs] * p.out_scale;
+                    *q = (TOUT)v[i];
                 }
             }
         }
     }
 
     // (5) one block of 8 output rows from NB5 consecutive chunks of R3
+    template <bool EDGE>
     __device__ __forceinline__ void wblock2(int wb, const uint32_t (&c0)[4], const uint32_t (&c1)[4]) const
     {
         float c[4] = {0.f, 0.f, 0.f, 0.f};
         mma_f(c, c0, b5[0][0], b5[0][1]);
         mma_f(c, c1, b5[1][0], b5[1][1]);
-        store(wb, c);
+        store<EDGE>(wb, c);
     }
+    template <bool EDGE>
     __device__ __forceinline__ void wblock4(int wb, const uint32_t (&c0)[4], const uint32_t (&c1)[4], const uint32_t (&c2)[4],
                                             const uint32_t (&c3)[4]) const
     {
@@ -361,85 +410,153 @@ struct FtcWarp {
         mma_f(c, c1, b5[1][0], b5[1][1]);
         mma_f(c, c2, b5[Geo::NB5 - 2][0], b5[Geo::NB5 - 2][1]);
         mma_f(c, c3, b5[Geo::NB5 - 1][0], b5[Geo::NB5 - 1][1]);
-        store(wb, c);
+        store<EDGE>(wb, c);
+    }
+
+    // ---- per-geometry pipelines.  Every strip runs  [0, lo) with EDGE handling, [lo, hi) without (all input
+    // rows / columns read and all outputs written by those iterations are inside the planes), [hi, iters) with.
+    static __device__ __forceinline__ int fdiv8(int a) { return a >> 3; }                 // floor(a / 8)
+
+    // U == 2, D == 2.  iteration it: input block it -> R1[it]; v-block it-1 from R1[it-1], R1[it];
+    // w-block it-2 from chunks it-2, it-1.
+    template <bool EDGE>
+    __device__ __forceinline__ void iter22(int it, uint32_t (&r1p)[Geo::NJ8], uint32_t (&r1c)[Geo::NJ8],
+                                           uint32_t (&a5p)[4], uint32_t (&a5c)[4]) const
+    {
+        uint32_t in[Geo::NC];
+        convert<EDGE>(it, in); step1(in, r1c); fetch<EDGE>(it + FTC_PD);
+        if (!EDGE || it >= 1) vblock(r1p, r1c, 0, a5c);
+        if (!EDGE || it >= 2) wblock2<EDGE>(it - 2, a5p, a5c);
+    }
+    __device__ void run22()
+    {
+        uint32_t r1a[Geo::NJ8], r1b[Geo::NJ8], a5a[4], a5b[4];
+        const int iters = nwb + 2;
+        int lo = 0, hi = 0;
+        if (interior) {
+            lo = max(2, fdiv8(-iy + 7));
+            hi = min(min(fdiv8(p.xh - 8 - iy) - FTC_PD, fdiv8(p.yh - w0) + 1) + 1, iters);
+        }
+        if (hi < lo) hi = lo = 0;
+        hi = lo + ((hi - lo) & ~1);                                     // the steady loop is unrolled by two
+        int it = 0;
+        for (; it < (hi > lo ? lo : iters); it++) {
+            iter22<true>(it, r1a, r1b, a5a, a5b);
+#pragma unroll
+            for (int i = 0; i < Geo::NJ8; i++) r1a[i] = r1b[i];
+#pragma unroll
+            for (int i = 0; i < 4; i++) a5a[i] = a5b[i];
+        }
+        if (hi > lo) {
+            for (; it < hi; it += 2) {                                  // "previous" buffers alternate, no copies
+                iter22<false>(it, r1a, r1b, a5a, a5b);
+                iter22<false>(it + 1, r1b, r1a, a5b, a5a);
+            }
+            for (; it < iters; it++) {
+                iter22<true>(it, r1a, r1b, a5a, a5b);
+#pragma unroll
+                for (int i = 0; i < Geo::NJ8; i++) r1a[i] = r1b[i];
+#pragma unroll
+                for (int i = 0; i < 4; i++) a5a[i] = a5b[i];
+            }
+        }
+    }
+
+    // U == 4, D == 2.  iteration it: input block it; v-blocks 2it-2, 2it-1 (two phases) from R1[it-1], R1[it];
+    // w-block 2it-3 from chunks (2it-3, 2it-2), w-block 2it-2 from chunks (2it-2, 2it-1)
+    template <bool EDGE>
+    __device__ __forceinline__ void iter42(int it, uint32_t (&r1p)[Geo::NJ8], uint32_t (&r1c)[Geo::NJ8], uint32_t (&a5l)[4]) const
+    {
+        uint32_t in[Geo::NC], a5a[4], a5b[4];
+        convert<EDGE>(it, in); step1(in, r1c); fetch<EDGE>(it + FTC_PD);
+        if (!EDGE || it >= 1) {
+            vblock(r1p, r1c, 0, a5a);
+            vblock(r1p, r1c, Geo::NPH - 1, a5b);
+            if (!EDGE || (it >= 2 && 2 * it - 3 < nwb)) wblock2<EDGE>(2 * it - 3, a5l, a5a);
+            if (!EDGE || 2 * it - 2 < nwb) wblock2<EDGE>(2 * it - 2, a5a, a5b);
+#pragma unroll
+            for (int i = 0; i < 4; i++) a5l[i] = a5b[i];
+        }
+    }
+    __device__ void run42()
+    {
+        uint32_t r1a[Geo::NJ8], r1b[Geo::NJ8], a5l[4];
+        const int iters = (nwb + 2) / 2 + 1;
+        int lo = 0, hi = 0;
+        if (interior) {
+            lo = max(2, fdiv8(-iy + 7));
+            hi = min(min(fdiv8(p.xh - 8 - iy) - FTC_PD, (fdiv8(p.yh - w0) + 1) >> 1) + 1, iters);
+        }
+        if (hi < lo) hi = lo = 0;
+        hi = lo + ((hi - lo) & ~1);
+        int it = 0;
+        for (; it < (hi > lo ? lo : iters); it++) {
+            iter42<true>(it, r1a, r1b, a5l);
+#pragma unroll
+            for (int i = 0; i < Geo::NJ8; i++) r1a[i] = r1b[i];
+        }
+        if (hi > lo) {
+            for (; it < hi; it += 2) {
+                iter42<false>(it, r1a, r1b, a5l);
+                iter42<false>(it + 1, r1b, r1a, a5l);
+            }
+            for (; it < iters; it++) {
+                iter42<true>(it, r1a, r1b, a5l);
+#pragma unroll
+                for (int i = 0; i < Geo::NJ8; i++) r1a[i] = r1b[i];
+            }
+        }
+    }
+
+    // U == 2, D == 4.  iteration it: input blocks 2it, 2it+1; v-block 2it-1 from R1[2it-1], R1[2it];
+    // v-block 2it from R1[2it], R1[2it+1]; w-block it-2 from chunks 2it-4 .. 2it-1
+    template <bool EDGE>
+    __device__ __forceinline__ void iter24(int it, uint32_t (&r1l)[Geo::NJ8], uint32_t (&q0)[4], uint32_t (&q1)[4],
+                                           uint32_t (&q2)[4]) const
+    {
+        uint32_t in[Geo::NC], r1a[Geo::NJ8], r1b[Geo::NJ8], qa[4], qb[4];
+        convert<EDGE>(2 * it, in); step1(in, r1a); fetch<EDGE>(2 * it + FTC_PD);
+        if (!EDGE || it >= 1) vblock(r1l, r1a, 0, qa);
+        convert<EDGE>(2 * it + 1, in); step1(in, r1b); fetch<EDGE>(2 * it + 1 + FTC_PD);
+        vblock(r1a, r1b, 0, qb);
+        if (!EDGE || it >= 2) wblock4<EDGE>(it - 2, q0, q1, q2, qa);
+#pragma unroll
+        for (int i = 0; i < 4; i++) { q0[i] = q2[i]; q1[i] = qa[i]; q2[i] = qb[i]; }
+#pragma unroll
+        for (int i = 0; i < Geo::NJ8; i++) r1l[i] = r1b[i];
+    }
+    __device__ void run24()
+    {
+        uint32_t r1l[Geo::NJ8], q0[4], q1[4], q2[4];
+        const int iters = nwb + 2;
+        int lo = 0, hi = 0;
+        if (interior) {
+            lo = max(2, (-iy + 15) >> 4);
+            hi = min(min((fdiv8(p.xh - 8 - iy) - FTC_PD - 1) >> 1, fdiv8(p.yh - w0) + 1) + 1, iters);
+        }
+        if (hi < lo) hi = lo = 0;
+        int it = 0;
+        for (; it < (hi > lo ? lo : iters); it++) iter24<true>(it, r1l, q0, q1, q2);
+        if (hi > lo) {
+            for (; it < hi; it++) iter24<false>(it, r1l, q0, q1, q2);
+            for (; it < iters; it++) iter24<true>(it, r1l, q0, q1, q2);
+        }
     }
 
     __device__ void run()
     {
-        RawT raw[Geo::NC];
-        uint32_t in[Geo::NC];
-        if (U == 2 && D == 2) {
-            // iteration it: input block it -> R1[it]; v-block it-1 from R1[it-1], R1[it]; w-block it-2 from chunks it-2, it-1.
-            // Unrolled by two so that the "previous" buffers alternate instead of being copied.
-            uint32_t r1a[Geo::NJ8], r1b[Geo::NJ8], a5a[4], a5b[4];
-            const int iters = nwb + 2;                                  // >= 3
-            fetch(0, raw);
-            convert(0, raw, in); step1(in, r1a);
-            fetch(1, raw);
-            convert(1, raw, in); step1(in, r1b);
-            fetch(2, raw);
-            vblock(r1a, r1b, 0, a5b);
-            int it = 2;
-            for (; it + 1 < iters; it += 2) {
-                convert(it, raw, in); step1(in, r1a);
-                fetch(it + 1, raw);
-                vblock(r1b, r1a, 0, a5a);
-                wblock2(it - 2, a5b, a5a);
-                convert(it + 1, raw, in); step1(in, r1b);
-                fetch(it + 2, raw);
-                vblock(r1a, r1b, 0, a5b);
-                wblock2(it - 1, a5a, a5b);
-            }
-            if (it < iters) {
-                convert(it, raw, in); step1(in, r1a);
-                vblock(r1b, r1a, 0, a5a);
-                wblock2(it - 2, a5b, a5a);
-            }
-        } else if (U == 4 && D == 2) {
-            // iteration it: input block it; v-blocks 2it-2, 2it-1 (two phases) from R1[it-1], R1[it];
-            // w-block 2it-3 from chunks (2it-3, 2it-2), w-block 2it-2 from chunks (2it-2, 2it-1)
-            uint32_t r1p[Geo::NJ8], r1c[Geo::NJ8], a5l[4], a5a[4], a5b[4];
-            const int iters = (nwb + 2) / 2 + 1;
-            fetch(0, raw);
-            for (int it = 0; it < iters; it++) {
-                convert(it, raw, in); step1(in, r1c);
-                fetch(it + 1, raw);
-                if (it >= 1) {
-                    vblock(r1p, r1c, 0, a5a);
-                    vblock(r1p, r1c, Geo::NPH - 1, a5b);
-                    if (it >= 2 && 2 * it - 3 < nwb) wblock2(2 * it - 3, a5l, a5a);
-                    if (2 * it - 2 < nwb) wblock2(2 * it - 2, a5a, a5b);
+        // the ring is primed with edge handling; these row blocks precede the steady range anyway
 #pragma unroll
-                    for (int i = 0; i < 4; i++) a5l[i] = a5b[i];
-                }
-#pragma unroll
-                for (int i = 0; i < Geo::NJ8; i++) r1p[i] = r1c[i];
-            }
-        } else {
-            // U == 2, D == 4.  iteration it: input blocks 2it, 2it+1; v-block 2it-1 from R1[2it-1], R1[2it];
-            // v-block 2it from R1[2it], R1[2it+1]; w-block it-2 from chunks 2it-4 .. 2it-1
-            uint32_t r1l[Geo::NJ8], r1a[Geo::NJ8], r1b[Geo::NJ8], q0[4], q1[4], q2[4], qa[4], qb[4];
-            const int iters = nwb + 2;
-            fetch(0, raw);
-            for (int it = 0; it < iters; it++) {
-                convert(2 * it, raw, in); step1(in, r1a);
-                fetch(2 * it + 1, raw);
-                if (it >= 1) vblock(r1l, r1a, 0, qa);
-                convert(2 * it + 1, raw, in); step1(in, r1b);
-                fetch(2 * it + 2, raw);
-                vblock(r1a, r1b, 0, qb);
-                if (it >= 2) wblock4(it - 2, q0, q1, q2, qa);
-#pragma unroll
-                for (int i = 0; i < 4; i++) { q0[i] = q2[i]; q1[i] = qa[i]; q2[i] = qb[i]; }
-#pragma unroll
-                for (int i = 0; i < Geo::NJ8; i++) r1l[i] = r1b[i];
-            }
-        }
+        for (int i = 0; i < FTC_PD; i++) fetch<true>(i);
+        if (U == 2 && D == 2) run22();
+        else if (U == 4 && D == 2) run42();
+        else run24();
+        cp_async_wait<0>();
     }
 };
 
 template <int U, int D, typename TIN, typename TOUT, int ACT>
-__global__ void __launch_bounds__(FTC_WARPS * 32)
+__global__ void __launch_bounds__(FTC_WARPS * 32, (U == 2 && D == 4) ? 3 : (U == 4 ? 5 : 6))
 flr_tc_kernel(const __grid_constant__ FlrTcParams p)
 {
     __shared__ float tab[4][FTC_TAB];
@@ -453,7 +570,10 @@ flr_tc_kernel(const __grid_constant__ FlrTcParams p)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long wid = (long long)blockIdx.x * FTC_WARPS + warp;
     if (wid >= p.total_warps) return;
-    FtcWarp<U, D, TIN, TOUT, ACT> w(p, lane);
+    extern __shared__ __align__(16) uint8_t ring_smem[];
+    typedef FtcWarp<U, D, TIN, TOUT, ACT> W;
+    W w(p, lane);
+    w.ring = (uint32_t)__cvta_generic_to_shared(ring_smem) + (uint32_t)(warp * W::WARP_RING_BYTES + lane * W::RAW_BYTES);
     w.load_consts(tab);
     w.begin_strip(wid);
     w.run();
@@ -479,7 +599,8 @@ static int launch_tc(FlrTcParams& p, int N, cudaStream_t st)
     p.total_warps = planes * p.strips * p.segs;
     const long long blocks = (p.total_warps + FTC_WARPS - 1) / FTC_WARPS;
     if (blocks > 0x7fffffffLL) { set_error("filtered_lrelu_tc: too many strips"); return AFCM_ERR_INVALID; }
-    flr_tc_kernel<U, D, TIN, TOUT, ACT><<<(unsigned)blocks, FTC_WARPS * 32, 0, st>>>(p);
+    const int smem = FTC_WARPS * FtcWarp<U, D, TIN, TOUT, ACT>::WARP_RING_BYTES;
+    flr_tc_kernel<U, D, TIN, TOUT, ACT><<<(unsigned)blocks, FTC_WARPS * 32, smem, st>>>(p);
     AFCM_LAUNCH_CHECK();
     count_launch();
     return AFCM_OK;
@@ -534,7 +655,8 @@ extern "C" int afcm_filtered_lrelu_tc(const void* x, const int64_t* xs, int x_dt
         set_error("filtered_lrelu_tc: x must have an even width, even strides and a pair-aligned base address");
         return AFCM_ERR_UNSUPPORTED;
     }
-    AFCM_CHECK_ARG(xs[2] >= 0 && xs[2] < (1ll << 28) && ys[2] >= 0 && ys[2] < (1ll << 28), "row strides out of range");
+    AFCM_CHECK_ARG(xs[2] >= 0 && ys[2] >= 0 && (long long)(xh + 64) * xs[2] < (1ll << 31) && (long long)(yh + 64) * ys[2] < (1ll << 31),
+                   "row strides out of range");
     FlrTcParams p;
     memset(&p, 0, sizeof(p));
     p.x = x; p.y = y; p.b = b; p.skip = skip;
@@ -564,7 +686,7 @@ extern "C" int afcm_filtered_lrelu_tc(const void* x, const int64_t* xs, int x_dt
     for (int t = 0; t < fd_taps; t++) {
         const float f = fd_host[flip_filter ? t : fd_taps - 1 - t];
         p.kdx[t] = f / u_scale;
-        p.kdy[t] = f;
+        p.kdy[t] = f * out_scale;
     }
     cudaStream_t st = (cudaStream_t)stream;
     if (x_dtype == AFCM_F32 && y_dtype == AFCM_F32) return dispatch_act<float, float>(p, N, up, down, act, st);
