@@ -56,6 +56,7 @@ struct FlrTcParams {
     long long total_warps;
     int ix0, iy0, iy_step;                                // input origin: col = strip*IXS + ix0, row = seg*iy_step + iy0
     int sx, sy, dx;
+    int y_pairs;                                          // y (and skip) rows are pair aligned: vector stores allowed
     float slope, out_scale, act_clamp;                    // act_clamp: clamp in the units of R2 (MINMAX mode)
     float kux[24], kuy[24], kdx[24], kdy[24];             // correlation-form taps (kuy, kdx carry gain and the clamp scale)
 };
@@ -146,8 +147,13 @@ template <int U, int D, typename TIN, typename TOUT, int ACT>
 struct FtcWarp {
     using Geo = FtcGeo<U, D>;
     using RawT = typename Pair<TIN>::type;
+    using OutPair = typename Pair<TOUT>::type;
+    static constexpr int MB = Geo::KC4;            // 16-wide blocks of up-sampled columns
+    static constexpr int JB = 2 * MB;              // 8-wide blocks of up-sampled columns
+    static constexpr int NAL = D / 2;              // 16-row chunks of up-sampled rows per window of 8 output rows
+    static constexpr int NREL = D;                 // 16-column chunks of up-sampled columns per 8 output columns
     // constant fragments (the FIR taps)
-    uint32_t a1[Geo::NPH][4], a2[Geo::NPH][4], a4[Geo::KC4][4], b5[Geo::NB5][2];
+    uint32_t a1[Geo::NPH][4], b2[U][2], a3[NAL][4], b4[NREL][2];
     uint32_t h_one, h_nslope, h_slope, h_cl, h_ncl, h_bias;
     const FlrTcParams& p;
     int g, t;
@@ -155,9 +161,7 @@ struct FtcWarp {
     const TIN* xc0;              // plane base + g rows + first column pair of the strip (chunk c at +8c)
     uint32_t ring;               // shared-memory address of this lane's slot in stage 0, chunk 0
     int ix;                      // first input column of the strip
-    TOUT* yt;                    // plane base + (w0 + 2t) rows + k0 + g
-    long long kofs;              // skip - y (elements), valid when has_skip
-    bool has_skip;
+    TOUT* yt;                    // plane base + (w0 + g) rows + k0 + 2t
     float bias;
     int iy, k0, w0, nwb;
     bool interior;               // every input column this strip reads and every output column it writes exists
@@ -165,6 +169,11 @@ struct FtcWarp {
     static constexpr int CHUNK_BYTES = 32 * RAW_BYTES;               // one chunk of one row block, all lanes
     static constexpr int STAGE_BYTES = Geo::NC * CHUNK_BYTES;
     static constexpr int WARP_RING_BYTES = FTC_STAGES * STAGE_BYTES;
+    // pipeline state.  Strip-local coordinates: X / Y input column / row, J / V up-sampled column / row,
+    // K / W output column / row;   up_x[J] = sum_X kux[(X - dx) U - J] in[X],   up_y[V] = sum_Y kuy[U Y - V] in[Y],
+    // out_x[K] = sum_J kdx[J - D K - sx] a[J],   out_y[W] = sum_V kdy[V - D W - sy] a[V].
+    uint32_t P[2][MB][2];        // R1 of the last two input row blocks (slot = block & 1): D-fragments [J 16][Y 8]
+    uint32_t carry[JB];          // lower half (rows +8..+15) of the last window of R3
 
     __device__ FtcWarp(const FlrTcParams& p_, int lane) : p(p_), g(lane >> 2), t(lane & 3) {}
 
@@ -177,30 +186,38 @@ struct FtcWarp {
 #pragma unroll
             for (int r = 0; r < 4; r++) {
                 const int row = g + (r & 1) * 8, col = 2 * t + (r >> 1) * 8;
-                // Tu[row, col] = ku[(col - delta) * U - 16 * ph - row]
+                // (1) A[m = J, k = X] = kux[(X - dx) U - J];  window phase ph: J = 16 ph + row (U == 4)
                 const int ex = (col - p.dx) * U - 16 * ph - row;
-                const int ey = col * U - 16 * ph - row;
                 a1[ph][r] = pack_h2(tux[ex], tux[ex + U]);
-                a2[ph][r] = pack_h2(tuy[ey], tuy[ey + U]);
             }
         }
 #pragma unroll
-        for (int kc = 0; kc < Geo::KC4; kc++) {
+        for (int nb = 0; nb < U; nb++) {
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                // (2) B[k = Y, n = V] = kuy[U Y - V],  Y = 2t + 8r + {0,1} in the 16-row window, V = 8 nb + g
+                const int e = U * (2 * t + 8 * r) - 8 * nb - g;
+                b2[nb][r] = pack_h2(tuy[e], tuy[e + U]);
+            }
+        }
+#pragma unroll
+        for (int al = 0; al < NAL; al++) {
 #pragma unroll
             for (int r = 0; r < 4; r++) {
                 const int row = g + (r & 1) * 8, col = 2 * t + (r >> 1) * 8;
-                // Td_x[row = k, col = j] = kd[16 kc + col - row * D - sx]
-                const int e = 16 * kc + col - row * D - p.sx;
-                a4[kc][r] = pack_h2(tdx[e], tdx[e + 1]);
+                // (3) A[m = W, k = V] = kdy[V - D W - sy] for chunk `al` of the window: V = 16 al + col (+ window
+                // origin), W = row - 8 (+ the same origin / D)
+                const int e = 16 * al + col - D * row + 8 * D - p.sy;
+                a3[al][r] = pack_h2(tdy[e], tdy[e + 1]);
             }
         }
 #pragma unroll
-        for (int q = 0; q < Geo::NB5; q++) {
+        for (int rel = 0; rel < NREL; rel++) {
 #pragma unroll
             for (int r = 0; r < 2; r++) {
-                // B[k = v, n = w] = kd[16 q + k - n * D - sy],  k = 2t + 8r + {0,1},  n = g
-                const int e = 16 * q + 2 * t + 8 * r - g * D - p.sy;
-                b5[q][r] = pack_h2(tdy[e], tdy[e + 1]);
+                // (4) B[k = J, n = K] = kdx[J - D K - sx],  J = 16 rel + 2t + 8r + {0,1} (+ 8 D nb), K = g (+ 8 nb)
+                const int e = 16 * rel + 2 * t + 8 * r - D * g - p.sx;
+                b4[rel][r] = pack_h2(tdx[e], tdx[e + 1]);
             }
         }
         h_one = pack_h2(1.f, 1.f);
@@ -218,21 +235,23 @@ struct FtcWarp {
         const long long plane = r / p.segs;
         const int n = (int)(plane / p.C), c = (int)(plane - (long long)n * p.C);
         const TIN* xg = (const TIN*)p.x + n * p.xs_n + c * p.xs_c + (long long)g * p.xs_h;
-        has_skip = p.skip != nullptr;
-        kofs = has_skip ? (const TOUT*)p.skip - (const TOUT*)p.y : 0;
         bias = p.b ? p.b[c] : 0.f;
         h_bias = pack_h2(bias, bias);
         ix = strip * Geo::IXS + p.ix0;
         iy = seg * p.iy_step + p.iy0;
         k0 = strip * 16;
         w0 = seg * p.seg_wblocks * 8;
-        yt = (TOUT*)p.y + n * p.ys_n + c * p.ys_c + (long long)(w0 + 2 * t) * p.ys_h + k0 + g;
+        yt = (TOUT*)p.y + n * p.ys_n + c * p.ys_c + (long long)(w0 + g) * p.ys_h + k0 + 2 * t;
         xc0 = xg + (ix + 2 * t);
         const int rows_left = p.yh - w0;
         nwb = (rows_left + 7) >> 3;
         if (nwb > p.seg_wblocks) nwb = p.seg_wblocks;
         // ix and xw are even (host-checked), so a column pair is either inside or outside the plane as a whole
-        interior = __all_sync(0xffffffffu, col_mask() == (1u << Geo::NC) - 1u) && k0 + 16 <= p.yw;
+        interior = __all_sync(0xffffffffu, col_mask() == (1u << Geo::NC) - 1u) && k0 + 16 <= p.yw && p.y_pairs;
+#pragma unroll
+        for (int mb = 0; mb < MB; mb++) { P[0][mb][0] = P[0][mb][1] = P[1][mb][0] = P[1][mb][1] = 0u; }
+#pragma unroll
+        for (int jb = 0; jb < JB; jb++) carry[jb] = 0u;
     }
 
     // bit c: this lane's column pair of chunk c lies inside the plane
@@ -309,20 +328,6 @@ struct FtcWarp {
         }
     }
 
-    // (1) horizontal up-FIR of one block of 8 input rows: r1[nb] = B-fragment half for column block nb of R2
-    __device__ __forceinline__ void step1(const uint32_t (&in)[Geo::NC], uint32_t (&r1)[Geo::NJ8]) const
-    {
-#pragma unroll
-        for (int b = 0; b < Geo::KC4; b++) {
-            const int w = (U == 2) ? b : (b >> 1);          // first input chunk of the window
-            const int ph = (U == 2) ? 0 : (b & 1);
-            uint32_t d[2];
-            mma_h(d, a1[ph], in[w], in[w + 1]);
-            r1[2 * b] = d[0];
-            r1[2 * b + 1] = d[1];
-        }
-    }
-
     // leaky ReLU + clamp of two packed samples (see the header)
     __device__ __forceinline__ uint32_t act2(uint32_t u) const
     {
@@ -335,211 +340,199 @@ struct FtcWarp {
         }
     }
 
-    // (2)+(nonlinearity)+(4): one block of 16 up-sampled rows -> A-fragment chunk of R3 for step (5)
-    __device__ __forceinline__ void vblock(const uint32_t (&ra)[Geo::NJ8], const uint32_t (&rb)[Geo::NJ8], int ph,
-                                           uint32_t (&a5)[4]) const
+    // (1) horizontal up-FIR of input row block yb (already converted) -> P[SLOT]
+    template <int SLOT>
+    __device__ __forceinline__ void step1(const uint32_t (&in)[Geo::NC])
     {
-        uint32_t c0[2], c1[2];
 #pragma unroll
-        for (int kc = 0; kc < Geo::KC4; kc++) {
-            uint32_t p2[2][2];
-#pragma unroll
-            for (int q = 0; q < 2; q++) {
-                const int nb = 2 * kc + q;
-                uint32_t d[2];
-                mma_h(d, a2[ph], ra[nb], rb[nb]);
-                p2[q][0] = act2(d[0]);
-                p2[q][1] = act2(d[1]);
-            }
-            if (kc == 0) {
-                mma_h(c0, a4[kc], p2[0][0], p2[1][0]);
-                mma_h(c1, a4[kc], p2[0][1], p2[1][1]);
-            } else {
-                mma_h_acc(c0, a4[kc], p2[0][0], p2[1][0]);
-                mma_h_acc(c1, a4[kc], p2[0][1], p2[1][1]);
-            }
+        for (int b = 0; b < MB; b++) {
+            const int w = (U == 2) ? b : (b >> 1);          // first input chunk of the window
+            const int ph = (U == 2) ? 0 : (b & 1);
+            mma_h(P[SLOT][b], a1[ph], in[w], in[w + 1]);
         }
-        a5[0] = c0[0]; a5[1] = c0[1]; a5[2] = c1[0]; a5[3] = c1[1];
     }
 
-    // out_scale is folded into the Td_y taps; a skip tensor is added as skip * out_scale
-    template <bool EDGE>
-    __device__ __forceinline__ void store(int wb, const float (&c)[4]) const
+    // (2) vertical up-FIR of the 16-row window (previous block | block in slot CUR) for the up-sampled row blocks
+    // NB0, NB0 + 1 (= one 16-row chunk), activation, and (3) that chunk's contribution to the window of R3
+    // ({ rows -8..-1, rows 0..7 } relative to the window's block of 8 output rows).
+    // MODE 0 (D == 2, the chunk is the whole window): X[jb] = carry + upper half, carry = lower half.
+    // MODE 1 (D == 4, first chunk): win = contribution.   MODE 2 (second chunk): win += contribution, then as MODE 0.
+    template <int CUR, int NB0, int MODE>
+    __device__ __forceinline__ void chunk(int al, uint32_t (&win)[JB][2], uint32_t (&X)[JB])
     {
-        const int o = 8 * wb * p.ys_h;
-        TOUT* q0 = yt + o;                                              // (row 2t, col g) of this block
-        TOUT* q1 = yt + (o + p.ys_h);
-        float v[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) v[i] = c[i];
-        if (!EDGE) {
-            if (has_skip) {
-                v[0] += (float)q0[kofs] * p.out_scale; v[1] += (float)q1[kofs] * p.out_scale;
-                v[2] += (float)q0[kofs + 8] * p.out_scale; v[3] += (float)q1[kofs + 8] * p.out_scale;
+        for (int mb = 0; mb < MB; mb++) {
+            const uint32_t quad[4] = {P[0][mb][0], P[0][mb][1], P[1][mb][0], P[1][mb][1]};
+            uint32_t e[2][2];
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                uint32_t d[2];
+                // slot 0 supplies k 0..7: if it holds the current block the two K halves of the constant swap
+                if (CUR == 1) mma_h(d, quad, b2[NB0 + q][0], b2[NB0 + q][1]);
+                else mma_h(d, quad, b2[NB0 + q][1], b2[NB0 + q][0]);
+                e[q][0] = act2(d[0]);
+                e[q][1] = act2(d[1]);
             }
-            q0[0] = (TOUT)v[0]; q1[0] = (TOUT)v[1]; q0[8] = (TOUT)v[2]; q1[8] = (TOUT)v[3];
-        } else {
-            const int y0 = w0 + 8 * wb + 2 * t;
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int yy = y0 + (i & 1), xx = k0 + g + (i >> 1) * 8;
-                if (yy < p.yh && xx < p.yw) {
-                    TOUT* q = ((i & 1) ? q1 : q0) + (i >> 1) * 8;
-                    if (has_skip) v[i] += (float)q[kofs] * p.out_scale;
-                    *q = (TOUT)v[i];
+            for (int h = 0; h < 2; h++) {
+                const int jb = 2 * mb + h;
+                if (MODE == 0) {
+                    uint32_t w[2];
+                    mma_h(w, a3[al], e[0][h], e[1][h]);
+                    asm("add.rn.f16x2 %0, %1, %2;" : "=r"(X[jb]) : "r"(carry[jb]), "r"(w[0]));
+                    carry[jb] = w[1];
+                } else if (MODE == 1) {
+                    mma_h(win[jb], a3[al], e[0][h], e[1][h]);
+                } else {
+                    mma_h_acc(win[jb], a3[al], e[0][h], e[1][h]);
+                    asm("add.rn.f16x2 %0, %1, %2;" : "=r"(X[jb]) : "r"(carry[jb]), "r"(win[jb][0]));
+                    carry[jb] = win[jb][1];
                 }
             }
         }
     }
 
-    // (5) one block of 8 output rows from NB5 consecutive chunks of R3
+    // (4) horizontal down-FIR of two blocks of 8 output rows (X0: rows 8b.., X1: rows 8b+8..), fp32 accumulate, store.
+    // out_scale is folded into the Td_x taps; a skip tensor is added as skip * out_scale.
+    // ROWS: 3 = both blocks, 2 = only the second (X1), 1 = only the first.
     template <bool EDGE>
-    __device__ __forceinline__ void wblock2(int wb, const uint32_t (&c0)[4], const uint32_t (&c1)[4]) const
+    __device__ __forceinline__ void emit(int b, const uint32_t (&X0)[JB], const uint32_t (&X1)[JB], int rows) const
     {
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
-        mma_f(c, c0, b5[0][0], b5[0][1]);
-        mma_f(c, c1, b5[1][0], b5[1][1]);
-        store<EDGE>(wb, c);
+#pragma unroll
+        for (int nb = 0; nb < 2; nb++) {
+            float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int rel = 0; rel < NREL; rel++) {
+                const int kc = nb * (D / 2) + rel;
+                const uint32_t quad[4] = {X0[2 * kc], X1[2 * kc], X0[2 * kc + 1], X1[2 * kc + 1]};
+                mma_f(c, quad, b4[rel][0], b4[rel][1]);
+            }
+            const bool has_skip = p.skip != nullptr;
+            const long long kofs = (const TOUT*)p.skip - (const TOUT*)p.y;      // used only when has_skip
+            const int o = 8 * b * p.ys_h + 8 * nb;
+            TOUT* q0 = yt + o;                                          // (row 8b + g, col k0 + 8nb + 2t)
+            TOUT* q1 = yt + (o + 8 * p.ys_h);
+            if (!EDGE) {
+                if (has_skip) {
+                    c[0] += (float)q0[kofs] * p.out_scale; c[1] += (float)q0[kofs + 1] * p.out_scale;
+                    c[2] += (float)q1[kofs] * p.out_scale; c[3] += (float)q1[kofs + 1] * p.out_scale;
+                }
+                if (rows & 1) store_pair(q0, c[0], c[1]);
+                if (rows & 2) store_pair(q1, c[2], c[3]);
+            } else {
+                const int xx = k0 + 8 * nb + 2 * t;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int yy = w0 + 8 * b + g + (i >> 1) * 8;
+                    const int wb = b + (i >> 1);
+                    if (((rows >> (i >> 1)) & 1) && wb >= 0 && wb < nwb && yy < p.yh && xx + (i & 1) < p.yw) {
+                        TOUT* q = ((i >> 1) ? q1 : q0) + (i & 1);
+                        float v = c[i];
+                        if (has_skip) v += (float)q[kofs] * p.out_scale;
+                        *q = (TOUT)v;
+                    }
+                }
+            }
+        }
     }
-    template <bool EDGE>
-    __device__ __forceinline__ void wblock4(int wb, const uint32_t (&c0)[4], const uint32_t (&c1)[4], const uint32_t (&c2)[4],
-                                            const uint32_t (&c3)[4]) const
-    {
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
-        mma_f(c, c0, b5[0][0], b5[0][1]);
-        mma_f(c, c1, b5[1][0], b5[1][1]);
-        mma_f(c, c2, b5[Geo::NB5 - 2][0], b5[Geo::NB5 - 2][1]);
-        mma_f(c, c3, b5[Geo::NB5 - 1][0], b5[Geo::NB5 - 1][1]);
-        store<EDGE>(wb, c);
-    }
+    static __device__ __forceinline__ void store_pair(float* q, float a, float b) { *reinterpret_cast<float2*>(q) = make_float2(a, b); }
+    static __device__ __forceinline__ void store_pair(__half* q, float a, float b) { *reinterpret_cast<__half2*>(q) = __floats2half2_rn(a, b); }
 
-    // ---- per-geometry pipelines.  Every strip runs  [0, lo) with EDGE handling, [lo, hi) without (all input
-    // rows / columns read and all outputs written by those iterations are inside the planes), [hi, iters) with.
     static __device__ __forceinline__ int fdiv8(int a) { return a >> 3; }                 // floor(a / 8)
 
-    // U == 2, D == 2.  iteration it: input block it -> R1[it]; v-block it-1 from R1[it-1], R1[it];
-    // w-block it-2 from chunks it-2, it-1.
+    // ---- U == 2, D == 2: super-iteration s = input row blocks 2s, 2s+1 -> up-sampled chunks 2s-1, 2s (= windows)
+    // -> output row blocks 2s-2, 2s-1, emitted together.
     template <bool EDGE>
-    __device__ __forceinline__ void iter22(int it, uint32_t (&r1p)[Geo::NJ8], uint32_t (&r1c)[Geo::NJ8],
-                                           uint32_t (&a5p)[4], uint32_t (&a5c)[4]) const
+    __device__ __forceinline__ void super22(int s, uint32_t (&X0)[JB], uint32_t (&X1)[JB])
     {
-        uint32_t in[Geo::NC];
-        convert<EDGE>(it, in); step1(in, r1c); fetch<EDGE>(it + FTC_PD);
-        if (!EDGE || it >= 1) vblock(r1p, r1c, 0, a5c);
-        if (!EDGE || it >= 2) wblock2<EDGE>(it - 2, a5p, a5c);
+        uint32_t in[Geo::NC], win[JB][2];
+        convert<EDGE>(2 * s, in); step1<0>(in); fetch<EDGE>(2 * s + FTC_PD);
+        chunk<0, 0, 0>(0, win, X0);                                     // block 2s-2
+        convert<EDGE>(2 * s + 1, in); step1<1>(in); fetch<EDGE>(2 * s + 1 + FTC_PD);
+        chunk<1, 0, 0>(0, win, X1);                                     // block 2s-1
+        if (!EDGE || s >= 1) emit<EDGE>(2 * s - 2, X0, X1, 3);
     }
     __device__ void run22()
     {
-        uint32_t r1a[Geo::NJ8], r1b[Geo::NJ8], a5a[4], a5b[4];
-        const int iters = nwb + 2;
+        uint32_t X0[JB], X1[JB];
+        const int S = ((nwb - 1) >> 1) + 2;
         int lo = 0, hi = 0;
         if (interior) {
-            lo = max(2, fdiv8(-iy + 7));
-            hi = min(min(fdiv8(p.xh - 8 - iy) - FTC_PD, fdiv8(p.yh - w0) + 1) + 1, iters);
+            lo = max(1, (-iy + 15) >> 4);
+            hi = min(min((fdiv8(p.xh - 8 - iy) - FTC_PD - 1) >> 1, min((p.yh - w0) >> 4, nwb >> 1)) + 1, S);
         }
         if (hi < lo) hi = lo = 0;
-        hi = lo + ((hi - lo) & ~1);                                     // the steady loop is unrolled by two
-        int it = 0;
-        for (; it < (hi > lo ? lo : iters); it++) {
-            iter22<true>(it, r1a, r1b, a5a, a5b);
-#pragma unroll
-            for (int i = 0; i < Geo::NJ8; i++) r1a[i] = r1b[i];
-#pragma unroll
-            for (int i = 0; i < 4; i++) a5a[i] = a5b[i];
-        }
+        int s = 0;
+        for (; s < (hi > lo ? lo : S); s++) super22<true>(s, X0, X1);
         if (hi > lo) {
-            for (; it < hi; it += 2) {                                  // "previous" buffers alternate, no copies
-                iter22<false>(it, r1a, r1b, a5a, a5b);
-                iter22<false>(it + 1, r1b, r1a, a5b, a5a);
-            }
-            for (; it < iters; it++) {
-                iter22<true>(it, r1a, r1b, a5a, a5b);
-#pragma unroll
-                for (int i = 0; i < Geo::NJ8; i++) r1a[i] = r1b[i];
-#pragma unroll
-                for (int i = 0; i < 4; i++) a5a[i] = a5b[i];
-            }
+            for (; s < hi; s++) super22<false>(s, X0, X1);
+            for (; s < S; s++) super22<true>(s, X0, X1);
         }
     }
 
-    // U == 4, D == 2.  iteration it: input block it; v-blocks 2it-2, 2it-1 (two phases) from R1[it-1], R1[it];
-    // w-block 2it-3 from chunks (2it-3, 2it-2), w-block 2it-2 from chunks (2it-2, 2it-1)
-    template <bool EDGE>
-    __device__ __forceinline__ void iter42(int it, uint32_t (&r1p)[Geo::NJ8], uint32_t (&r1c)[Geo::NJ8], uint32_t (&a5l)[4]) const
+    // ---- U == 4, D == 2: iteration it = input row block it -> chunks (= windows) 2it-2, 2it-1 -> output row blocks
+    // 2it-3 (odd, completes the pair started by the previous iteration) and 2it-2 (even, kept in X0).
+    template <bool EDGE, int CUR>
+    __device__ __forceinline__ void iter42(int it, uint32_t (&X0)[JB])
     {
-        uint32_t in[Geo::NC], a5a[4], a5b[4];
-        convert<EDGE>(it, in); step1(in, r1c); fetch<EDGE>(it + FTC_PD);
-        if (!EDGE || it >= 1) {
-            vblock(r1p, r1c, 0, a5a);
-            vblock(r1p, r1c, Geo::NPH - 1, a5b);
-            if (!EDGE || (it >= 2 && 2 * it - 3 < nwb)) wblock2<EDGE>(2 * it - 3, a5l, a5a);
-            if (!EDGE || 2 * it - 2 < nwb) wblock2<EDGE>(2 * it - 2, a5a, a5b);
-#pragma unroll
-            for (int i = 0; i < 4; i++) a5l[i] = a5b[i];
-        }
+        uint32_t in[Geo::NC], win[JB][2], X1[JB];
+        convert<EDGE>(it, in); step1<CUR>(in); fetch<EDGE>(it + FTC_PD);
+        chunk<CUR, 0, 0>(0, win, X1);                                   // block 2it-3
+        if (!EDGE || it >= 2) emit<EDGE>(2 * it - 4, X0, X1, 3);
+        chunk<CUR, 2, 0>(0, win, X0);                                   // block 2it-2
     }
     __device__ void run42()
     {
-        uint32_t r1a[Geo::NJ8], r1b[Geo::NJ8], a5l[4];
-        const int iters = (nwb + 2) / 2 + 1;
+        uint32_t X0[JB];
+        const int iters = ((nwb - 1) >> 1) + 3;
+        const int S = (iters + 1) >> 1;
         int lo = 0, hi = 0;
         if (interior) {
-            lo = max(2, fdiv8(-iy + 7));
-            hi = min(min(fdiv8(p.xh - 8 - iy) - FTC_PD, (fdiv8(p.yh - w0) + 1) >> 1) + 1, iters);
+            // iterations 2s, 2s+1: input blocks up to 2s+1 (+PD), output pairs s-2.. : blocks 4s-4 .. 4s-1
+            lo = max(1, (-iy + 15) >> 4);
+            hi = min(min((fdiv8(p.xh - 8 - iy) - FTC_PD - 1) >> 1, min((p.yh - w0) >> 5, nwb >> 2)) + 1, S);
         }
         if (hi < lo) hi = lo = 0;
-        hi = lo + ((hi - lo) & ~1);
-        int it = 0;
-        for (; it < (hi > lo ? lo : iters); it++) {
-            iter42<true>(it, r1a, r1b, a5l);
-#pragma unroll
-            for (int i = 0; i < Geo::NJ8; i++) r1a[i] = r1b[i];
-        }
+        int s = 0;
+        for (; s < (hi > lo ? lo : S); s++) { iter42<true, 0>(2 * s, X0); iter42<true, 1>(2 * s + 1, X0); }
         if (hi > lo) {
-            for (; it < hi; it += 2) {
-                iter42<false>(it, r1a, r1b, a5l);
-                iter42<false>(it + 1, r1b, r1a, a5l);
-            }
-            for (; it < iters; it++) {
-                iter42<true>(it, r1a, r1b, a5l);
-#pragma unroll
-                for (int i = 0; i < Geo::NJ8; i++) r1a[i] = r1b[i];
-            }
+            for (; s < hi; s++) { iter42<false, 0>(2 * s, X0); iter42<false, 1>(2 * s + 1, X0); }
+            for (; s < S; s++) { iter42<true, 0>(2 * s, X0); iter42<true, 1>(2 * s + 1, X0); }
         }
     }
 
-    // U == 2, D == 4.  iteration it: input blocks 2it, 2it+1; v-block 2it-1 from R1[2it-1], R1[2it];
-    // v-block 2it from R1[2it], R1[2it+1]; w-block it-2 from chunks 2it-4 .. 2it-1
+    // ---- U == 2, D == 4: iteration it = input row blocks 2it, 2it+1 -> chunks 2it-1 (second half of window it-1)
+    // and 2it (first half of window it) -> output row block it-2; blocks are emitted one at a time as the second
+    // half of the pair (it-3, it-2).
     template <bool EDGE>
-    __device__ __forceinline__ void iter24(int it, uint32_t (&r1l)[Geo::NJ8], uint32_t (&q0)[4], uint32_t (&q1)[4],
-                                           uint32_t (&q2)[4]) const
+    __device__ __forceinline__ void iter24(int it, uint32_t (&win)[JB][2], uint32_t (&Xp)[JB])
     {
-        uint32_t in[Geo::NC], r1a[Geo::NJ8], r1b[Geo::NJ8], qa[4], qb[4];
-        convert<EDGE>(2 * it, in); step1(in, r1a); fetch<EDGE>(2 * it + FTC_PD);
-        if (!EDGE || it >= 1) vblock(r1l, r1a, 0, qa);
-        convert<EDGE>(2 * it + 1, in); step1(in, r1b); fetch<EDGE>(2 * it + 1 + FTC_PD);
-        vblock(r1a, r1b, 0, qb);
-        if (!EDGE || it >= 2) wblock4<EDGE>(it - 2, q0, q1, q2, qa);
+        uint32_t in[Geo::NC], X[JB];
+        convert<EDGE>(2 * it, in); step1<0>(in); fetch<EDGE>(2 * it + FTC_PD);
+        chunk<0, 0, 2>(1, win, X);                                      // block it-2
+        if (!EDGE || it >= 2) emit<EDGE>(it - 3, Xp, X, 2);
 #pragma unroll
-        for (int i = 0; i < 4; i++) { q0[i] = q2[i]; q1[i] = qa[i]; q2[i] = qb[i]; }
-#pragma unroll
-        for (int i = 0; i < Geo::NJ8; i++) r1l[i] = r1b[i];
+        for (int jb = 0; jb < JB; jb++) Xp[jb] = X[jb];
+        convert<EDGE>(2 * it + 1, in); step1<1>(in); fetch<EDGE>(2 * it + 1 + FTC_PD);
+        chunk<1, 0, 1>(0, win, X);
     }
     __device__ void run24()
     {
-        uint32_t r1l[Geo::NJ8], q0[4], q1[4], q2[4];
+        uint32_t win[JB][2], Xp[JB];
+#pragma unroll
+        for (int jb = 0; jb < JB; jb++) { win[jb][0] = win[jb][1] = 0u; Xp[jb] = 0u; }
         const int iters = nwb + 2;
         int lo = 0, hi = 0;
         if (interior) {
-            lo = max(2, (-iy + 15) >> 4);
+            lo = max(3, (-iy + 15) >> 4);
             hi = min(min((fdiv8(p.xh - 8 - iy) - FTC_PD - 1) >> 1, fdiv8(p.yh - w0) + 1) + 1, iters);
         }
         if (hi < lo) hi = lo = 0;
         int it = 0;
-        for (; it < (hi > lo ? lo : iters); it++) iter24<true>(it, r1l, q0, q1, q2);
+        for (; it < (hi > lo ? lo : iters); it++) iter24<true>(it, win, Xp);
         if (hi > lo) {
-            for (; it < hi; it++) iter24<false>(it, r1l, q0, q1, q2);
-            for (; it < iters; it++) iter24<true>(it, r1l, q0, q1, q2);
+            for (; it < hi; it++) iter24<false>(it, win, Xp);
+            for (; it < iters; it++) iter24<true>(it, win, Xp);
         }
     }
 
@@ -556,7 +549,7 @@ struct FtcWarp {
 };
 
 template <int U, int D, typename TIN, typename TOUT, int ACT>
-__global__ void __launch_bounds__(FTC_WARPS * 32, (U == 2 && D == 4) ? 3 : (U == 4 ? 5 : 6))
+__global__ void __launch_bounds__(FTC_WARPS * 32, (U == 2 && D == 4) ? 2 : (U == 4 ? 4 : 5))
 flr_tc_kernel(const __grid_constant__ FlrTcParams p)
 {
     __shared__ float tab[4][FTC_TAB];
@@ -672,6 +665,10 @@ extern "C" int afcm_filtered_lrelu_tc(const void* x, const int64_t* xs, int x_dt
     p.ix0 = bx - p.dx;
     p.iy0 = (-p.sy - py0) / up;
     p.slope = slope; p.out_scale = out_scale;
+    {
+        const uintptr_t ypair = y_dtype == AFCM_F32 ? 8 : 4;
+        p.y_pairs = !((ys[0] & 1) || (ys[1] & 1) || (ys[2] & 1) || ((uintptr_t)y % ypair) || (skip && ((uintptr_t)skip % ypair)));
+    }
     // activation scale: R2 is computed in units of `clamp` when the sat() form applies
     const bool finite_clamp = clamp > 0.f && clamp < 3.0e38f;
     int act = FTC_ACT_MINMAX;
@@ -685,8 +682,8 @@ extern "C" int afcm_filtered_lrelu_tc(const void* x, const int64_t* xs, int x_dt
     }
     for (int t = 0; t < fd_taps; t++) {
         const float f = fd_host[flip_filter ? t : fd_taps - 1 - t];
-        p.kdx[t] = f / u_scale;
-        p.kdy[t] = f * out_scale;
+        p.kdx[t] = f * out_scale;
+        p.kdy[t] = f / u_scale;
     }
     cudaStream_t st = (cudaStream_t)stream;
     if (x_dtype == AFCM_F32 && y_dtype == AFCM_F32) return dispatch_act<float, float>(p, N, up, down, act, st);
