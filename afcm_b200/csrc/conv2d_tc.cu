@@ -38,7 +38,8 @@ constexpr long long TC_WATCHDOG_CYCLES = 4000000000LL; // ~2 s: trap instead of 
 
 struct TcParams {
     const float* ocoef;     // [N, Co] or null
-    float* y;               // [N, Co, OH, OW]
+    void* y;                // [N, Co, OH, OW] fp32, or fp16 when y_half
+    int y_half;
     int N, Ci, Co, H, W, Wp, OH, OW, pad;
     int BN, n_tiles, m_tiles, cblocks;     // channel tile, #channel tiles, #pixel tiles per sample, ceil(Ci/64)
     int total_tiles;
@@ -264,16 +265,25 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int pix = mt * TC_BM + wq * 32 + lane;
             const int oy = pix / p.Wp, ox = pix - oy * p.Wp;
             const bool ok = oy < p.OH && ox < p.OW;
-            float* yb = p.y + ((long long)n * p.Co + o0) * ohw + (long long)oy * p.OW + ox;
+            const long long yofs = ((long long)n * p.Co + o0) * ohw + (long long)oy * p.OW + ox;
+            float* yb = reinterpret_cast<float*>(p.y) + yofs;
+            __half* yh = reinterpret_cast<__half*>(p.y) + yofs;
             for (int c0 = 0; c0 < p.BN; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * 256 + c0), v);
                 tmem_ld_wait();
                 if (ok) {
+                    if (p.y_half) {
 #pragma unroll
-                    for (int j = 0; j < 32; j++)
-                        if (o0 + c0 + j < p.Co)
-                            yb[(long long)(c0 + j) * ohw] = __uint_as_float(v[j]) * s_ocoef[acc * 256 + c0 + j];
+                        for (int j = 0; j < 32; j++)
+                            if (o0 + c0 + j < p.Co)
+                                yh[(long long)(c0 + j) * ohw] = __float2half_rn(__uint_as_float(v[j]) * s_ocoef[acc * 256 + c0 + j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j++)
+                            if (o0 + c0 + j < p.Co)
+                                yb[(long long)(c0 + j) * ohw] = __uint_as_float(v[j]) * s_ocoef[acc * 256 + c0 + j];
+                    }
                 }
             }
             tc_fence_before();
@@ -293,12 +303,78 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
 }
 
-// ---- activation packing: fp32 NCHW -> 16-bit [n][flat pixel][channel], modulation folded in ------------
-// One CTA transposes a tile of 64 flat pixels x 64 channels through shared memory: coalesced reads along
-// x, 16-byte coalesced writes along the channel axis.
-template <typename TC>
+// ---- activation packing: fp32 / fp16 NCHW -> 16-bit [n][flat pixel][channel], modulation folded in -----
+// One CTA transposes a tile of 128 flat pixels x 64 channels through shared memory.  Reads are aligned pixel
+// PAIRS (float2 / half2: W, the row pitch W+2 and all strides are even, so a pair never straddles a row end),
+// one warp per 8 channels; the tile is kept as [pixel][channel pair] words with a 33-word pitch (2-way store
+// conflicts, conflict-free reads); writes are 16-byte stores, 4 pixels x 128 B per warp instruction.
+__device__ __forceinline__ float2 load_pair(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ float2 load_pair(const __half* p) { return __half22float2(*reinterpret_cast<const __half2*>(p)); }
+__device__ __forceinline__ uint32_t pack_tc(float lo, float hi, __half*)
+{
+    __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_tc(float lo, float hi, __nv_bfloat16*)
+{
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <typename TIN, typename TC>
 __global__ void __launch_bounds__(256)
-tc_pack_kernel(const float* __restrict__ x, const float* __restrict__ icoef, TC* __restrict__ xp,
+tc_pack_pairs_kernel(const TIN* __restrict__ x, const float* __restrict__ icoef, TC* __restrict__ xp,
+                     int Ci, int c_pad, int H, int W, int Wp, int rows)
+{
+    __shared__ uint32_t tile[128][33];
+    const int n = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 128;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long plane = (long long)H * W;
+    int yy[2], xx[2];
+    bool ok[2];
+#pragma unroll
+    for (int it = 0; it < 2; it++) {
+        const int pp = p0 + 2 * (lane + 32 * it);
+        yy[it] = pp / Wp; xx[it] = pp - yy[it] * Wp;
+        ok[it] = pp < rows && xx[it] < W;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int cpair = warp * 4 + j, c = c0 + 2 * cpair;
+        const bool c_ok0 = c < Ci, c_ok1 = c + 1 < Ci;
+        float s0 = 1.f, s1 = 1.f;
+        if (icoef) { s0 = c_ok0 ? icoef[(long long)n * Ci + c] : 0.f; s1 = c_ok1 ? icoef[(long long)n * Ci + c + 1] : 0.f; }
+        const TIN* xc = x + ((long long)n * Ci + c) * plane;
+#pragma unroll
+        for (int it = 0; it < 2; it++) {
+            float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
+            if (ok[it]) {
+                const long long o = (long long)yy[it] * W + xx[it];
+                if (c_ok0) a = load_pair(xc + o);
+                if (c_ok1) b = load_pair(xc + plane + o);
+            }
+            const int r = 2 * (lane + 32 * it);
+            tile[r][cpair] = pack_tc(a.x * s0, b.x * s1, (TC*)nullptr);
+            tile[r + 1][cpair] = pack_tc(a.y * s0, b.y * s1, (TC*)nullptr);
+        }
+    }
+    __syncthreads();
+    const int g8 = tid & 7;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int pw = (tid >> 3) + 32 * j;
+        const int pp = p0 + pw, cc = c0 + g8 * 8;
+        if (pp < rows && cc < c_pad) {
+            const uint4 v = make_uint4(tile[pw][g8 * 4], tile[pw][g8 * 4 + 1], tile[pw][g8 * 4 + 2], tile[pw][g8 * 4 + 3]);
+            *reinterpret_cast<uint4*>(xp + ((long long)n * rows + pp) * c_pad + cc) = v;
+        }
+    }
+}
+
+// General variant (odd W or unaligned base): scalar reads, 64 pixels x 64 channels per CTA.
+template <typename TIN, typename TC>
+__global__ void __launch_bounds__(256)
+tc_pack_kernel(const TIN* __restrict__ x, const float* __restrict__ icoef, TC* __restrict__ xp,
                int Ci, int c_pad, int H, int W, int Wp, int rows)
 {
     __shared__ float tile[64][65];
@@ -313,7 +389,7 @@ tc_pack_kernel(const float* __restrict__ x, const float* __restrict__ icoef, TC*
         const int c = c0 + cq * 16 + j;
         float v = 0.f;
         if (pix_ok && c < Ci) {
-            v = x[(((long long)n * Ci + c) * H + yy) * W + xx];
+            v = (float)x[(((long long)n * Ci + c) * H + yy) * W + xx];
             if (icoef) v *= icoef[n * Ci + c];
         }
         tile[cq * 16 + j][px] = v;
@@ -331,6 +407,20 @@ tc_pack_kernel(const float* __restrict__ x, const float* __restrict__ icoef, TC*
             for (int k = 0; k < 8; k++) v[k] = (TC)tile[g8 * 8 + k][pw];
             *reinterpret_cast<uint4*>(xp + ((long long)n * rows + pp) * c_pad + cc) = *reinterpret_cast<const uint4*>(v);
         }
+    }
+}
+
+template <typename TIN, typename TC>
+static void launch_pack(const void* x, const float* icoef, void* xp, int N, int Ci, int H, int W, cudaStream_t st)
+{
+    const int Wp = W + 2, rows = H * Wp, c_pad = (Ci + 7) & ~7;
+    const bool pairs = !(W & 1) && ((uintptr_t)x % (2 * sizeof(TIN))) == 0;
+    if (pairs) {
+        dim3 grid(ceil_div(rows, 128), ceil_div(c_pad, 64), N);
+        tc_pack_pairs_kernel<TIN, TC><<<grid, 256, 0, st>>>((const TIN*)x, icoef, (TC*)xp, Ci, c_pad, H, W, Wp, rows);
+    } else {
+        dim3 grid(ceil_div(rows, 64), ceil_div(c_pad, 64), N);
+        tc_pack_kernel<TIN, TC><<<grid, 256, 0, st>>>((const TIN*)x, icoef, (TC*)xp, Ci, c_pad, H, W, Wp, rows);
     }
 }
 
@@ -395,32 +485,37 @@ extern "C" int64_t afcm_conv_tc_plane_elems(int H, int W, int Ci)
     return (int64_t)H * (W + 2) * ((Ci + 7) & ~7);           // [H*(W+2) flat pixels][Ci padded to 8]
 }
 
-extern "C" int afcm_conv_tc_pack(const float* x, const float* icoef, void* xp, int tc_dtype,
+extern "C" int afcm_conv_tc_pack(const void* x, int x_dtype, const float* icoef, void* xp, int tc_dtype,
                                  int N, int Ci, int H, int W, void* stream)
 {
     AFCM_CHECK_ARG(x && xp && N > 0 && Ci > 0 && H > 0 && W > 0, "empty problem");
+    AFCM_CHECK_ARG(x_dtype == AFCM_F32 || x_dtype == AFCM_F16, "x must be float32 or float16");
     AFCM_CHECK_ARG(tc_dtype == AFCM_F16 || tc_dtype == AFCM_BF16, "tc dtype must be F16 or BF16");
     AFCM_CHECK_ARG(N <= 65535, "batch too large");
-    const int Wp = W + 2, rows = H * Wp, c_pad = (Ci + 7) & ~7;
-    dim3 grid(ceil_div(rows, 64), ceil_div(c_pad, 64), N);
     cudaStream_t st = (cudaStream_t)stream;
-    if (tc_dtype == AFCM_BF16) tc_pack_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, icoef, (__nv_bfloat16*)xp, Ci, c_pad, H, W, Wp, rows);
-    else tc_pack_kernel<__half><<<grid, 256, 0, st>>>(x, icoef, (__half*)xp, Ci, c_pad, H, W, Wp, rows);
+    if (x_dtype == AFCM_F32) {
+        if (tc_dtype == AFCM_BF16) launch_pack<float, __nv_bfloat16>(x, icoef, xp, N, Ci, H, W, st);
+        else launch_pack<float, __half>(x, icoef, xp, N, Ci, H, W, st);
+    } else {
+        if (tc_dtype == AFCM_BF16) launch_pack<__half, __nv_bfloat16>(x, icoef, xp, N, Ci, H, W, st);
+        else launch_pack<__half, __half>(x, icoef, xp, N, Ci, H, W, st);
+    }
     AFCM_LAUNCH_CHECK();
     count_launch();
     return AFCM_OK;
 }
 
-extern "C" int afcm_conv2d_tc(const void* xp, const void* w_tc, const float* ocoef, float* y, int tc_dtype,
+extern "C" int afcm_conv2d_tc(const void* xp, const void* w_tc, const float* ocoef, void* y, int y_dtype, int tc_dtype,
                               int N, int Ci, int H, int W, int Co, int pad, void* stream)
 {
     AFCM_CHECK_ARG(xp && w_tc && y, "xp, w_tc and y must be given");
+    AFCM_CHECK_ARG(y_dtype == AFCM_F32 || y_dtype == AFCM_F16, "y must be float32 or float16");
     AFCM_CHECK_ARG(N > 0 && Ci > 0 && Co > 0 && H > 0 && W > 0, "empty problem");
     AFCM_CHECK_ARG(tc_dtype == AFCM_F16 || tc_dtype == AFCM_BF16, "tc dtype must be F16 or BF16");
     if (pad != 1 && pad != 2) { set_error("conv2d_tc: padding %d not supported (1 or 2)", pad); return AFCM_ERR_UNSUPPORTED; }
     TcParams p;
     memset(&p, 0, sizeof(p));
-    p.ocoef = ocoef; p.y = y; p.dbg = g_dbg_dev; p.dbg_mode = g_dbg_mode;
+    p.ocoef = ocoef; p.y = y; p.y_half = y_dtype == AFCM_F16; p.dbg = g_dbg_dev; p.dbg_mode = g_dbg_mode;
     p.N = N; p.Ci = Ci; p.Co = Co; p.H = H; p.W = W; p.Wp = W + 2; p.pad = pad;
     p.OH = H + 2 * pad - 2; p.OW = W + 2 * pad - 2;
     p.n_tiles = ceil_div(Co, 256);

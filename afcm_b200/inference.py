@@ -1,0 +1,89 @@
+"""Inference-side host runtime of the hot path: precision selection, CUDA-graph replay of the generator
+forward, and the slice partition used to shard a volume (or a batch of slices) across the GPUs of one box.
+
+The reference runs inference slice by slice through `StyleGAN3Model.forward` -> `netG_ema(z, c, real_A)`
+(models/stylegan3_model.py:67-86, evaluate.py:43-104) on one device (`nn.DataParallel` at most).  Here
+every rank owns a contiguous block of slices and runs the same generator on it; nothing crosses NVLink on
+the data path.
+"""
+import torch
+
+from .torch_utils.ops import conv2d_gradfix
+
+PRECISIONS = ('fp32', 'tc', 'fast')
+
+
+def set_precision(mode):
+    """'fp32': exact SIMT kernels everywhere (parity path, <= 1e-4 of the reference).
+    'tc'  : tcgen05 convolutions with fp16 operands / fp32 accumulation, fp32 activation storage, exact
+            filtered_lrelu.
+    'fast': 'tc' + tensor-core filtered_lrelu + fp16 activation storage between the operators (the
+            benchmarked inference path; tolerance stated in tests/test_gpu_generator.py)."""
+    assert mode in PRECISIONS, mode
+    if mode == 'fp32':
+        conv2d_gradfix.set_conv_impl('f32')
+    elif mode == 'tc':
+        conv2d_gradfix.set_conv_impl('tc', torch.float16)
+    else:
+        conv2d_gradfix.set_conv_impl('tc', torch.float16, act=torch.float16)
+
+
+def get_precision():
+    if conv2d_gradfix.conv_impl == 'f32':
+        return 'fp32'
+    return 'fast' if conv2d_gradfix.fast_path() else 'tc'
+
+
+class GraphedGenerator:
+    """Replays the generator forward for a fixed batch size as ONE CUDA graph launch (~250 kernel launches
+    per forward otherwise; at small batches the forward is launch-bound).  Inputs are copied into static
+    device buffers on the current stream, the graph is replayed, the static output is returned (valid until
+    the next call).  Host-side filter taps and tensor maps are baked into the captured kernel parameters, so
+    the graph must be rebuilt (`capture()`) after the weights change."""
+
+    def __init__(self, G, batch, device=None, noise_mode='const', warmup=2):
+        self.G = G
+        self.batch = int(batch)
+        p = next(G.parameters())
+        self.device = torch.device(device) if device is not None else p.device
+        self.noise_mode = noise_mode
+        self.warmup = warmup
+        self.z = torch.zeros([self.batch, G.z_dim], dtype=torch.float32, device=self.device)
+        self.c = torch.zeros([self.batch, max(G.c_dim, 1)], dtype=torch.float32, device=self.device)
+        S = G.synthesis
+        self.x = torch.zeros([self.batch, S.img_channels_in, S.img_resolution, S.img_resolution], dtype=torch.float32,
+                             device=self.device)
+        self.y = None
+        self.graph = None
+        self.precision = None
+
+    def capture(self):
+        self.precision = get_precision()
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(self.warmup):               # JIT-free, but fills the weight / tap caches before capture
+                self.G(self.z, self.c, self.x, noise_mode=self.noise_mode)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.y = self.G(self.z, self.c, self.x, noise_mode=self.noise_mode)
+        return self
+
+    def __call__(self, z, c, x):
+        if self.graph is None or self.precision != get_precision():
+            self.capture()
+        assert z.shape[0] == self.batch, f'graph captured for batch {self.batch}, got {z.shape[0]}'
+        self.z.copy_(z, non_blocking=True)
+        self.c.copy_(c.reshape(self.batch, -1), non_blocking=True)
+        self.x.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.y
+
+
+def slice_partition(num_slices, world_size, rank):
+    """Contiguous block [lo, hi) of slice indices owned by `rank` (ceil(D / world) per rank)."""
+    assert 0 <= rank < world_size and num_slices >= 0
+    per = -(-num_slices // world_size)
+    lo = min(rank * per, num_slices)
+    return lo, min(lo + per, num_slices)

@@ -21,7 +21,7 @@ from .torch_utils.ops.filtered_lrelu import _run_fused as _flrelu_fused
 
 
 @misc.profiled_function
-def modulated_conv2d(x, w, s, demodulate=True, padding=0, input_gain=None, impl=None):
+def modulated_conv2d(x, w, s, demodulate=True, padding=0, input_gain=None, impl=None, out_dtype=None):
     """NET:25-64.  x [N,I,H,W], w [O,I,k,k], s [N,I]; input_gain [] / [I] / [N,I] or None.
 
     The reference materialises a per-sample weight w*s*d*g and runs a grouped conv.  Here the same
@@ -50,7 +50,7 @@ def modulated_conv2d(x, w, s, demodulate=True, padding=0, input_gain=None, impl=
     if input_gain is not None and input_gain.numel() != 1 and demodulate:
         icoef = icoef * input_gain.expand(N, I)        # rare general form (NET:55-57); AFCM passes a scalar
     return conv2d_gradfix.conv2d_native(x, w, int(padding), icoef=icoef, ocoef=ocoef, pre_scale=1.0,
-                                        normalize=bool(demodulate), impl=impl)
+                                        normalize=bool(demodulate), impl=impl, out_dtype=out_dtype)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -230,21 +230,30 @@ class _AliasFreeLayerBase(torch.nn.Module):
         pad_hi = pad_total - pad_lo
         self.padding = [int(pad_lo[0]), int(pad_hi[0]), int(pad_lo[1]), int(pad_hi[1])]
 
-    def _filtered_lrelu(self, x, gain, slope, skip=None, out_scale=1.0):
+    def _filtered_lrelu(self, x, gain, slope, skip=None, out_scale=1.0, out_dtype=None):
         """bias + filtered leaky ReLU + clamp (NET:371-372 / NET:510-511), with the skip addition
         (NET:376-377) and the output scale (NET:699-700) folded into the kernel epilogue when no autograd
-        graph is needed."""
-        b = self.bias.to(x.dtype)
+        graph is needed.  On the fast inference path (conv2d_gradfix.fast_path()) the tensor-core kernel
+        runs it on fp16 planes; `out_dtype` then selects the storage type of the result."""
+        b = self.bias.to(torch.float32)
         needs_graph = torch.is_grad_enabled() and (x.requires_grad or b.requires_grad)
         if not needs_graph:
             px0, px1, py0, py1 = self.padding
             clamp = float(self.conv_clamp) if self.conv_clamp is not None else float('inf')
-            y, _, rc = _flrelu_fused(x, self.up_filter, self.down_filter, b, None, self.up_factor, self.down_factor,
-                                     px0, px1, py0, py1, 0, 0, float(gain), float(slope), clamp, False, False,
-                                     skip=skip, out_scale=float(out_scale))
-            if rc == 0:
-                return y
-        y = filtered_lrelu.filtered_lrelu(x=x, fu=self.up_filter, fd=self.down_filter, b=b, up=self.up_factor,
+            if conv2d_gradfix.fast_path() and self.up_filter is not None and self.down_filter is not None:
+                y = filtered_lrelu.filtered_lrelu_tc(x, self.up_filter, self.down_filter, b, up=self.up_factor,
+                                                     down=self.down_factor, padding=self.padding, gain=float(gain),
+                                                     slope=float(slope), clamp=self.conv_clamp, skip=skip,
+                                                     out_scale=float(out_scale), out_dtype=out_dtype or x.dtype)
+                if y is not None:
+                    return y
+            if x.dtype == torch.float32:
+                y, _, rc = _flrelu_fused(x, self.up_filter, self.down_filter, b, None, self.up_factor, self.down_factor,
+                                         px0, px1, py0, py1, 0, 0, float(gain), float(slope), clamp, False, False,
+                                         skip=skip, out_scale=float(out_scale))
+                if rc == 0:
+                    return y
+        y = filtered_lrelu.filtered_lrelu(x=x, fu=self.up_filter, fd=self.down_filter, b=b.to(x.dtype), up=self.up_factor,
                                           down=self.down_factor, padding=self.padding, gain=gain, slope=slope,
                                           clamp=self.conv_clamp)
         if skip is not None:
@@ -280,7 +289,7 @@ class SynthesisLayer(_AliasFreeLayerBase):
                             is_critically_sampled)
 
     def forward(self, x, w, global_w, E_features=None, include_skip=True, noise_mode='random', force_fp32=False,
-                update_emas=False, out_scale=1.0):
+                update_emas=False, out_scale=1.0, out_dtype=None):
         assert noise_mode in ['random', 'const', 'none']
         misc.assert_shape(x, [None, self.in_channels, int(self.in_size[1]), int(self.in_size[0])])
         misc.assert_shape(w, [x.shape[0], self.w_dim])
@@ -296,11 +305,14 @@ class SynthesisLayer(_AliasFreeLayerBase):
         x_skip = None
         if E_features is not None and include_skip:
             x_skip = E_features[self.out_size[0]]
-        x = modulated_conv2d(x=x.float(), w=self.weight, s=styles, padding=self.conv_kernel - 1,
-                             demodulate=(not self.is_torgb), input_gain=input_gain)
+        fast = conv2d_gradfix.fast_path() and not self.is_torgb
+        x = modulated_conv2d(x=x if fast else x.float(), w=self.weight, s=styles, padding=self.conv_kernel - 1,
+                             demodulate=(not self.is_torgb), input_gain=input_gain,
+                             out_dtype=conv2d_gradfix.act_dtype if fast else None)
         gain = 1 if self.is_torgb else np.sqrt(2)
         slope = 1 if self.is_torgb else 0.2
-        x = self._filtered_lrelu(x, gain, slope, skip=x_skip if include_skip else None, out_scale=out_scale)
+        x = self._filtered_lrelu(x, gain, slope, skip=x_skip if include_skip else None, out_scale=out_scale,
+                                 out_dtype=out_dtype)
         misc.assert_shape(x, [None, self.out_channels, int(self.out_size[1]), int(self.out_size[0])])
         return x
 
@@ -331,7 +343,9 @@ class EncoderLayer(_AliasFreeLayerBase):
         if update_emas:
             magnitude_cur = x.detach().to(torch.float32).square().mean()
             self.magnitude_ema.copy_(magnitude_cur.lerp(self.magnitude_ema, self.magnitude_ema_beta))
-        x = conv2d_gradfix.conv2d_native(x.float(), self.weight, self.conv_kernel - 1, pre_scale=self.weight_gain)
+        fast = conv2d_gradfix.fast_path()
+        x = conv2d_gradfix.conv2d_native(x if fast else x.float(), self.weight, self.conv_kernel - 1, pre_scale=self.weight_gain,
+                                         out_dtype=conv2d_gradfix.act_dtype if fast else None)
         x = self._filtered_lrelu(x, np.sqrt(2), 0.2)
         misc.assert_shape(x, [None, self.out_channels, int(self.out_size[1]), int(self.out_size[0])])
         return x
@@ -367,8 +381,9 @@ class Conv2dLayer(torch.nn.Module):
                 self.bias = None
 
     def forward(self, x, gain=1):
+        x = conv2d_gradfix.conv2d_native(x if conv2d_gradfix.fast_path() else x.float(), self.weight, self.padding,
+                                         pre_scale=self.weight_gain)
         b = self.bias.to(x.dtype) if self.bias is not None else None
-        x = conv2d_gradfix.conv2d_native(x.float(), self.weight, self.padding, pre_scale=self.weight_gain)
         act_gain = self.act_gain * gain
         act_clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
         return bias_act.bias_act(x, b, act=self.activation, gain=act_gain, clamp=act_clamp)
@@ -451,12 +466,30 @@ class SynthesisNetwork(torch.nn.Module):
                                                     _lib.stream_ptr(x.device)))
         return y
 
+    _u8_lut = None
+
+    @classmethod
+    def u8_lut(cls):
+        """float32 value of every uint8 code under the reference's input transform: Normalize(0, 255) then
+        clip(2 v - 1, -1, 1) in float64, cast to float32 (data/augment/transforms.py:604-616)."""
+        if cls._u8_lut is None:
+            v = np.arange(256, dtype=np.float64) / 255.0
+            cls._u8_lut = np.ascontiguousarray(np.clip(2.0 * v - 1.0, -1, 1).astype(np.float32))
+        return cls._u8_lut
+
     def pad_input(self, img):
+        """NET:669 zero margin.  A uint8 image stack is normalised on the fly (the volume is uploaded as bytes:
+        4x fewer host-to-device bytes than the float32 stack the reference uploads)."""
         N, C, H, W = img.shape
         m = self.margin_size
         y = torch.empty([N, C, H + 2 * m, W + 2 * m], dtype=torch.float32, device=img.device)
-        img = img.float().contiguous()
-        _lib.check(_lib.lib().afcm_pad_input(_lib.ptr(img), _lib.ptr(y), None, N * C, H, W, m, _lib.stream_ptr(img.device)))
+        lut = None
+        if img.dtype == torch.uint8:
+            lut = _lib.np_ptr(self.u8_lut())
+            img = img.contiguous()
+        else:
+            img = img.float().contiguous()
+        _lib.check(_lib.lib().afcm_pad_input(_lib.ptr(img), _lib.ptr(y), lut, N * C, H, W, m, _lib.stream_ptr(img.device)))
         return y
 
     def forward(self, ws, img_in, **layer_kwargs):
@@ -486,7 +519,10 @@ class SynthesisNetwork(torch.nn.Module):
             else:
                 include_skip = False
             scale = self.output_scale if idx == last else 1.0                         # NET:699-700 folded
-            x = getattr(self, name)(x, w, img_global, E_features, include_skip, out_scale=scale, **layer_kwargs)
+            # fast path: activations stay fp16 up to the last 3x3 layer, whose result feeds the fp32 ToRGB
+            od = torch.float32 if idx >= last - 1 else None
+            x = getattr(self, name)(x, w, img_global, E_features, include_skip, out_scale=scale, out_dtype=od,
+                                    **layer_kwargs)
         misc.assert_shape(x, [None, self.img_channels_out, self.img_resolution, self.img_resolution])
         return x.to(torch.float32)
 

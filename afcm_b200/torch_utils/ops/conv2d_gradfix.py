@@ -6,6 +6,9 @@ the tcgen05/TMEM implicit GEMM with 16-bit operands and fp32 accumulation (`impl
 Module switches (process-wide, like the reference's `enabled` flag):
     conv_impl : 'f32' | 'tc'      default implementation used by conv2d() / modulated_conv2d()
     tc_dtype  : torch.float16 | torch.bfloat16   operand type of the tensor-core path
+    act_dtype : torch.float32 | torch.float16    storage type of the activations BETWEEN the operators of
+                the generator (float16 = the fast inference path: tcgen05 conv -> fp16 NCHW -> tensor-core
+                filtered_lrelu -> fp16 NCHW -> pack; only meaningful with conv_impl 'tc')
 """
 import numpy as np
 import torch
@@ -14,19 +17,30 @@ from ... import _lib
 
 conv_impl = 'f32'
 tc_dtype = torch.float16
+act_dtype = torch.float32
 enabled = False                      # kept for API compatibility with the reference module
 weight_gradients_disabled = False
 
 _prep_cache = {}
 
 
-def set_conv_impl(impl, dtype=None):
-    global conv_impl, tc_dtype
+def set_conv_impl(impl, dtype=None, act=None):
+    global conv_impl, tc_dtype, act_dtype
     assert impl in ('f32', 'tc')
     conv_impl = impl
     if dtype is not None:
         assert dtype in (torch.float16, torch.bfloat16)
         tc_dtype = dtype
+    act = act or torch.float32
+    assert act in (torch.float32, torch.float16)
+    assert act == torch.float32 or impl == 'tc', 'fp16 activation storage needs the tensor-core path'
+    act_dtype = act
+
+
+def fast_path():
+    """True when the generator runs its fast inference path (tcgen05 conv + tensor-core filtered_lrelu,
+    fp16 activation storage)."""
+    return conv_impl == 'tc' and act_dtype == torch.float16
 
 
 def prepare_weight(w, pre_scale=1.0, normalize=False, want_tc=False, want_wsq=False, dtype=None):
@@ -70,33 +84,39 @@ def prepare_weight(w, pre_scale=1.0, normalize=False, want_tc=False, want_wsq=Fa
     return ent
 
 
-def conv2d_native(x, w, padding, icoef=None, ocoef=None, pre_scale=1.0, normalize=False, impl=None, out=None):
+def conv2d_native(x, w, padding, icoef=None, ocoef=None, pre_scale=1.0, normalize=False, impl=None, out=None,
+                  out_dtype=None):
     """y[n,o] = ocoef[n,o] * conv(icoef[n,i] * x[n,i], prepared(w))  -- the shared formulation of the
-    encoder conv, Conv2dLayer and modulated_conv2d (include/afcm_b200.h)."""
+    encoder conv, Conv2dLayer and modulated_conv2d (include/afcm_b200.h).  The tensor-core path accepts
+    float32 or float16 activations and writes `out_dtype` (float32 default); the exact path is float32 only."""
     impl = impl or conv_impl
     _lib.require_cuda(x, w)
     L = _lib.lib()
     N, Ci, H, W = x.shape
     Co, Ci2, kh, kw = w.shape
     assert Ci == Ci2 and kh == kw
-    if x.dtype != torch.float32:
-        raise RuntimeError('afcm conv2d: activations must be float32 (the reference network runs in fp32)')
+    use_tc = impl == 'tc' and kh == 3 and padding in (1, 2)
+    out_dtype = out_dtype or torch.float32
+    if x.dtype != torch.float32 and not (use_tc and x.dtype == torch.float16):
+        raise RuntimeError('afcm conv2d: activations must be float32 (or float16 on the tensor-core path)')
+    if out_dtype != torch.float32 and not (use_tc and out_dtype == torch.float16):
+        raise RuntimeError('afcm conv2d: the result is float32 (or float16 on the tensor-core path)')
     x = x.contiguous()
     OH, OW = H + 2 * padding - kh + 1, W + 2 * padding - kw + 1
-    y = out if out is not None else torch.empty([N, Co, OH, OW], dtype=torch.float32, device=x.device)
+    y = out if out is not None else torch.empty([N, Co, OH, OW], dtype=out_dtype, device=x.device)
+    assert y.dtype == out_dtype and y.is_contiguous()
     st = _lib.stream_ptr(x.device)
-    use_tc = impl == 'tc' and kh == 3 and padding in (1, 2)
     ent = prepare_weight(w, pre_scale, normalize, want_tc=use_tc)
     if use_tc:
         plane = int(L.afcm_conv_tc_plane_elems(H, W, Ci))
         xp = torch.empty([N, plane], dtype=tc_dtype, device=x.device)
         code = _lib.dtype_code(tc_dtype)
         flops = 2.0 * N * Co * Ci * kh * kw * OH * OW
-        _lib.timed('conv_tc_pack', 4.0 * x.numel() + 2.0 * xp.numel(), lambda: _lib.check(
-            L.afcm_conv_tc_pack(_lib.ptr(x), _lib.ptr(icoef), _lib.ptr(xp), code, N, Ci, H, W, st)))
+        _lib.timed('conv_tc_pack', float(x.element_size() * x.numel() + 2 * xp.numel()), lambda: _lib.check(
+            L.afcm_conv_tc_pack(_lib.ptr(x), _lib.dtype_code(x.dtype), _lib.ptr(icoef), _lib.ptr(xp), code, N, Ci, H, W, st)))
         _lib.timed('conv2d_tc', flops, lambda: _lib.check(
-            L.afcm_conv2d_tc(_lib.ptr(xp), _lib.ptr(ent[('w_tc', tc_dtype)]), _lib.ptr(ocoef), _lib.ptr(y), code,
-                             N, Ci, H, W, Co, padding, st)))
+            L.afcm_conv2d_tc(_lib.ptr(xp), _lib.ptr(ent[('w_tc', tc_dtype)]), _lib.ptr(ocoef), _lib.ptr(y),
+                             _lib.dtype_code(out_dtype), code, N, Ci, H, W, Co, padding, st)))
     else:
         _lib.check(L.afcm_conv2d_f32(_lib.ptr(x), _lib.ptr(ent['w_f32']), _lib.ptr(icoef), _lib.ptr(ocoef), _lib.ptr(y),
                                      N, Ci, H, W, Co, kh, padding, st))

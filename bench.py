@@ -45,17 +45,20 @@ def load_peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source='fallback')
 
 
-def synthetic_inputs(batch, seed=0):
+def synthetic_inputs(batch, seed=0, as_uint8=False):
     """uint8-quantised slices mapped to [-1,1] like data/augment/transforms.py:604-616 of the reference;
-    4-slice stacks; fractional slice position c; z ~ N(0,1)."""
+    4-slice stacks; fractional slice position c; z ~ N(0,1).  as_uint8: return the codes themselves (the
+    generator normalises them on the GPU with the same float64-derived table)."""
     import numpy as np
     import torch
     rng = np.random.RandomState(seed)
-    v = rng.randint(0, 256, size=(batch, 4, 256, 256)).astype(np.float64)
-    x = np.clip(2.0 * v / 255.0 - 1.0, -1, 1).astype(np.float32)
+    u8 = rng.randint(0, 256, size=(batch, 4, 256, 256)).astype(np.uint8)
     g = torch.Generator().manual_seed(seed)
     z = torch.randn(batch, 512, generator=g)
     c = torch.zeros(batch, 1)
+    if as_uint8:
+        return z, c, torch.from_numpy(u8)
+    x = np.clip(2.0 * u8.astype(np.float64) / 255.0 - 1.0, -1, 1).astype(np.float32)
     return z, c, torch.from_numpy(x)
 
 
@@ -157,9 +160,8 @@ def run_reference(args, rank):
 def run_ours(args, rank, world):
     import torch
     import torch.distributed as dist
-    from afcm_b200 import _lib
+    from afcm_b200 import _lib, inference
     from afcm_b200.networks_stylegan3 import afcm_generator
-    from afcm_b200.torch_utils.ops import conv2d_gradfix
 
     local = int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local)
@@ -174,9 +176,9 @@ def run_ours(args, rank, world):
         torch.cuda.synchronize()
 
     B = args.batch
-    conv2d_gradfix.set_conv_impl('tc', torch.float16)
+    inference.set_precision(args.precision)
     G = afcm_generator(seed=0, device=dev)
-    z, c, x = synthetic_inputs(B, seed=rank)
+    z, c, x = synthetic_inputs(B, seed=rank, as_uint8=True)       # slices travel as bytes, normalised on the GPU
     hz, hc, hx = z.pin_memory(), c.pin_memory(), x.pin_memory()
     hy = torch.empty([B, 1, 256, 256], dtype=torch.float32).pin_memory()
     dz, dc, dx = hz.to(dev), hc.to(dev), hx.to(dev)
@@ -253,14 +255,17 @@ def run_ours(args, rank, world):
     r_pack = roof('conv_tc_pack', 'hbm')
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                 ms_per_step=ms_total / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
-                dtype='f16 operands / f32 accumulate (conv), f32 elsewhere', data='synthetic',
+                dtype={'fast': 'f16 operands and activation storage / f32 accumulate', 'tc': 'f16 conv operands / f32 '
+                       'accumulate, f32 storage', 'fp32': 'f32'}[args.precision], data='synthetic',
                 config=dict(workload=WORKLOAD, batch_per_gpu=B, global_batch=B * world, resolution=256,
+                            precision=args.precision,
                             sharding='slices across ranks, no data-path collective',
                             l2='working set per step (>5 GB of activations) exceeds the 126 MB L2; no explicit flush'),
                 clocks=clocks, gpu_launches=int(launches),
                 e2e=dict(value=e2e, unit=UNIT, h2d_bytes_per_step=int(hz.nbytes + hc.nbytes + hx.nbytes),
                          d2h_bytes_per_step=int(hy.nbytes), ms_per_step=ms_e2e / args.steps),
-                roofline=r_conv, rooflines=dict(conv2d_tc=r_conv, filtered_lrelu=r_flr, conv_tc_pack=r_pack))
+                roofline=max([r for r in (r_conv, r_flr, r_pack) if r], key=lambda r: r['ms_per_step'], default=None),
+                rooflines=dict(conv2d_tc=r_conv, filtered_lrelu=r_flr, conv_tc_pack=r_pack))
     if world == 1 and not args.no_cpu_baseline:
         sps, ms, cores, sample = cpu_reference_slices_per_sec(1, 1)
         line['cpu_baseline'] = dict(value=sps, unit=UNIT, cores=cores, kind='port', sample=sample)
@@ -277,6 +282,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=64)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--precision', default='fast', choices=['fast', 'tc', 'fp32'])
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))

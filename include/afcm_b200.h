@@ -160,12 +160,14 @@ int afcm_modconv_coefs(const float* styles, const float* wsq, const float* input
  * vertical taps fall off the plane where TMA zero-fills); afcm_conv_tc_plane_elems(H,W,Ci) elements per
  * sample.  icoef is folded here (modulation on the activation side).
  * Step 2: afcm_conv2d_tc runs the GEMM  D[pixel, o] = sum_{tap,i} A_tap[pixel,i] * B_tap[o,i]  with
- * M = 128 flat pixels, N = up to 256 output channels per CTA, TMA-fed, and writes fp32 NCHW
- * y [N,Co,H+2*pad-2,W+2*pad-2] scaled by ocoef.  ksize must be 3, pad 1 or 2. */
+ * M = 128 flat pixels, N = up to 256 output channels per CTA, TMA-fed, and writes NCHW
+ * y [N,Co,H+2*pad-2,W+2*pad-2] scaled by ocoef (y_dtype AFCM_F32 or AFCM_F16; x_dtype of the pack step
+ * likewise: fp16 activations stay 16-bit between the layers of the fast inference path).  ksize must be 3,
+ * pad 1 or 2. */
 int64_t afcm_conv_tc_plane_elems(int H, int W, int Ci);
-int afcm_conv_tc_pack(const float* x, const float* icoef, void* xp, int tc_dtype,
+int afcm_conv_tc_pack(const void* x, int x_dtype, const float* icoef, void* xp, int tc_dtype,
                       int N, int Ci, int H, int W, void* stream);
-int afcm_conv2d_tc(const void* xp, const void* w_tc, const float* ocoef, float* y, int tc_dtype,
+int afcm_conv2d_tc(const void* xp, const void* w_tc, const float* ocoef, void* y, int y_dtype, int tc_dtype,
                    int N, int Ci, int H, int W, int Co, int pad, void* stream);
 
 /* Debug aid, not part of the stable ABI: progress markers of the tcgen05 kernel in mapped host memory. */

@@ -77,3 +77,61 @@ def test_full_generator_fp32(golden_full):
         y0 = G(torch.as_tensor(g['z'][:1], device=dev), torch.as_tensor(g['c'][:1], device=dev), x[:1], noise_mode='const')
     assert rel_err(y0.cpu().numpy(), g['y0_alone']) < 1e-4
     assert rel_err(y0.cpu().numpy(), g['y'][:1]) < 1e-4
+
+
+FAST_TOL = 2e-2          # max|y - y_ref| / max|y_ref| of the fast path (fp16 operands AND fp16 activation storage)
+FAST_PSNR = 45.0         # dB, peak = max|y_ref|
+
+
+def _psnr(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(10 * np.log10(np.abs(b).max() ** 2 / max(np.mean((a - b) ** 2), 1e-300)))
+
+
+def test_full_generator_fast_path(golden_full):
+    """The benchmarked inference path: tcgen05 convolutions, tensor-core filtered_lrelu, fp16 activations
+    between the operators.  Stated tolerance against the reference fp32 golden output: FAST_TOL / FAST_PSNR.
+    Also: the CUDA-graph replay returns exactly what the eager fast path returns."""
+    from afcm_b200 import inference
+    from afcm_b200.networks_stylegan3 import afcm_generator
+    dev = torch.device('cuda:0')
+    g = golden_full
+    G = afcm_generator(seed=0, device=dev)
+    x = (torch.as_tensor(g['x_u8']).float() * (2.0 / 255.0) - 1.0).clamp(-1, 1).to(dev)
+    z, c = torch.as_tensor(g['z'], device=dev), torch.as_tensor(g['c'], device=dev)
+    inference.set_precision('fast')
+    try:
+        taps = {}
+        _hook(G, taps)
+        with torch.no_grad():
+            y = G(z, c, x, noise_mode='const')
+        assert y.dtype == torch.float32
+        inter = [k for k, v in taps.items() if v.ndim == 4 and v.dtype == torch.float16]
+        assert len(inter) >= 26, inter                    # activations really are stored as fp16
+        err, psnr = rel_err(y.cpu().numpy(), g['y']), _psnr(y.cpu().numpy(), g['y'])
+        print(f'fast path: rel err {err:.3e}, PSNR {psnr:.1f} dB')
+        assert err < FAST_TOL and psnr > FAST_PSNR
+        runner = inference.GraphedGenerator(G, batch=z.shape[0])
+        yg = runner(z, c, x).clone()
+        yg2 = runner(z, c, x)
+        torch.cuda.synchronize()
+        assert torch.equal(yg, y) and torch.equal(yg2, y)
+    finally:
+        inference.set_precision('fp32')
+
+
+def test_tiny_generator_fast_path(golden_tiny):
+    from afcm_b200 import inference
+    dev = torch.device('cuda:0')
+    g = golden_tiny
+    G = _load_tiny(g, dev)
+    inference.set_precision('fast')
+    try:
+        with torch.no_grad():
+            y = G(torch.as_tensor(g['z'], device=dev), torch.as_tensor(g['c'], device=dev),
+                  torch.as_tensor(g['x'], device=dev), noise_mode='const')
+        err = rel_err(y.cpu().numpy(), g['y'])
+        print(f'tiny fast path: rel err {err:.3e}')
+        assert err < FAST_TOL
+    finally:
+        inference.set_precision('fp32')

@@ -92,3 +92,27 @@ def test_full_generator_tc(golden_full):
     print(f'tc fp16: psnr {psnr:.1f} dB, max-abs/peak {np.abs(err).max() / peak:.2e}')
     assert psnr >= 50.0
     assert np.abs(err).max() / peak <= 1e-2
+
+
+@pytest.mark.parametrize('shape', [(2, 128, 96, 36, 36, 2), (1, 4, 64, 52, 52, 2), (2, 91, 181, 30, 22, 2),
+                                   (2, 96, 80, 36, 36, 1), (1, 8, 16, 21, 21, 2)])
+def test_conv2d_tc_fp16_storage(shape):
+    """fp16 activations in, fp16 result out (the storage format of the fast inference path): the same GEMM,
+    so the result equals the fp32-in / fp32-out tensor-core result of the fp16-rounded input, rounded once."""
+    from afcm_b200.torch_utils.ops import conv2d_gradfix
+    N, Ci, Co, H, W, pad = shape
+    dev = torch.device('cuda:0')
+    g = torch.Generator(device='cpu').manual_seed(23)
+    x = torch.randn(N, Ci, H, W, generator=g).to(dev).half()
+    w = torch.randn(Co, Ci, 3, 3, generator=g).to(dev)
+    icoef = (torch.rand(N, Ci, generator=g) + 0.5).to(dev)
+    ocoef = (torch.rand(N, Co, generator=g) + 0.5).to(dev)
+    scale = 1.0 / np.sqrt(Ci * 9)
+    conv2d_gradfix.set_conv_impl('f32', torch.float16)
+    ref = conv2d_gradfix.conv2d_native(x.float(), w, pad, icoef=icoef, ocoef=ocoef, pre_scale=scale, impl='tc')
+    got = conv2d_gradfix.conv2d_native(x, w, pad, icoef=icoef, ocoef=ocoef, pre_scale=scale, impl='tc',
+                                       out_dtype=torch.float16)
+    assert got.dtype == torch.float16 and got.shape == ref.shape
+    assert torch.equal(got, ref.half())          # odd W (21) exercises the scalar pack kernel
+    exact = conv2d_gradfix.conv2d_native(x.float(), w, pad, icoef=icoef, ocoef=ocoef, pre_scale=scale, impl='f32')
+    assert rel_err(got.float().cpu().numpy(), exact.cpu().numpy()) < 3e-3

@@ -19,7 +19,12 @@ from afcm_b200.torch_utils.ops import conv2d_gradfix  # noqa: E402
 from afcm_b200.torch_utils.ops.filtered_lrelu import _run_fused, filtered_lrelu_tc  # noqa: E402
 
 
-def time_cuda(fn, iters=5, warmup=2, flush=None):
+ITERS, WARMUP = 5, 2
+
+
+def time_cuda(fn, iters=None, warmup=None, flush=None):
+    iters = ITERS if iters is None else iters
+    warmup = WARMUP if warmup is None else warmup
     for _ in range(warmup):
         fn()
     ts = []
@@ -39,8 +44,13 @@ def main():
     ap.add_argument('--ops', default='flrelu,conv_tc')
     ap.add_argument('--json', default='')
     ap.add_argument('--tile', default='')
+    ap.add_argument('--layers', default='', help='comma-separated layer names (prefix match on enc<i> / L<i>_); default all')
+    ap.add_argument('--iters', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=2)
     args = ap.parse_args()
     ops = args.ops.split(',')
+    global ITERS, WARMUP
+    ITERS, WARMUP = args.iters, args.warmup
     dev = torch.device('cuda:0')
     peaks = {}
     pk = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'MEASURED_PEAKS.json')
@@ -58,7 +68,10 @@ def main():
         _lib.lib().afcm_filtered_lrelu_set_tile(tw, th)
     rows = []
     tot = dict(flrelu_ms=0.0, flrelu_bytes=0.0, conv_tc_ms=0.0, pack_ms=0.0, conv_f32_ms=0.0, flops=0.0)
+    want = [w for w in args.layers.split(',') if w]
     for name, L in layers:
+        if want and not any(name == w or name.startswith(w + '_') for w in want):
+            continue
         cin, cout = L.in_channels, L.out_channels
         H = int(L.in_size[0]); k = L.conv_kernel; Hc = H + k - 1; out = int(L.out_size[0])
         row = dict(layer=name, cin=cin, cout=cout, H=H, Hc=Hc, out=out, up=L.up_factor, down=L.down_factor)
@@ -83,7 +96,7 @@ def main():
             fn = lambda: filtered_lrelu_tc(x, L.up_filter, L.down_filter, b, up=L.up_factor, down=L.down_factor,
                                            padding=L.padding, gain=float(np.sqrt(2)), slope=0.2, clamp=256.0, out_dtype=out_dt)
             ms = time_cuda(fn, flush=flush)
-            nbytes = 4.0 * B * cout * (Hc * Hc + out * out)
+            nbytes = float(B * cout * (x.element_size() * Hc * Hc + (2 if out_dt == torch.float16 else 4) * out * out))
             row.update(flrelu_tc_ms=ms, flrelu_tc_gbs=nbytes / ms / 1e6, flrelu_tc_frac=nbytes / ms / 1e6 / hbm)
             tot['flrelu_tc_ms'] = tot.get('flrelu_tc_ms', 0.0) + ms; tot['flrelu_tc_bytes'] = tot.get('flrelu_tc_bytes', 0.0) + nbytes
             del x
@@ -91,23 +104,26 @@ def main():
         tot['flops'] += flops
         if k == 3 and ('conv_tc' in ops or 'conv_f32' in ops):
             x = torch.randn(B, cin, H, H, device=dev)
+            if 'f16in' in ops:
+                x = x.half()
             w = L.weight.detach()
             if 'conv_tc' in ops:
                 Lb = _lib.lib()
                 ent = conv2d_gradfix.prepare_weight(w, 1.0, False, want_tc=True)
                 plane = int(Lb.afcm_conv_tc_plane_elems(H, H, cin))
                 xp = torch.empty(B, plane, dtype=torch.float16, device=dev)
-                y = torch.empty(B, cout, Hc, Hc, device=dev)
+                y = torch.empty(B, cout, Hc, Hc, device=dev, dtype=torch.float16 if 'f16out' in ops else torch.float32)
                 st = _lib.stream_ptr(dev)
-                pack = lambda: _lib.check(Lb.afcm_conv_tc_pack(_lib.ptr(x), None, _lib.ptr(xp), 1, B, cin, H, H, st))
+                pack = lambda: _lib.check(Lb.afcm_conv_tc_pack(_lib.ptr(x), _lib.dtype_code(x.dtype), None, _lib.ptr(xp), 1, B, cin, H, H, st))
                 gemm = lambda: _lib.check(Lb.afcm_conv2d_tc(_lib.ptr(xp), _lib.ptr(ent[('w_tc', torch.float16)]), None,
-                                                            _lib.ptr(y), 1, B, cin, H, H, cout, 2, st))
+                                                            _lib.ptr(y), _lib.dtype_code(y.dtype), 1, B, cin, H, H, cout, 2, st))
                 pms = time_cuda(pack, flush=flush); gms = time_cuda(gemm, flush=flush)
-                row.update(pack_ms=pms, conv_tc_ms=gms, conv_tc_tflops=flops / gms / 1e9, conv_tc_frac=flops / gms / 1e9 / tf)
+                pbytes = float(x.element_size() * x.numel() + 2 * xp.numel())
+                row.update(pack_ms=pms, pack_gbs=pbytes / pms / 1e6, conv_tc_ms=gms, conv_tc_tflops=flops / gms / 1e9, conv_tc_frac=flops / gms / 1e9 / tf)
                 tot['conv_tc_ms'] += gms; tot['pack_ms'] += pms
                 del xp, y
             if 'conv_f32' in ops:
-                fms = time_cuda(lambda: conv2d_gradfix.conv2d_native(x, w, 2, impl='f32'), iters=2, warmup=1)
+                fms = time_cuda(lambda: conv2d_gradfix.conv2d_native(x.float(), w, 2, impl='f32'), iters=2, warmup=1)
                 row.update(conv_f32_ms=fms, conv_f32_tflops=flops / fms / 1e9)
                 tot['conv_f32_ms'] += fms
             del x
