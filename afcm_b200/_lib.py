@@ -49,12 +49,13 @@ SIGNATURES = {
     'afcm_modconv_coefs': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'afcm_conv_tc_plane_elems': (_i64, [_i, _i, _i]),
     'afcm_conv_tc_pack': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
-    'afcm_conv2d_tc': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    'afcm_conv2d_tc': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'afcm_conv_tc_debug_buffer': (_vp, [_i]),
     'afcm_fully_connected': (_i, [_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _f, _f, _i, _f, _f, _vp]),
     'afcm_normalize_2nd_moment': (_i, [_vp, _i64, _vp, _i64, _i, _i, _f, _vp]),
     'afcm_adaptive_avgpool': (_i, [_vp, _vp, _i64, _i, _i, _i, _i, _vp]),
     'afcm_pad_input': (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _vp]),
+    'afcm_torgb': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i64, _f, _f, _f, _f, _vp]),
     'afcm_fourier_features': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _vp]),
 }
 

@@ -38,6 +38,7 @@ constexpr long long TC_WATCHDOG_CYCLES = 4000000000LL; // ~2 s: trap instead of 
 
 struct TcParams {
     const float* ocoef;     // [N, Co] or null
+    const float* bias;      // [Co] or null: added after the demodulation scale (the bias of the following filtered_lrelu)
     void* y;                // [N, Co, OH, OW] fp32, or fp16 when y_half
     int y_half;
     int N, Ci, Co, H, W, Wp, OH, OW, pad;
@@ -152,6 +153,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint64_t* tempty = tfull + 2;                                       // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     float* s_ocoef = reinterpret_cast<float*>(tail + 128);              // [2][256]
+    float* s_bias = s_ocoef + 512;                                      // [2][256]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -257,6 +259,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int j = et; j < p.BN; j += 128) {
                 const int o = o0 + j;
                 s_ocoef[acc * 256 + j] = (o < p.Co) ? (p.ocoef ? p.ocoef[(long long)n * p.Co + o] : 1.f) : 0.f;
+                s_bias[acc * 256 + j] = (o < p.Co && p.bias) ? p.bias[o] : 0.f;
             }
             mbar_wait(&tfull[acc], acc_phase, p.dbg, 0x400u | (unsigned)acc);
             tc_fence_after();
@@ -277,12 +280,12 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
                         for (int j = 0; j < 32; j++)
                             if (o0 + c0 + j < p.Co)
-                                yh[(long long)(c0 + j) * ohw] = __float2half_rn(__uint_as_float(v[j]) * s_ocoef[acc * 256 + c0 + j]);
+                                yh[(long long)(c0 + j) * ohw] = __float2half_rn(fmaf(__uint_as_float(v[j]), s_ocoef[acc * 256 + c0 + j], s_bias[acc * 256 + c0 + j]));
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; j++)
                             if (o0 + c0 + j < p.Co)
-                                yb[(long long)(c0 + j) * ohw] = __uint_as_float(v[j]) * s_ocoef[acc * 256 + c0 + j];
+                                yb[(long long)(c0 + j) * ohw] = fmaf(__uint_as_float(v[j]), s_ocoef[acc * 256 + c0 + j], s_bias[acc * 256 + c0 + j]);
                     }
                 }
             }
@@ -505,7 +508,7 @@ extern "C" int afcm_conv_tc_pack(const void* x, int x_dtype, const float* icoef,
     return AFCM_OK;
 }
 
-extern "C" int afcm_conv2d_tc(const void* xp, const void* w_tc, const float* ocoef, void* y, int y_dtype, int tc_dtype,
+extern "C" int afcm_conv2d_tc(const void* xp, const void* w_tc, const float* ocoef, const float* bias, void* y, int y_dtype, int tc_dtype,
                               int N, int Ci, int H, int W, int Co, int pad, void* stream)
 {
     AFCM_CHECK_ARG(xp && w_tc && y, "xp, w_tc and y must be given");
@@ -515,7 +518,7 @@ extern "C" int afcm_conv2d_tc(const void* xp, const void* w_tc, const float* oco
     if (pad != 1 && pad != 2) { set_error("conv2d_tc: padding %d not supported (1 or 2)", pad); return AFCM_ERR_UNSUPPORTED; }
     TcParams p;
     memset(&p, 0, sizeof(p));
-    p.ocoef = ocoef; p.y = y; p.y_half = y_dtype == AFCM_F16; p.dbg = g_dbg_dev; p.dbg_mode = g_dbg_mode;
+    p.ocoef = ocoef; p.bias = bias; p.y = y; p.y_half = y_dtype == AFCM_F16; p.dbg = g_dbg_dev; p.dbg_mode = g_dbg_mode;
     p.N = N; p.Ci = Ci; p.Co = Co; p.H = H; p.W = W; p.Wp = W + 2; p.pad = pad;
     p.OH = H + 2 * pad - 2; p.OW = W + 2 * pad - 2;
     p.n_tiles = ceil_div(Co, 256);
@@ -538,7 +541,7 @@ extern "C" int afcm_conv2d_tc(const void* xp, const void* w_tc, const float* oco
                    TC_BK, (uint32_t)p.BN);
     if (rc) return rc;
 
-    const int smem = TC_STAGES * (TC_A_BYTES + p.BN * TC_BK * 2) + 128 + 2 * 256 * 4 + 1024;
+    const int smem = TC_STAGES * (TC_A_BYTES + p.BN * TC_BK * 2) + 128 + 4 * 256 * 4 + 1024;
     AFCM_CUDA(cudaFuncSetAttribute(conv2d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int grid = sm_count();
     if (grid > p.total_tiles) grid = p.total_tiles;

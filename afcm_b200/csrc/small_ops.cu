@@ -176,6 +176,68 @@ __global__ void __launch_bounds__(256) fourier_features_kernel(const __grid_cons
     }
 }
 
+
+// ---- ToRGB: modulated 1x1 convolution with a handful of output channels + bias + gain/lrelu/clamp + output scale
+// (NET:353-372 with is_torgb, NET:699-700).  HBM-bound: every input plane is read once (pixel pairs, coalesced),
+// the C_out <= 4 dot products stay in registers; the per-sample weights w[o,i] * icoef[n,i] are staged in shared memory.
+constexpr int TORGB_MAX_CO = 4;
+constexpr int TORGB_MAX_CI = 1024;
+
+__device__ __forceinline__ float2 ld_pair(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ float2 ld_pair(const __half* p) { return __half22float2(*reinterpret_cast<const __half2*>(p)); }
+
+template <typename T, int CO>
+__global__ void __launch_bounds__(256)
+torgb_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ icoef,
+             const float* __restrict__ ocoef, const float* __restrict__ b, float* __restrict__ y,
+             int Ci, long long HW, float gain, float slope, float clamp, float out_scale)
+{
+    __shared__ float cw[CO][TORGB_MAX_CI];
+    const int n = blockIdx.y;
+    for (int i = threadIdx.x; i < CO * Ci; i += blockDim.x) {
+        const int o = i / Ci, c = i - o * Ci;
+        cw[o][c] = w[o * Ci + c] * (icoef ? icoef[(long long)n * Ci + c] : 1.f);
+    }
+    __syncthreads();
+    const T* xn = x + (long long)n * Ci * HW;
+    for (long long p = 2 * ((long long)blockIdx.x * blockDim.x + threadIdx.x); p < HW; p += 2LL * gridDim.x * blockDim.x) {
+        float2 acc[CO];
+#pragma unroll
+        for (int o = 0; o < CO; o++) acc[o] = make_float2(0.f, 0.f);
+#pragma unroll 8
+        for (int c = 0; c < Ci; c++) {
+            const float2 v = ld_pair(xn + c * HW + p);
+#pragma unroll
+            for (int o = 0; o < CO; o++) { acc[o].x = fmaf(v.x, cw[o][c], acc[o].x); acc[o].y = fmaf(v.y, cw[o][c], acc[o].y); }
+        }
+#pragma unroll
+        for (int o = 0; o < CO; o++) {
+            const float oc = ocoef ? ocoef[(long long)n * CO + o] : 1.f;
+            const float bb = b ? b[o] : 0.f;
+            float v0 = (acc[o].x * oc + bb) * gain, v1 = (acc[o].y * oc + bb) * gain;
+            v0 = v0 < 0.f ? v0 * slope : v0; v1 = v1 < 0.f ? v1 * slope : v1;
+            v0 = fminf(fmaxf(v0, -clamp), clamp) * out_scale; v1 = fminf(fmaxf(v1, -clamp), clamp) * out_scale;
+            *reinterpret_cast<float2*>(y + ((long long)n * CO + o) * HW + p) = make_float2(v0, v1);
+        }
+    }
+}
+
+template <typename T>
+static int launch_torgb(const void* x, const float* w, const float* icoef, const float* ocoef, const float* b, float* y,
+                        int N, int Ci, int Co, long long HW, float gain, float slope, float clamp, float out_scale, cudaStream_t st)
+{
+    dim3 grid((unsigned)min((long long)ceil_div(HW / 2, 256), 4LL * sm_count()), N);
+#define AFCM_TORGB(CO) torgb_kernel<T, CO><<<grid, 256, 0, st>>>((const T*)x, w, icoef, ocoef, b, y, Ci, HW, gain, slope, clamp, out_scale)
+    switch (Co) {
+    case 1: AFCM_TORGB(1); break;
+    case 2: AFCM_TORGB(2); break;
+    case 3: AFCM_TORGB(3); break;
+    default: AFCM_TORGB(4); break;
+    }
+#undef AFCM_TORGB
+    return AFCM_OK;
+}
+
 static unsigned grid_for(long long total, int per_sm)
 {
     long long blocks = (total + 255) / 256;
@@ -250,6 +312,26 @@ extern "C" int afcm_fourier_features(const float* t, const float* freqs, const f
     FourierParams p = {t, freqs, phases, weight, transform3x3, y, N, C, size_h, size_w, sampling_rate, bandwidth};
     dim3 grid(grid_for((long long)size_h * size_w * C, 4), N);
     fourier_features_kernel<<<grid, 256, 4 * C * sizeof(float), (cudaStream_t)stream>>>(p);
+    AFCM_LAUNCH_CHECK();
+    count_launch();
+    return AFCM_OK;
+}
+
+extern "C" int afcm_torgb(const void* x, int x_dtype, const float* w, const float* icoef, const float* ocoef, const float* b,
+                          float* y, int N, int Ci, int Co, int64_t HW, float gain, float slope, float clamp, float out_scale,
+                          void* stream)
+{
+    AFCM_CHECK_ARG(x && w && y && N > 0 && Ci > 0 && Co > 0 && HW > 0, "empty problem");
+    AFCM_CHECK_ARG(x_dtype == AFCM_F32 || x_dtype == AFCM_F16, "x must be float32 or float16");
+    AFCM_CHECK_ARG(N <= 65535, "batch too large");
+    if (Co > TORGB_MAX_CO || Ci > TORGB_MAX_CI || (HW & 1) || ((uintptr_t)x % (x_dtype == AFCM_F32 ? 8 : 4)) || ((uintptr_t)y % 8)) {
+        set_error("torgb: needs Co <= %d, Ci <= %d, an even plane size and pair-aligned pointers", TORGB_MAX_CO, TORGB_MAX_CI);
+        return AFCM_ERR_UNSUPPORTED;
+    }
+    if (!(clamp >= 0.f)) clamp = 3.4e38f;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (x_dtype == AFCM_F32) launch_torgb<float>(x, w, icoef, ocoef, b, y, N, Ci, Co, HW, gain, slope, clamp, out_scale, st);
+    else launch_torgb<__half>(x, w, icoef, ocoef, b, y, N, Ci, Co, HW, gain, slope, clamp, out_scale, st);
     AFCM_LAUNCH_CHECK();
     count_launch();
     return AFCM_OK;

@@ -21,7 +21,7 @@ from .torch_utils.ops.filtered_lrelu import _run_fused as _flrelu_fused
 
 
 @misc.profiled_function
-def modulated_conv2d(x, w, s, demodulate=True, padding=0, input_gain=None, impl=None, out_dtype=None):
+def modulated_conv2d(x, w, s, demodulate=True, padding=0, input_gain=None, impl=None, out_dtype=None, bias=None):
     """NET:25-64.  x [N,I,H,W], w [O,I,k,k], s [N,I]; input_gain [] / [I] / [N,I] or None.
 
     The reference materialises a per-sample weight w*s*d*g and runs a grouped conv.  Here the same
@@ -50,7 +50,7 @@ def modulated_conv2d(x, w, s, demodulate=True, padding=0, input_gain=None, impl=
     if input_gain is not None and input_gain.numel() != 1 and demodulate:
         icoef = icoef * input_gain.expand(N, I)        # rare general form (NET:55-57); AFCM passes a scalar
     return conv2d_gradfix.conv2d_native(x, w, int(padding), icoef=icoef, ocoef=ocoef, pre_scale=1.0,
-                                        normalize=bool(demodulate), impl=impl, out_dtype=out_dtype)
+                                        normalize=bool(demodulate), impl=impl, out_dtype=out_dtype, bias=bias)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -230,13 +230,13 @@ class _AliasFreeLayerBase(torch.nn.Module):
         pad_hi = pad_total - pad_lo
         self.padding = [int(pad_lo[0]), int(pad_hi[0]), int(pad_lo[1]), int(pad_hi[1])]
 
-    def _filtered_lrelu(self, x, gain, slope, skip=None, out_scale=1.0, out_dtype=None):
+    def _filtered_lrelu(self, x, gain, slope, skip=None, out_scale=1.0, out_dtype=None, bias_done=False):
         """bias + filtered leaky ReLU + clamp (NET:371-372 / NET:510-511), with the skip addition
         (NET:376-377) and the output scale (NET:699-700) folded into the kernel epilogue when no autograd
         graph is needed.  On the fast inference path (conv2d_gradfix.fast_path()) the tensor-core kernel
         runs it on fp16 planes; `out_dtype` then selects the storage type of the result."""
-        b = self.bias.to(torch.float32)
-        needs_graph = torch.is_grad_enabled() and (x.requires_grad or b.requires_grad)
+        b = None if bias_done else self.bias.to(torch.float32)    # bias_done: the conv epilogue already added it
+        needs_graph = torch.is_grad_enabled() and (x.requires_grad or (b is not None and b.requires_grad))
         if not needs_graph:
             px0, px1, py0, py1 = self.padding
             clamp = float(self.conv_clamp) if self.conv_clamp is not None else float('inf')
@@ -253,7 +253,7 @@ class _AliasFreeLayerBase(torch.nn.Module):
                                          skip=skip, out_scale=float(out_scale))
                 if rc == 0:
                     return y
-        y = filtered_lrelu.filtered_lrelu(x=x, fu=self.up_filter, fd=self.down_filter, b=b.to(x.dtype), up=self.up_factor,
+        y = filtered_lrelu.filtered_lrelu(x=x, fu=self.up_filter, fd=self.down_filter, b=None if b is None else b.to(x.dtype), up=self.up_factor,
                                           down=self.down_factor, padding=self.padding, gain=gain, slope=slope,
                                           clamp=self.conv_clamp)
         if skip is not None:
@@ -288,6 +288,27 @@ class SynthesisLayer(_AliasFreeLayerBase):
                             out_half_width, conv_kernel, filter_size, lrelu_upsampling, use_radial_filters, is_torgb,
                             is_critically_sampled)
 
+    def _torgb_fused(self, x, styles, input_gain, out_scale):
+        """ToRGB in one kernel (afcm_torgb): 1x1 modulated conv without demodulation + bias + clamp + output scale."""
+        L = _lib.lib()
+        N, I, H, W = x.shape
+        O = self.out_channels
+        if x.dtype not in (torch.float32, torch.float16) or not x.is_contiguous() or input_gain.numel() != 1:
+            return None
+        s = styles.contiguous().float()
+        icoef = torch.empty([N, I], dtype=torch.float32, device=x.device)
+        st = _lib.stream_ptr(x.device)
+        _lib.check(L.afcm_modconv_coefs(_lib.ptr(s), None, _lib.ptr(input_gain.reshape(1).float().contiguous()),
+                                        _lib.ptr(icoef), None, N, I, O, 0, st))
+        y = torch.empty([N, O, H, W], dtype=torch.float32, device=x.device)
+        clamp = float(self.conv_clamp) if self.conv_clamp is not None else -1.0
+        rc = _lib.timed('torgb', float(x.element_size() * x.numel() + 4 * y.numel()), lambda: L.afcm_torgb(
+            _lib.ptr(x), _lib.dtype_code(x.dtype), _lib.ptr(self.weight.detach().reshape(O, I).float().contiguous()),
+            _lib.ptr(icoef), None, _lib.ptr(self.bias.detach().float().contiguous()), _lib.ptr(y), N, I, O, H * W,
+            1.0, 1.0, clamp, float(out_scale), st))
+        _lib.check(rc, allow_unsupported=True)
+        return y if rc == 0 else None
+
     def forward(self, x, w, global_w, E_features=None, include_skip=True, noise_mode='random', force_fp32=False,
                 update_emas=False, out_scale=1.0, out_dtype=None):
         assert noise_mode in ['random', 'const', 'none']
@@ -305,14 +326,20 @@ class SynthesisLayer(_AliasFreeLayerBase):
         x_skip = None
         if E_features is not None and include_skip:
             x_skip = E_features[self.out_size[0]]
-        fast = conv2d_gradfix.fast_path() and not self.is_torgb
+        fast = conv2d_gradfix.fast_path() and not torch.is_grad_enabled()
+        if fast and self.is_torgb:
+            y = self._torgb_fused(x, styles, input_gain, out_scale)
+            if y is not None:
+                return y
+        fast = fast and not self.is_torgb
         x = modulated_conv2d(x=x if fast else x.float(), w=self.weight, s=styles, padding=self.conv_kernel - 1,
                              demodulate=(not self.is_torgb), input_gain=input_gain,
-                             out_dtype=conv2d_gradfix.act_dtype if fast else None)
+                             out_dtype=conv2d_gradfix.act_dtype if fast else None,
+                             bias=self.bias.detach().float() if fast else None)
         gain = 1 if self.is_torgb else np.sqrt(2)
         slope = 1 if self.is_torgb else 0.2
         x = self._filtered_lrelu(x, gain, slope, skip=x_skip if include_skip else None, out_scale=out_scale,
-                                 out_dtype=out_dtype)
+                                 out_dtype=out_dtype, bias_done=fast)
         misc.assert_shape(x, [None, self.out_channels, int(self.out_size[1]), int(self.out_size[0])])
         return x
 
@@ -343,10 +370,11 @@ class EncoderLayer(_AliasFreeLayerBase):
         if update_emas:
             magnitude_cur = x.detach().to(torch.float32).square().mean()
             self.magnitude_ema.copy_(magnitude_cur.lerp(self.magnitude_ema, self.magnitude_ema_beta))
-        fast = conv2d_gradfix.fast_path()
+        fast = conv2d_gradfix.fast_path() and not torch.is_grad_enabled()
         x = conv2d_gradfix.conv2d_native(x if fast else x.float(), self.weight, self.conv_kernel - 1, pre_scale=self.weight_gain,
-                                         out_dtype=conv2d_gradfix.act_dtype if fast else None)
-        x = self._filtered_lrelu(x, np.sqrt(2), 0.2)
+                                         out_dtype=conv2d_gradfix.act_dtype if fast else None,
+                                         bias=self.bias.detach().float() if fast else None)
+        x = self._filtered_lrelu(x, np.sqrt(2), 0.2, bias_done=fast)
         misc.assert_shape(x, [None, self.out_channels, int(self.out_size[1]), int(self.out_size[0])])
         return x
 
@@ -519,8 +547,8 @@ class SynthesisNetwork(torch.nn.Module):
             else:
                 include_skip = False
             scale = self.output_scale if idx == last else 1.0                         # NET:699-700 folded
-            # fast path: activations stay fp16 up to the last 3x3 layer, whose result feeds the fp32 ToRGB
-            od = torch.float32 if idx >= last - 1 else None
+            # fast path: activations stay fp16 up to and including the input of the fused ToRGB kernel
+            od = None
             x = getattr(self, name)(x, w, img_global, E_features, include_skip, out_scale=scale, out_dtype=od,
                                     **layer_kwargs)
         misc.assert_shape(x, [None, self.img_channels_out, self.img_resolution, self.img_resolution])

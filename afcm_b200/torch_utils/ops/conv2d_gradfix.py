@@ -85,10 +85,11 @@ def prepare_weight(w, pre_scale=1.0, normalize=False, want_tc=False, want_wsq=Fa
 
 
 def conv2d_native(x, w, padding, icoef=None, ocoef=None, pre_scale=1.0, normalize=False, impl=None, out=None,
-                  out_dtype=None):
+                  out_dtype=None, bias=None):
     """y[n,o] = ocoef[n,o] * conv(icoef[n,i] * x[n,i], prepared(w))  -- the shared formulation of the
     encoder conv, Conv2dLayer and modulated_conv2d (include/afcm_b200.h).  The tensor-core path accepts
-    float32 or float16 activations and writes `out_dtype` (float32 default); the exact path is float32 only."""
+    float32 or float16 activations and writes `out_dtype` (float32 default); the exact path is float32 only.
+    `bias` [Co] is added after the ocoef scale (fused in the tensor-core epilogue)."""
     impl = impl or conv_impl
     _lib.require_cuda(x, w)
     L = _lib.lib()
@@ -115,11 +116,14 @@ def conv2d_native(x, w, padding, icoef=None, ocoef=None, pre_scale=1.0, normaliz
         _lib.timed('conv_tc_pack', float(x.element_size() * x.numel() + 2 * xp.numel()), lambda: _lib.check(
             L.afcm_conv_tc_pack(_lib.ptr(x), _lib.dtype_code(x.dtype), _lib.ptr(icoef), _lib.ptr(xp), code, N, Ci, H, W, st)))
         _lib.timed('conv2d_tc', flops, lambda: _lib.check(
-            L.afcm_conv2d_tc(_lib.ptr(xp), _lib.ptr(ent[('w_tc', tc_dtype)]), _lib.ptr(ocoef), _lib.ptr(y),
+            L.afcm_conv2d_tc(_lib.ptr(xp), _lib.ptr(ent[('w_tc', tc_dtype)]), _lib.ptr(ocoef), _lib.ptr(bias), _lib.ptr(y),
                              _lib.dtype_code(out_dtype), code, N, Ci, H, W, Co, padding, st)))
+        bias = None
     else:
         _lib.check(L.afcm_conv2d_f32(_lib.ptr(x), _lib.ptr(ent['w_f32']), _lib.ptr(icoef), _lib.ptr(ocoef), _lib.ptr(y),
                                      N, Ci, H, W, Co, kh, padding, st))
+    if bias is not None:
+        y += bias.reshape(1, -1, 1, 1).to(y.dtype)
     return y
 
 

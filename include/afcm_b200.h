@@ -162,12 +162,13 @@ int afcm_modconv_coefs(const float* styles, const float* wsq, const float* input
  * Step 2: afcm_conv2d_tc runs the GEMM  D[pixel, o] = sum_{tap,i} A_tap[pixel,i] * B_tap[o,i]  with
  * M = 128 flat pixels, N = up to 256 output channels per CTA, TMA-fed, and writes NCHW
  * y [N,Co,H+2*pad-2,W+2*pad-2] scaled by ocoef (y_dtype AFCM_F32 or AFCM_F16; x_dtype of the pack step
- * likewise: fp16 activations stay 16-bit between the layers of the fast inference path).  ksize must be 3,
- * pad 1 or 2. */
+ * likewise: fp16 activations stay 16-bit between the layers of the fast inference path).  bias [Co] or NULL
+ * is added after the scale: y = acc * ocoef + bias (the bias of the filtered_lrelu / bias_act that follows,
+ * NET:371, NET:510, which then runs bias-free).  ksize must be 3, pad 1 or 2. */
 int64_t afcm_conv_tc_plane_elems(int H, int W, int Ci);
 int afcm_conv_tc_pack(const void* x, int x_dtype, const float* icoef, void* xp, int tc_dtype,
                       int N, int Ci, int H, int W, void* stream);
-int afcm_conv2d_tc(const void* xp, const void* w_tc, const float* ocoef, void* y, int y_dtype, int tc_dtype,
+int afcm_conv2d_tc(const void* xp, const void* w_tc, const float* ocoef, const float* bias, void* y, int y_dtype, int tc_dtype,
                    int N, int Ci, int H, int W, int Co, int pad, void* stream);
 
 /* Debug aid, not part of the stable ABI: progress markers of the tcgen05 kernel in mapped host memory. */
@@ -195,6 +196,15 @@ int afcm_adaptive_avgpool(const float* x, float* y, int64_t planes, int H, int W
  * float32 value of every code (computed on the host in float64 exactly like the reference transform). */
 int afcm_pad_input(const void* x, float* y, const float* lut_host, int64_t planes, int H, int W, int margin,
                    void* stream);
+
+/* ToRGB layer in one pass (NET:353-372 with is_torgb, NET:699-700): 1x1 modulated convolution with Co <= 4 output
+ * channels, then the (up 1, down 1) filtered_lrelu = bias, gain, leaky slope, clamp, then the output scale:
+ *   y[n,o,p] = clamp(lrelu((ocoef[n,o] * sum_i w[o,i] * icoef[n,i] * x[n,i,p] + b[o]) * gain, slope), +-clamp) * out_scale
+ * x [N,Ci,HW] float32 or float16 (dense), y [N,Co,HW] float32.  icoef / ocoef / b may be NULL.  Returns
+ * AFCM_ERR_UNSUPPORTED for Co > 4, Ci > 1024 or odd HW (the caller then composes conv + filtered_lrelu). */
+int afcm_torgb(const void* x, int x_dtype, const float* w, const float* icoef, const float* ocoef, const float* b,
+               float* y, int N, int Ci, int Co, int64_t HW, float gain, float slope, float clamp, float out_scale,
+               void* stream);
 
 /* SynthesisInput Fourier features (NET:198-243), API parity only (AFCM never instantiates it).
  * t [N,4] = affine(w); freqs [C,2]; phases [C]; weight [C,C]; y [N,C,size,size]. */

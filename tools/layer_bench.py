@@ -115,7 +115,7 @@ def main():
                 y = torch.empty(B, cout, Hc, Hc, device=dev, dtype=torch.float16 if 'f16out' in ops else torch.float32)
                 st = _lib.stream_ptr(dev)
                 pack = lambda: _lib.check(Lb.afcm_conv_tc_pack(_lib.ptr(x), _lib.dtype_code(x.dtype), None, _lib.ptr(xp), 1, B, cin, H, H, st))
-                gemm = lambda: _lib.check(Lb.afcm_conv2d_tc(_lib.ptr(xp), _lib.ptr(ent[('w_tc', torch.float16)]), None,
+                gemm = lambda: _lib.check(Lb.afcm_conv2d_tc(_lib.ptr(xp), _lib.ptr(ent[('w_tc', torch.float16)]), None, None,
                                                             _lib.ptr(y), _lib.dtype_code(y.dtype), 1, B, cin, H, H, cout, 2, st))
                 pms = time_cuda(pack, flush=flush); gms = time_cuda(gemm, flush=flush)
                 pbytes = float(x.element_size() * x.numel() + 2 * xp.numel())
