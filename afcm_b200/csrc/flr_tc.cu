@@ -57,6 +57,7 @@ struct FlrTcParams {
     int ix0, iy0, iy_step;                                // input origin: col = strip*IXS + ix0, row = seg*iy_step + iy0
     int sx, sy, dx;
     int y_pairs;                                          // y (and skip) rows are pair aligned: vector stores allowed
+    unsigned zero;                                        // always 0 (keeps duplicated constant fragments in registers of their own)
     float slope, out_scale, act_clamp;                    // act_clamp: clamp in the units of R2 (MINMAX mode)
     float kux[24], kuy[24], kdx[24], kdy[24];             // correlation-form taps (kuy, kdx carry gain and the clamp scale)
 };
@@ -143,8 +144,10 @@ template <typename T> struct Pair;
 template <> struct Pair<float> { typedef float2 type; };
 template <> struct Pair<__half> { typedef uint32_t type; };
 
-template <int U, int D, typename TIN, typename TOUT, int ACT>
+template <int U, int D, typename TIN, typename TOUT, int ACT, bool FAST>
 struct FtcWarp {
+    // FAST: no bias and no skip tensor (the fast inference path: the convolution epilogue has already added the
+    // bias).  Zero-filled halo samples then need no masking after the copy and the epilogue has no skip loads.
     using Geo = FtcGeo<U, D>;
     using RawT = typename Pair<TIN>::type;
     using OutPair = typename Pair<TOUT>::type;
@@ -152,23 +155,32 @@ struct FtcWarp {
     static constexpr int JB = 2 * MB;              // 8-wide blocks of up-sampled columns
     static constexpr int NAL = D / 2;              // 16-row chunks of up-sampled rows per window of 8 output rows
     static constexpr int NREL = D;                 // 16-column chunks of up-sampled columns per 8 output columns
-    // constant fragments (the FIR taps)
-    uint32_t a1[Geo::NPH][4], b2[U][2], a3[NAL][4], b4[NREL][2];
+    // constant fragments (the FIR taps); b2r = b2 with the two K halves exchanged (kept as separate registers so
+    // that either order is a ready-made operand pair)
+    uint32_t a1[Geo::NPH][4], b2[U][2], b2r[U][2], a3[NAL][4], b4[NREL][2];
     uint32_t h_one, h_nslope, h_slope, h_cl, h_ncl, h_bias;
     const FlrTcParams& p;
     int g, t;
     // strip state
-    const TIN* xc0;              // plane base + g rows + first column pair of the strip (chunk c at +8c)
+    const TIN* xf;               // next row block to fetch: plane base + (its first row + g) rows + ix + 2t
+    const TIN* xsafe;            // row 0 of the plane at this lane's column origin (source of zero-size copies)
+    int fy;                      // row index of xf
+    int ccol[Geo::NC];           // EDGE: element offset (relative to xf) of chunk c's column pair, clamped into the plane
+    uint32_t csz[Geo::NC];       // EDGE: RAW_BYTES if the column pair is inside the plane, else 0
     uint32_t ring;               // shared-memory address of this lane's slot in stage 0, chunk 0
+    uint32_t rd;                 // byte offset of the stage holding the next row block to convert
     int ix;                      // first input column of the strip
-    TOUT* yt;                    // plane base + (w0 + g) rows + k0 + 2t
+    TOUT* yq;                    // output pointer of the next block pair to emit: row (w0 + 8 b + g), column k0 + 2t
+    int eb;                      // b of yq
     float bias;
     int iy, k0, w0, nwb;
     bool interior;               // every input column this strip reads and every output column it writes exists
     static constexpr int RAW_BYTES = (int)sizeof(RawT);
     static constexpr int CHUNK_BYTES = 32 * RAW_BYTES;               // one chunk of one row block, all lanes
-    static constexpr int STAGE_BYTES = Geo::NC * CHUNK_BYTES;
+    static constexpr int pow2ceil(int v) { int r = 1; while (r < v) r <<= 1; return r; }
+    static constexpr int STAGE_BYTES = pow2ceil(Geo::NC * CHUNK_BYTES);          // power of two: slot = offset & mask
     static constexpr int WARP_RING_BYTES = FTC_STAGES * STAGE_BYTES;
+    static constexpr uint32_t RING_MASK = (uint32_t)(WARP_RING_BYTES - 1);
     // pipeline state.  Strip-local coordinates: X / Y input column / row, J / V up-sampled column / row,
     // K / W output column / row;   up_x[J] = sum_X kux[(X - dx) U - J] in[X],   up_y[V] = sum_Y kuy[U Y - V] in[Y],
     // out_x[K] = sum_J kdx[J - D K - sx] a[J],   out_y[W] = sum_V kdy[V - D W - sy] a[V].
@@ -199,6 +211,9 @@ struct FtcWarp {
                 const int e = U * (2 * t + 8 * r) - 8 * nb - g;
                 b2[nb][r] = pack_h2(tuy[e], tuy[e + U]);
             }
+            // the exchanged copy must not be merged with the original by value numbering: p.zero is 0 at run time
+            b2r[nb][0] = b2[nb][1] + p.zero;
+            b2r[nb][1] = b2[nb][0] + p.zero;
         }
 #pragma unroll
         for (int al = 0; al < NAL; al++) {
@@ -234,76 +249,98 @@ struct FtcWarp {
         const int seg = (int)(r % p.segs);
         const long long plane = r / p.segs;
         const int n = (int)(plane / p.C), c = (int)(plane - (long long)n * p.C);
-        const TIN* xg = (const TIN*)p.x + n * p.xs_n + c * p.xs_c + (long long)g * p.xs_h;
-        bias = p.b ? p.b[c] : 0.f;
+        const TIN* xplane = (const TIN*)p.x + n * p.xs_n + c * p.xs_c;
+        bias = (!FAST && p.b) ? p.b[c] : 0.f;
         h_bias = pack_h2(bias, bias);
         ix = strip * Geo::IXS + p.ix0;
         iy = seg * p.iy_step + p.iy0;
         k0 = strip * 16;
         w0 = seg * p.seg_wblocks * 8;
-        yt = (TOUT*)p.y + n * p.ys_n + c * p.ys_c + (long long)(w0 + g) * p.ys_h + k0 + 2 * t;
-        xc0 = xg + (ix + 2 * t);
+        eb = 0;
+        yq = (TOUT*)p.y + n * p.ys_n + c * p.ys_c + (long long)(w0 + g) * p.ys_h + k0 + 2 * t;
+        fy = iy + g;
+        xf = xplane + (long long)fy * p.xs_h + (ix + 2 * t);
+        xsafe = xplane + (ix + 2 * t);          // + ccol[c] is a readable address in row 0 of the plane
+        rd = 0;
         const int rows_left = p.yh - w0;
         nwb = (rows_left + 7) >> 3;
         if (nwb > p.seg_wblocks) nwb = p.seg_wblocks;
         // ix and xw are even (host-checked), so a column pair is either inside or outside the plane as a whole
-        interior = __all_sync(0xffffffffu, col_mask() == (1u << Geo::NC) - 1u) && k0 + 16 <= p.yw && p.y_pairs;
+        unsigned cm = 0;
+#pragma unroll
+        for (int c8 = 0; c8 < Geo::NC; c8++) {
+            const int col = ix + 8 * c8 + 2 * t;
+            const bool ok = col >= 0 && col < p.xw;
+            if (ok) cm |= 1u << c8;
+            csz[c8] = ok ? (uint32_t)RAW_BYTES : 0u;
+            ccol[c8] = (ok ? col : 0) - (ix + 2 * t);
+        }
+        interior = __all_sync(0xffffffffu, cm == (1u << Geo::NC) - 1u) && k0 + 16 <= p.yw && p.y_pairs;
 #pragma unroll
         for (int mb = 0; mb < MB; mb++) { P[0][mb][0] = P[0][mb][1] = P[1][mb][0] = P[1][mb][1] = 0u; }
 #pragma unroll
         for (int jb = 0; jb < JB; jb++) carry[jb] = 0u;
     }
 
-    // bit c: this lane's column pair of chunk c lies inside the plane
-    __device__ __forceinline__ unsigned col_mask() const
-    {
-        unsigned m = 0;
-#pragma unroll
-        for (int c8 = 0; c8 < Geo::NC; c8++) {
-            const int col = ix + 8 * c8 + 2 * t;
-            if (col >= 0 && col < p.xw) m |= 1u << c8;
-        }
-        return m;
-    }
-
-    // ---- input: issue the asynchronous copies of one block of 8 input rows into the ring (this thread: row g,
-    // NC column pairs).  EDGE: rows / columns outside the plane are zero-filled (src size 0, address clamped).
+    // ---- input: issue the asynchronous copies of the next block of 8 input rows into the ring stage that was
+    // converted last (prefetch distance 3 of 4 stages).  This thread: row g, NC column pairs.
+    // EDGE: rows / columns outside the plane are zero-filled (source size 0, address clamped into the plane).
     template <bool EDGE>
-    __device__ __forceinline__ void fetch(int yb) const
+    __device__ __forceinline__ void fetch()
     {
-        const int row0 = iy + 8 * yb;
-        const uint32_t dst = ring + (uint32_t)((yb & (FTC_STAGES - 1)) * STAGE_BYTES);
+        const uint32_t dst = ring + ((rd + (uint32_t)((FTC_PD - 1) * STAGE_BYTES)) & RING_MASK);   // == stage of block yb + PD
         if (!EDGE) {
-            const TIN* rp = xc0 + row0 * p.xs_h;
 #pragma unroll
-            for (int c8 = 0; c8 < Geo::NC; c8++) cp_async<RAW_BYTES>(dst + c8 * CHUNK_BYTES, rp + 8 * c8, RAW_BYTES);
+            for (int c8 = 0; c8 < Geo::NC; c8++) cp_async<RAW_BYTES>(dst + c8 * CHUNK_BYTES, xf + 8 * c8, RAW_BYTES);
         } else {
-            const int row = row0 + g;
-            const bool rok = row >= 0 && row < p.xh;
-            const TIN* rp = xc0 + (rok ? row0 : -g) * p.xs_h - (ix + 2 * t);          // start of a valid row
+            const bool rok = (unsigned)fy < (unsigned)p.xh;
+            const TIN* rp = rok ? xf : xsafe;
+            const uint32_t rmask = rok ? 0xffffffffu : 0u;
 #pragma unroll
-            for (int c8 = 0; c8 < Geo::NC; c8++) {
-                const int col = ix + 8 * c8 + 2 * t;
-                const bool ok = rok && col >= 0 && col < p.xw;
-                cp_async<RAW_BYTES>(dst + c8 * CHUNK_BYTES, rp + (ok ? col : 0), ok ? RAW_BYTES : 0);
-            }
+            for (int c8 = 0; c8 < Geo::NC; c8++)
+                cp_async<RAW_BYTES>(dst + c8 * CHUNK_BYTES, rp + ccol[c8], (int)(csz[c8] & rmask));
         }
         cp_async_commit();
+        xf += 8 * p.xs_h;
+        fy += 8;
     }
-    __device__ __forceinline__ uint32_t cvt_pair(const float2& v) const { return pack_h2(v.x + bias, v.y + bias); }
+    // the first FTC_PD blocks go to stages 0 .. PD-1
+    __device__ __forceinline__ void prime()
+    {
+#pragma unroll
+        for (int i = 0; i < FTC_PD; i++) {
+            const uint32_t dst = ring + (uint32_t)(i * STAGE_BYTES);
+            const bool rok = (unsigned)fy < (unsigned)p.xh;
+            const TIN* rp = rok ? xf : xsafe;
+            const uint32_t rmask = rok ? 0xffffffffu : 0u;
+#pragma unroll
+            for (int c8 = 0; c8 < Geo::NC; c8++)
+                cp_async<RAW_BYTES>(dst + c8 * CHUNK_BYTES, rp + ccol[c8], (int)(csz[c8] & rmask));
+            cp_async_commit();
+            xf += 8 * p.xs_h;
+            fy += 8;
+        }
+    }
+    __device__ __forceinline__ uint32_t cvt_pair(const float2& v) const
+    {
+        return FAST ? pack_h2(v.x, v.y) : pack_h2(v.x + bias, v.y + bias);
+    }
     __device__ __forceinline__ uint32_t cvt_pair(const uint32_t& v) const
     {
+        if (FAST) return v;
         uint32_t r;
         asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(h_bias));
         return r;
     }
-    // wait until row block yb has landed (at most FTC_PD - 1 younger groups may still be in flight), read this
-    // lane's pairs back, add the bias and round to fp16.  EDGE: pairs outside the plane stay zero (no bias there).
+    // wait until the oldest row block in flight has landed (at most FTC_PD - 1 younger groups may still be in
+    // flight), read this lane's pairs back, add the bias and round to fp16.  EDGE (only with a bias): pairs outside
+    // the plane stay zero.  `cy` = first row of the block (for the row test).
     template <bool EDGE>
-    __device__ __forceinline__ void convert(int yb, uint32_t (&in)[Geo::NC]) const
+    __device__ __forceinline__ void convert(int yb, uint32_t (&in)[Geo::NC])
     {
         cp_async_wait<FTC_PD - 1>();
-        const uint32_t src = ring + (uint32_t)((yb & (FTC_STAGES - 1)) * STAGE_BYTES);
+        const uint32_t src = ring + rd;
+        rd = (rd + (uint32_t)STAGE_BYTES) & RING_MASK;
         RawT raw[Geo::NC];
 #pragma unroll
         for (int c8 = 0; c8 < Geo::NC; c8++) {
@@ -317,14 +354,14 @@ struct FtcWarp {
                 raw[c8] = *reinterpret_cast<RawT*>(&v);
             }
         }
-        if (!EDGE) {
+        if (!EDGE || FAST) {
 #pragma unroll
             for (int c8 = 0; c8 < Geo::NC; c8++) in[c8] = cvt_pair(raw[c8]);
         } else {
             const int row = iy + 8 * yb + g;
-            const unsigned m = (row >= 0 && row < p.xh) ? col_mask() : 0u;
+            const bool rok = row >= 0 && row < p.xh;
 #pragma unroll
-            for (int c8 = 0; c8 < Geo::NC; c8++) in[c8] = ((m >> c8) & 1u) ? cvt_pair(raw[c8]) : 0u;
+            for (int c8 = 0; c8 < Geo::NC; c8++) in[c8] = (rok && csz[c8]) ? cvt_pair(raw[c8]) : 0u;
         }
     }
 
@@ -369,7 +406,7 @@ struct FtcWarp {
                 uint32_t d[2];
                 // slot 0 supplies k 0..7: if it holds the current block the two K halves of the constant swap
                 if (CUR == 1) mma_h(d, quad, b2[NB0 + q][0], b2[NB0 + q][1]);
-                else mma_h(d, quad, b2[NB0 + q][1], b2[NB0 + q][0]);
+                else mma_h(d, quad, b2r[NB0 + q][0], b2r[NB0 + q][1]);
                 e[q][0] = act2(d[0]);
                 e[q][1] = act2(d[1]);
             }
@@ -394,10 +431,18 @@ struct FtcWarp {
 
     // (4) horizontal down-FIR of two blocks of 8 output rows (X0: rows 8b.., X1: rows 8b+8..), fp32 accumulate, store.
     // out_scale is folded into the Td_x taps; a skip tensor is added as skip * out_scale.
-    // ROWS: 3 = both blocks, 2 = only the second (X1), 1 = only the first.
-    template <bool EDGE>
-    __device__ __forceinline__ void emit(int b, const uint32_t (&X0)[JB], const uint32_t (&X1)[JB], int rows) const
+    // `rows`: 3 = both blocks, 2 = only the second (X1), 1 = only the first.  The block pair is the one yq points
+    // at; ADV = number of 8-row blocks yq advances afterwards.
+    template <bool EDGE, int ADV>
+    __device__ __forceinline__ void emit(const uint32_t (&X0)[JB], const uint32_t (&X1)[JB], int rows)
     {
+        TOUT* q0 = yq;                                              // (row w0 + 8 eb + g, col k0 + 2t)
+        TOUT* q1 = yq + 8 * p.ys_h;
+        bool r0 = (rows & 1) != 0, r1 = (rows & 2) != 0;
+        if (EDGE) {
+            r0 = r0 && eb >= 0 && eb < nwb && w0 + 8 * eb + g < p.yh;
+            r1 = r1 && eb + 1 >= 0 && eb + 1 < nwb && w0 + 8 * eb + 8 + g < p.yh;
+        }
 #pragma unroll
         for (int nb = 0; nb < 2; nb++) {
             float c[4] = {0.f, 0.f, 0.f, 0.f};
@@ -407,26 +452,32 @@ struct FtcWarp {
                 const uint32_t quad[4] = {X0[2 * kc], X1[2 * kc], X0[2 * kc + 1], X1[2 * kc + 1]};
                 mma_f(c, quad, b4[rel][0], b4[rel][1]);
             }
-            const bool has_skip = p.skip != nullptr;
+            const bool has_skip = !FAST && p.skip != nullptr;
             const long long kofs = (const TOUT*)p.skip - (const TOUT*)p.y;      // used only when has_skip
-            const int o = 8 * b * p.ys_h + 8 * nb;
-            TOUT* q0 = yt + o;                                          // (row 8b + g, col k0 + 8nb + 2t)
-            TOUT* q1 = yt + (o + 8 * p.ys_h);
             if (!EDGE) {
                 if (has_skip) {
-                    c[0] += (float)q0[kofs] * p.out_scale; c[1] += (float)q0[kofs + 1] * p.out_scale;
-                    c[2] += (float)q1[kofs] * p.out_scale; c[3] += (float)q1[kofs + 1] * p.out_scale;
+                    c[0] += (float)q0[8 * nb + kofs] * p.out_scale; c[1] += (float)q0[8 * nb + kofs + 1] * p.out_scale;
+                    c[2] += (float)q1[8 * nb + kofs] * p.out_scale; c[3] += (float)q1[8 * nb + kofs + 1] * p.out_scale;
                 }
-                if (rows & 1) store_pair(q0, c[0], c[1]);
-                if (rows & 2) store_pair(q1, c[2], c[3]);
+                if (r0) store_pair(q0 + 8 * nb, c[0], c[1]);
+                if (r1) store_pair(q1 + 8 * nb, c[2], c[3]);
+            } else if (p.y_pairs) {
+                // yw is even and the strip origin is even: a column pair is inside or outside as a whole
+                const bool cok = k0 + 8 * nb + 2 * t < p.yw;
+                if (r0 && cok) {
+                    if (has_skip) { c[0] += (float)q0[8 * nb + kofs] * p.out_scale; c[1] += (float)q0[8 * nb + kofs + 1] * p.out_scale; }
+                    store_pair(q0 + 8 * nb, c[0], c[1]);
+                }
+                if (r1 && cok) {
+                    if (has_skip) { c[2] += (float)q1[8 * nb + kofs] * p.out_scale; c[3] += (float)q1[8 * nb + kofs + 1] * p.out_scale; }
+                    store_pair(q1 + 8 * nb, c[2], c[3]);
+                }
             } else {
                 const int xx = k0 + 8 * nb + 2 * t;
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    const int yy = w0 + 8 * b + g + (i >> 1) * 8;
-                    const int wb = b + (i >> 1);
-                    if (((rows >> (i >> 1)) & 1) && wb >= 0 && wb < nwb && yy < p.yh && xx + (i & 1) < p.yw) {
-                        TOUT* q = ((i >> 1) ? q1 : q0) + (i & 1);
+                    if (((i >> 1) ? r1 : r0) && xx + (i & 1) < p.yw) {
+                        TOUT* q = ((i >> 1) ? q1 : q0) + 8 * nb + (i & 1);
                         float v = c[i];
                         if (has_skip) v += (float)q[kofs] * p.out_scale;
                         *q = (TOUT)v;
@@ -434,6 +485,7 @@ struct FtcWarp {
                 }
             }
         }
+        if (ADV) { yq += ADV * 8 * p.ys_h; eb += ADV; }
     }
     static __device__ __forceinline__ void store_pair(float* q, float a, float b) { *reinterpret_cast<float2*>(q) = make_float2(a, b); }
     static __device__ __forceinline__ void store_pair(__half* q, float a, float b) { *reinterpret_cast<__half2*>(q) = __floats2half2_rn(a, b); }
@@ -446,11 +498,11 @@ struct FtcWarp {
     __device__ __forceinline__ void super22(int s, uint32_t (&X0)[JB], uint32_t (&X1)[JB])
     {
         uint32_t in[Geo::NC], win[JB][2];
-        convert<EDGE>(2 * s, in); step1<0>(in); fetch<EDGE>(2 * s + FTC_PD);
+        convert<EDGE>(2 * s, in); step1<0>(in); fetch<EDGE>();
         chunk<0, 0, 0>(0, win, X0);                                     // block 2s-2
-        convert<EDGE>(2 * s + 1, in); step1<1>(in); fetch<EDGE>(2 * s + 1 + FTC_PD);
+        convert<EDGE>(2 * s + 1, in); step1<1>(in); fetch<EDGE>();
         chunk<1, 0, 0>(0, win, X1);                                     // block 2s-1
-        if (!EDGE || s >= 1) emit<EDGE>(2 * s - 2, X0, X1, 3);
+        emit<EDGE, 2>(X0, X1, 3);                                       // EDGE: blocks < 0 are masked by the row test
     }
     __device__ void run22()
     {
@@ -462,6 +514,7 @@ struct FtcWarp {
             hi = min(min((fdiv8(p.xh - 8 - iy) - FTC_PD - 1) >> 1, min((p.yh - w0) >> 4, nwb >> 1)) + 1, S);
         }
         if (hi < lo) hi = lo = 0;
+        eb = -2; yq -= 16 * p.ys_h;
         int s = 0;
         for (; s < (hi > lo ? lo : S); s++) super22<true>(s, X0, X1);
         if (hi > lo) {
@@ -476,14 +529,16 @@ struct FtcWarp {
     __device__ __forceinline__ void iter42(int it, uint32_t (&X0)[JB])
     {
         uint32_t in[Geo::NC], win[JB][2], X1[JB];
-        convert<EDGE>(it, in); step1<CUR>(in); fetch<EDGE>(it + FTC_PD);
+        convert<EDGE>(it, in); step1<CUR>(in); fetch<EDGE>();
         chunk<CUR, 0, 0>(0, win, X1);                                   // block 2it-3
-        if (!EDGE || it >= 2) emit<EDGE>(2 * it - 4, X0, X1, 3);
+        emit<EDGE, 2>(X0, X1, 3);                                       // pair (2it-4, 2it-3)
         chunk<CUR, 2, 0>(0, win, X0);                                   // block 2it-2
     }
     __device__ void run42()
     {
         uint32_t X0[JB];
+#pragma unroll
+        for (int jb = 0; jb < JB; jb++) X0[jb] = 0u;
         const int iters = ((nwb - 1) >> 1) + 3;
         const int S = (iters + 1) >> 1;
         int lo = 0, hi = 0;
@@ -493,6 +548,7 @@ struct FtcWarp {
             hi = min(min((fdiv8(p.xh - 8 - iy) - FTC_PD - 1) >> 1, min((p.yh - w0) >> 5, nwb >> 2)) + 1, S);
         }
         if (hi < lo) hi = lo = 0;
+        eb = -4; yq -= 32 * p.ys_h;
         int s = 0;
         for (; s < (hi > lo ? lo : S); s++) { iter42<true, 0>(2 * s, X0); iter42<true, 1>(2 * s + 1, X0); }
         if (hi > lo) {
@@ -508,12 +564,12 @@ struct FtcWarp {
     __device__ __forceinline__ void iter24(int it, uint32_t (&win)[JB][2], uint32_t (&Xp)[JB])
     {
         uint32_t in[Geo::NC], X[JB];
-        convert<EDGE>(2 * it, in); step1<0>(in); fetch<EDGE>(2 * it + FTC_PD);
+        convert<EDGE>(2 * it, in); step1<0>(in); fetch<EDGE>();
         chunk<0, 0, 2>(1, win, X);                                      // block it-2
-        if (!EDGE || it >= 2) emit<EDGE>(it - 3, Xp, X, 2);
+        emit<EDGE, 1>(Xp, X, 2);                                        // pair (it-3, it-2), second half only
 #pragma unroll
         for (int jb = 0; jb < JB; jb++) Xp[jb] = X[jb];
-        convert<EDGE>(2 * it + 1, in); step1<1>(in); fetch<EDGE>(2 * it + 1 + FTC_PD);
+        convert<EDGE>(2 * it + 1, in); step1<1>(in); fetch<EDGE>();
         chunk<1, 0, 1>(0, win, X);
     }
     __device__ void run24()
@@ -528,6 +584,7 @@ struct FtcWarp {
             hi = min(min((fdiv8(p.xh - 8 - iy) - FTC_PD - 1) >> 1, fdiv8(p.yh - w0) + 1) + 1, iters);
         }
         if (hi < lo) hi = lo = 0;
+        eb = -3; yq -= 24 * p.ys_h;
         int it = 0;
         for (; it < (hi > lo ? lo : iters); it++) iter24<true>(it, win, Xp);
         if (hi > lo) {
@@ -538,9 +595,7 @@ struct FtcWarp {
 
     __device__ void run()
     {
-        // the ring is primed with edge handling; these row blocks precede the steady range anyway
-#pragma unroll
-        for (int i = 0; i < FTC_PD; i++) fetch<true>(i);
+        prime();
         if (U == 2 && D == 2) run22();
         else if (U == 4 && D == 2) run42();
         else run24();
@@ -548,8 +603,11 @@ struct FtcWarp {
     }
 };
 
-template <int U, int D, typename TIN, typename TOUT, int ACT>
-__global__ void __launch_bounds__(FTC_WARPS * 32, (U == 2 && D == 4) ? 2 : (U == 4 ? 4 : 5))
+#ifndef AFCM_FTC_MINB22
+#define AFCM_FTC_MINB22 5
+#endif
+template <int U, int D, typename TIN, typename TOUT, int ACT, bool FAST>
+__global__ void __launch_bounds__(FTC_WARPS * 32, (U == 2 && D == 4) ? 2 : (U == 4 ? 4 : AFCM_FTC_MINB22))
 flr_tc_kernel(const __grid_constant__ FlrTcParams p)
 {
     __shared__ float tab[4][FTC_TAB];
@@ -564,7 +622,7 @@ flr_tc_kernel(const __grid_constant__ FlrTcParams p)
     const long long wid = (long long)blockIdx.x * FTC_WARPS + warp;
     if (wid >= p.total_warps) return;
     extern __shared__ __align__(16) uint8_t ring_smem[];
-    typedef FtcWarp<U, D, TIN, TOUT, ACT> W;
+    typedef FtcWarp<U, D, TIN, TOUT, ACT, FAST> W;
     W w(p, lane);
     w.ring = (uint32_t)__cvta_generic_to_shared(ring_smem) + (uint32_t)(warp * W::WARP_RING_BYTES + lane * W::RAW_BYTES);
     w.load_consts(tab);
@@ -574,7 +632,7 @@ flr_tc_kernel(const __grid_constant__ FlrTcParams p)
 
 static int floor_mod(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
 
-template <int U, int D, typename TIN, typename TOUT, int ACT>
+template <int U, int D, typename TIN, typename TOUT, int ACT, bool FAST>
 static int launch_tc(FlrTcParams& p, int N, cudaStream_t st)
 {
     p.strips = ceil_div(p.yw, 16);
@@ -592,27 +650,27 @@ static int launch_tc(FlrTcParams& p, int N, cudaStream_t st)
     p.total_warps = planes * p.strips * p.segs;
     const long long blocks = (p.total_warps + FTC_WARPS - 1) / FTC_WARPS;
     if (blocks > 0x7fffffffLL) { set_error("filtered_lrelu_tc: too many strips"); return AFCM_ERR_INVALID; }
-    const int smem = FTC_WARPS * FtcWarp<U, D, TIN, TOUT, ACT>::WARP_RING_BYTES;
-    flr_tc_kernel<U, D, TIN, TOUT, ACT><<<(unsigned)blocks, FTC_WARPS * 32, smem, st>>>(p);
+    const int smem = FTC_WARPS * FtcWarp<U, D, TIN, TOUT, ACT, FAST>::WARP_RING_BYTES;
+    flr_tc_kernel<U, D, TIN, TOUT, ACT, FAST><<<(unsigned)blocks, FTC_WARPS * 32, smem, st>>>(p);
     AFCM_LAUNCH_CHECK();
     count_launch();
     return AFCM_OK;
 }
 
-template <typename TIN, typename TOUT, int ACT>
+template <typename TIN, typename TOUT, int ACT, bool FAST>
 static int dispatch_geo(FlrTcParams& p, int N, int up, int down, cudaStream_t st)
 {
-    if (up == 2 && down == 2) return launch_tc<2, 2, TIN, TOUT, ACT>(p, N, st);
-    if (up == 4 && down == 2) return launch_tc<4, 2, TIN, TOUT, ACT>(p, N, st);
-    if (up == 2 && down == 4) return launch_tc<2, 4, TIN, TOUT, ACT>(p, N, st);
+    if (up == 2 && down == 2) return launch_tc<2, 2, TIN, TOUT, ACT, FAST>(p, N, st);
+    if (up == 4 && down == 2) return launch_tc<4, 2, TIN, TOUT, ACT, FAST>(p, N, st);
+    if (up == 2 && down == 4) return launch_tc<2, 4, TIN, TOUT, ACT, FAST>(p, N, st);
     return AFCM_ERR_UNSUPPORTED;
 }
 
 template <typename TIN, typename TOUT>
 static int dispatch_act(FlrTcParams& p, int N, int up, int down, int act, cudaStream_t st)
 {
-    if (act == FTC_ACT_SAT) return dispatch_geo<TIN, TOUT, FTC_ACT_SAT>(p, N, up, down, st);
-    return dispatch_geo<TIN, TOUT, FTC_ACT_MINMAX>(p, N, up, down, st);
+    if (act == FTC_ACT_SAT) return dispatch_geo<TIN, TOUT, FTC_ACT_SAT, false>(p, N, up, down, st);
+    return dispatch_geo<TIN, TOUT, FTC_ACT_MINMAX, false>(p, N, up, down, st);
 }
 
 }  // namespace afcm
@@ -686,8 +744,14 @@ extern "C" int afcm_filtered_lrelu_tc(const void* x, const int64_t* xs, int x_dt
         p.kdy[t] = f / u_scale;
     }
     cudaStream_t st = (cudaStream_t)stream;
+#ifdef AFCM_MINI_U           // development switch: instantiate one kernel only (fast SASS inspection with tools/sass_loops.py)
+    return launch_tc<AFCM_MINI_U, AFCM_MINI_D, __half, __half, FTC_ACT_SAT, true>(p, N, st);
+#else
     if (x_dtype == AFCM_F32 && y_dtype == AFCM_F32) return dispatch_act<float, float>(p, N, up, down, act, st);
     if (x_dtype == AFCM_F32 && y_dtype == AFCM_F16) return dispatch_act<float, __half>(p, N, up, down, act, st);
     if (x_dtype == AFCM_F16 && y_dtype == AFCM_F32) return dispatch_act<__half, float>(p, N, up, down, act, st);
+    // the fast inference path: fp16 planes, bias already added by the convolution epilogue, no skip tensor
+    if (!b && !skip && act == FTC_ACT_SAT) return dispatch_geo<__half, __half, FTC_ACT_SAT, true>(p, N, up, down, st);
     return dispatch_act<__half, __half>(p, N, up, down, act, st);
+#endif
 }

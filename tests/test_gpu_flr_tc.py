@@ -121,3 +121,25 @@ def test_tc_matches_exact_kernel_full_size():
         assert y is not None and y.shape == ref.shape
         err = float((y - ref).abs().max() / ref.abs().max())
         assert err <= TOL, (name, err)
+
+
+@pytest.mark.parametrize('up,down,pad,N,C,H,W', CASES)
+def test_tc_fast_variant_matches_oracle(up, down, pad, N, C, H, W):
+    """The variant the fast inference path runs: fp16 planes in and out, no bias (the convolution epilogue added it),
+    no skip tensor, sat() activation."""
+    import torch
+    from afcm_b200.torch_utils.ops.filtered_lrelu import filtered_lrelu_tc
+    from oracle import afcm_oracle as orc
+    rng = np.random.RandomState(H * 11 + W)
+    fu, fd = _filters(up, down)
+    x = (rng.randn(N, C, H, W) * 2).astype(np.float16)
+    ref = orc.filtered_lrelu(x.astype(np.float32), fu, fd, None, up=up, down=down, padding=pad, gain=np.sqrt(2), slope=0.2, clamp=3.0)
+    ref = ref[0] if isinstance(ref, tuple) else ref
+    dev = torch.device('cuda')
+    y = filtered_lrelu_tc(torch.from_numpy(x).to(dev), torch.from_numpy(fu).to(dev), torch.from_numpy(fd).to(dev), None,
+                          up=up, down=down, padding=pad, gain=np.sqrt(2), slope=0.2, clamp=3.0, out_dtype=torch.float16)
+    assert y is not None and y.dtype == torch.float16
+    y = y.float().cpu().numpy()
+    assert y.shape == ref.shape
+    err = np.abs(y - ref).max() / np.abs(ref).max()
+    assert err <= 2 * TOL, err

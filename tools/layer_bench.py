@@ -93,6 +93,8 @@ def main():
             out_dt = torch.float16 if 'f16out' in ops else torch.float32
             if 'f16in' in ops:
                 x = x.half()
+            if 'nobias' in ops:
+                b = None
             fn = lambda: filtered_lrelu_tc(x, L.up_filter, L.down_filter, b, up=L.up_factor, down=L.down_factor,
                                            padding=L.padding, gain=float(np.sqrt(2)), slope=0.2, clamp=256.0, out_dtype=out_dt)
             ms = time_cuda(fn, flush=flush)
