@@ -30,9 +30,11 @@ namespace afcm {
 
 constexpr int TC_BM = 128;            // pixels per tile (UMMA M)
 constexpr int TC_BK = 64;             // channels per pipeline stage
-constexpr int TC_STAGES = 4;
+constexpr int TC_MAX_STAGES = 8;      // pipeline depth is chosen per launch: small channel tiles need more stages in flight
 constexpr int TC_THREADS = 256;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;          // 16 KB
+constexpr int TC_AROW_PX = TC_BM + 8;                  // row-reuse mode: 128 pixels + the two pixels to the right, rounded to 8
+constexpr int TC_AROW_BYTES = TC_AROW_PX * TC_BK * 2;  // 17 KB
 constexpr int TC_TMEM_COLS = 512;
 constexpr long long TC_WATCHDOG_CYCLES = 4000000000LL; // ~2 s: trap instead of hanging the GPU
 
@@ -44,6 +46,8 @@ struct TcParams {
     int N, Ci, Co, H, W, Wp, OH, OW, pad;
     int BN, n_tiles, m_tiles, cblocks;     // channel tile, #channel tiles, #pixel tiles per sample, ceil(Ci/64)
     int total_tiles;
+    int stages;                            // TMA -> MMA ring depth (2 .. TC_MAX_STAGES)
+    int rowreuse;                          // 1: one A tile of 136 pixels per (ky, channel block) serves the three kx taps
     unsigned idesc;
     unsigned* dbg;          // mapped host memory for progress markers (AFCM_TC_DEBUG), or null
     int dbg_mode;           // debug bisection switches (see afcm_conv_tc_debug_buffer)
@@ -140,19 +144,19 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 // ---- the kernel --------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const __grid_constant__ TcParams p)
+                 const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ TcParams p)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int b_bytes = p.BN * TC_BK * 2;
-    const int stage_bytes = TC_A_BYTES + b_bytes;
-    uint8_t* tail = smem + TC_STAGES * stage_bytes;
-    uint64_t* full = reinterpret_cast<uint64_t*>(tail);                 // [TC_STAGES]
-    uint64_t* empty = full + TC_STAGES;                                 // [TC_STAGES]
-    uint64_t* tfull = empty + TC_STAGES;                                // [2]
+    const int stage_bytes = p.rowreuse ? TC_AROW_BYTES + 3 * b_bytes : TC_A_BYTES + b_bytes;
+    uint8_t* tail = smem + p.stages * stage_bytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(tail);                 // [TC_MAX_STAGES]
+    uint64_t* empty = full + TC_MAX_STAGES;                             // [TC_MAX_STAGES]
+    uint64_t* tfull = empty + TC_MAX_STAGES;                            // [2]
     uint64_t* tempty = tfull + 2;                                       // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-    float* s_ocoef = reinterpret_cast<float*>(tail + 128);              // [2][256]
+    float* s_ocoef = reinterpret_cast<float*>(tail + 256);              // [2][256]
     float* s_bias = s_ocoef + 512;                                      // [2][256]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -162,7 +166,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_b) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < TC_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -176,7 +180,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const uint32_t tmem_base = *tmem_slot;
     if (blockIdx.x == 0 && threadIdx.x == 0) { dbg_mark(p.dbg, 5, tmem_base); dbg_mark(p.dbg, 6, 0xC0DE0001u); }
 
-    const int kblocks = 9 * p.cblocks;
+    const int kblocks = (p.rowreuse ? 3 : 9) * p.cblocks;
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -187,7 +191,21 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 const int r = tile / p.n_tiles;
                 const int mt = r % p.m_tiles, n = r / p.m_tiles;
                 const int p0 = mt * TC_BM, o0 = nt * p.BN;
-                for (int kb = 0; kb < ((p.dbg_mode & 8) ? min(kblocks, TC_STAGES) : kblocks); kb++) {
+                for (int kb = 0; kb < ((p.dbg_mode & 8) ? min(kblocks, p.stages) : kblocks); kb++) {
+                    if (p.rowreuse) {
+                        // stage = (ky, channel block): one A tile of 136 consecutive flat pixels starting at the kx = 0
+                        // tap + the three B tiles of that kernel row; kx becomes a 128-byte offset of the A descriptor
+                        const int ky = kb / p.cblocks, cb = kb - ky * p.cblocks;
+                        mbar_wait(&empty[stage], phase ^ 1, p.dbg, 0x100u | (unsigned)stage);
+                        uint8_t* sa = smem + stage * stage_bytes;
+                        mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
+                        tma_load_3d(sa, &map_a2, &full[stage], cb * TC_BK, p0 + (ky - p.pad) * p.Wp - p.pad, n);
+#pragma unroll
+                        for (int kx = 0; kx < 3; kx++)
+                            tma_load_3d(sa + TC_AROW_BYTES + kx * b_bytes, &map_b, &full[stage], cb * TC_BK, o0, ky * 3 + kx);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
                     const int ky = tap / 3, kx = tap - ky * 3;
                     const int shift = (ky - p.pad) * p.Wp + (kx - p.pad);
@@ -210,7 +228,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         dbg_mark(p.dbg, 15, (unsigned)kb + 1);
                     }
                     if (blockIdx.x == 0) dbg_mark(p.dbg, 0, (unsigned)(kb + 1) | ((unsigned)tile << 16));
-                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -228,6 +246,25 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     tc_fence_after();
                     if (blockIdx.x == 0) dbg_mark(p.dbg, 1, (unsigned)(kb + 1) | ((unsigned)tile << 16));
                     const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+                    if (p.rowreuse) {
+                        const uint32_t sb3 = sa + TC_AROW_BYTES;
+#pragma unroll
+                        for (int kx = 0; kx < 3; kx++) {
+#pragma unroll
+                            for (int k = 0; k < TC_BK / 16; k++) {
+                                // the kx tap is the same tile read one pixel (= one 128-byte swizzled row) further on
+                                // (the swizzle is a function of the shared-memory address, so the descriptor's base-offset
+                                // field stays 0: measured bit-exact on B200, tests/test_gpu_tc.py)
+                                const uint64_t adesc = make_desc(sa + kx * 128 + k * 32, 16, 1024);
+                                const uint64_t bdesc = make_desc(sb3 + kx * b_bytes + k * 32, 16, 1024);
+                                umma_f16(tmem_d, adesc, bdesc, p.idesc, (kb | kx | k) != 0);
+                            }
+                        }
+                        umma_commit(&empty[stage]);
+                        if (kb == kblocks - 1) umma_commit(&tfull[acc]);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     const uint32_t sb = sa + TC_A_BYTES;
 #pragma unroll
                     for (int k = 0; k < TC_BK / 16; k++) {
@@ -240,7 +277,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     umma_commit(&empty[stage]);
                     if (kb == kblocks - 1) umma_commit(&tfull[acc]);
                     if (blockIdx.x == 0) dbg_mark(p.dbg, 2, (unsigned)(kb + 1) | ((unsigned)tile << 16));
-                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
@@ -464,6 +501,8 @@ static int encode_3d(CUtensorMap* map, int tc_dtype, const void* base, uint64_t 
 static unsigned* g_dbg_host = nullptr;
 static unsigned* g_dbg_dev = nullptr;
 static int g_dbg_mode = 0;
+static int g_force_stages = 0;
+static int g_rowreuse = -1;          // -1 automatic, 0 / 1 forced
 
 }  // namespace afcm
 
@@ -482,6 +521,10 @@ extern "C" void* afcm_conv_tc_debug_buffer(int enable)
     if (cudaHostGetDevicePointer((void**)&g_dbg_dev, g_dbg_host, 0) != cudaSuccess) { g_dbg_dev = nullptr; return nullptr; }
     return g_dbg_host;
 }
+
+// Tuning aid (not part of the stable ABI): force the TMA->MMA ring depth (0 = automatic).
+extern "C" int afcm_conv_tc_set_stages(int stages) { g_force_stages = stages; return AFCM_OK; }
+extern "C" int afcm_conv_tc_set_rowreuse(int mode) { g_rowreuse = mode; return AFCM_OK; }
 
 extern "C" int64_t afcm_conv_tc_plane_elems(int H, int W, int Ci)
 {
@@ -541,11 +584,26 @@ extern "C" int afcm_conv2d_tc(const void* xp, const void* w_tc, const float* oco
                    TC_BK, (uint32_t)p.BN);
     if (rc) return rc;
 
-    const int smem = TC_STAGES * (TC_A_BYTES + p.BN * TC_BK * 2) + 128 + 4 * 256 * 4 + 1024;
+    // small channel tiles are bound by re-reading the activation tile once per tap from L2 (9 x 16 KB per 128 pixels):
+    // there one tile per kernel ROW serves its three taps.  Large tiles keep the per-tap stages (B dominates).
+    p.rowreuse = g_rowreuse >= 0 ? g_rowreuse : (p.BN <= 192);
+    CUtensorMap map_a2 = map_a;
+    if (p.rowreuse) {
+        rc = encode_3d(&map_a2, tc_dtype, xp, c_pad, rows, (uint64_t)N, c_pad * 2, rows * c_pad * 2, TC_BK, TC_AROW_PX);
+        if (rc) return rc;
+    }
+    const int stage_bytes = p.rowreuse ? TC_AROW_BYTES + 3 * p.BN * TC_BK * 2 : TC_A_BYTES + p.BN * TC_BK * 2;
+    const int fixed = 256 + 4 * 256 * 4 + 1024;
+    int stages = (max_smem_optin() - fixed) / stage_bytes;
+    if (g_force_stages > 0) stages = g_force_stages;
+    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    if (stages < 2) { set_error("conv2d_tc: not enough shared memory for the pipeline"); return AFCM_ERR_UNSUPPORTED; }
+    p.stages = stages;
+    const int smem = stages * stage_bytes + fixed;
     AFCM_CUDA(cudaFuncSetAttribute(conv2d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int grid = sm_count();
     if (grid > p.total_tiles) grid = p.total_tiles;
-    conv2d_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, p);
+    conv2d_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, map_a2, p);
     AFCM_LAUNCH_CHECK();
     count_launch();
     return AFCM_OK;

@@ -604,7 +604,7 @@ struct FtcWarp {
 };
 
 #ifndef AFCM_FTC_MINB22
-#define AFCM_FTC_MINB22 5
+#define AFCM_FTC_MINB22 4
 #endif
 template <int U, int D, typename TIN, typename TOUT, int ACT, bool FAST>
 __global__ void __launch_bounds__(FTC_WARPS * 32, (U == 2 && D == 4) ? 2 : (U == 4 ? 4 : AFCM_FTC_MINB22))

@@ -171,7 +171,10 @@ int afcm_conv_tc_pack(const void* x, int x_dtype, const float* icoef, void* xp, 
 int afcm_conv2d_tc(const void* xp, const void* w_tc, const float* ocoef, const float* bias, void* y, int y_dtype, int tc_dtype,
                    int N, int Ci, int H, int W, int Co, int pad, void* stream);
 
-/* Debug aid, not part of the stable ABI: progress markers of the tcgen05 kernel in mapped host memory. */
+/* Debug / tuning aids, not part of the stable ABI: progress markers of the tcgen05 kernel in mapped host memory;
+ * forced TMA->MMA ring depth (0 = automatic: as many stages as fit, at most 8). */
+int afcm_conv_tc_set_stages(int stages);
+int afcm_conv_tc_set_rowreuse(int mode);   /* A-tile reuse across the three kx taps: -1 automatic, 0 off, 1 on */
 void* afcm_conv_tc_debug_buffer(int enable);
 
 /* ---------------------------------------------------------------------------------------------- */

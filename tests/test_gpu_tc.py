@@ -116,3 +116,26 @@ def test_conv2d_tc_fp16_storage(shape):
     assert torch.equal(got, ref.half())          # odd W (21) exercises the scalar pack kernel
     exact = conv2d_gradfix.conv2d_native(x.float(), w, pad, icoef=icoef, ocoef=ocoef, pre_scale=scale, impl='f32')
     assert rel_err(got.float().cpu().numpy(), exact.cpu().numpy()) < 3e-3
+
+
+@pytest.mark.parametrize('mode', [0, 1])
+def test_conv2d_tc_rowreuse_modes_exact(mode):
+    """Both pipelines of the tcgen05 kernel -- one A tile per tap, and one A tile per kernel row re-read at a
+    128-byte descriptor offset per kx tap -- are bit-identical to the fp32 kernel on representable inputs."""
+    from afcm_b200 import _lib
+    from afcm_b200.torch_utils.ops import conv2d_gradfix
+    dev = torch.device('cuda:0')
+    g = torch.Generator(device='cpu').manual_seed(5)
+    _lib.lib().afcm_conv_tc_set_rowreuse(mode)
+    try:
+        for (N, Ci, Co, H, W) in [(2, 64, 64, 36, 36), (1, 192, 96, 30, 22), (2, 91, 128, 52, 52), (1, 200, 181, 20, 38)]:
+            x = torch.randint(-4, 5, (N, Ci, H, W), generator=g).float().to(dev)
+            w = torch.randint(-2, 3, (Co, Ci, 3, 3), generator=g).float().to(dev)
+            ref = conv2d_gradfix.conv2d_native(x, w, 2, impl='f32')
+            got = conv2d_gradfix.conv2d_native(x, w, 2, impl='tc')
+            assert torch.equal(ref, got), (mode, N, Ci, Co, H, W)
+            ref1 = conv2d_gradfix.conv2d_native(x, w, 1, impl='f32')
+            got1 = conv2d_gradfix.conv2d_native(x, w, 1, impl='tc')
+            assert torch.equal(ref1, got1), (mode, 'pad1', N, Ci, Co, H, W)
+    finally:
+        _lib.lib().afcm_conv_tc_set_rowreuse(-1)
