@@ -41,7 +41,7 @@ class GraphedGenerator:
     the next call).  Host-side filter taps and tensor maps are baked into the captured kernel parameters, so
     the graph must be rebuilt (`capture()`) after the weights change."""
 
-    def __init__(self, G, batch, device=None, noise_mode='const', warmup=2):
+    def __init__(self, G, batch, device=None, noise_mode='const', warmup=2, input_dtype=torch.float32):
         self.G = G
         self.batch = int(batch)
         p = next(G.parameters())
@@ -51,11 +51,13 @@ class GraphedGenerator:
         self.z = torch.zeros([self.batch, G.z_dim], dtype=torch.float32, device=self.device)
         self.c = torch.zeros([self.batch, max(G.c_dim, 1)], dtype=torch.float32, device=self.device)
         S = G.synthesis
-        self.x = torch.zeros([self.batch, S.img_channels_in, S.img_resolution, S.img_resolution], dtype=torch.float32,
+        assert input_dtype in (torch.float32, torch.uint8)      # uint8 codes are normalised by the pad kernel
+        self.x = torch.zeros([self.batch, S.img_channels_in, S.img_resolution, S.img_resolution], dtype=input_dtype,
                              device=self.device)
         self.y = None
         self.graph = None
         self.precision = None
+        self.kernels_per_replay = 0
 
     def capture(self):
         self.precision = get_precision()
@@ -65,9 +67,12 @@ class GraphedGenerator:
             for _ in range(self.warmup):               # JIT-free, but fills the weight / tap caches before capture
                 self.G(self.z, self.c, self.x, noise_mode=self.noise_mode)
         torch.cuda.current_stream(self.device).wait_stream(side)
+        from . import _lib
         self.graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
         with torch.no_grad(), torch.cuda.graph(self.graph):
             self.y = self.G(self.z, self.c, self.x, noise_mode=self.noise_mode)
+        self.kernels_per_replay = _lib.launch_count() - n0        # library kernels recorded in the graph
         return self
 
     def __call__(self, z, c, x):

@@ -1,0 +1,123 @@
+"""Volume-level inference around the generator forward: the 4-slice input stack and the
+fractional slice position `c` of every output slice, batching, slice sharding across ranks, result collection.
+
+Reference behaviour restated here (paths relative to the reference repo):
+  * data/cmsr_dataset.py:121-151 -- for output slice i and slice thickness t: idx_A = int((i // t) * t); the input is
+    the stack of raw slices (idx_A - t, idx_A, idx_A + t, idx_A + 2t), a raw-zero slice where the index falls outside
+    [0, D-1]; `slice_idx` c = (i - idx_A) / t.  t = 1 is plain cross-modality translation (c = 0), t > 1 is
+    through-plane super-resolution, and t need not be an integer.
+  * models/comodgan_model.py:101-108 -- z ~ N(0, I) per slice, c = slice_idx.
+  * models/predictor.py:144-202 -- slices are processed batch by batch and written into the output volume.  With the
+    2-D generator every output voxel is produced exactly once (patch_halo z = 0), so the overlap averaging of the
+    reference reduces to a plain scatter, which is what collect() does.
+Slices are independent, so ranks own contiguous blocks of output slices (inference.slice_partition) and exchange
+nothing while computing; the only communication is the final gather of results (`collect`), which is not on the data
+path and works with any torch.distributed backend (gloo in the CPU tests, nccl on the GPUs).
+"""
+import numpy as np
+import torch
+
+from .inference import slice_partition
+
+
+def stack_indices(i, num_slices, thickness):
+    """-> (idx_A, [four raw slice indices or None], c) for output slice i (data/cmsr_dataset.py:131-136,151)."""
+    t = thickness
+    idx_a = int((i // t) * t)
+    cand = [idx_a - t, idx_a, idx_a + t, idx_a + 2 * t]
+    sl = []
+    for k, j in enumerate(cand):
+        if k == 0:
+            ok = j >= 0
+        elif k == 1:
+            ok = True
+        else:
+            ok = j <= num_slices - 1
+        sl.append(int(j) if ok else None)
+    return idx_a, sl, np.float32(i - idx_a) / np.float32(t)
+
+
+def build_stacks(volume, lo, hi, thickness=1):
+    """Input stacks and slice positions for output slices [lo, hi) of a raw volume [D,H,W] (uint8 codes or float32
+    already normalised).  Missing neighbours are raw zero -- for uint8 that is code 0, which the generator's input
+    table maps to -1 exactly like the reference transform of a zero slice.  -> x [n,4,H,W], c [n,1] float32."""
+    vol = np.asarray(volume)
+    D, H, W = vol.shape
+    n = max(hi - lo, 0)
+    fill = 0 if vol.dtype == np.uint8 else -1.0
+    x = np.full((n, 4, H, W), fill, dtype=vol.dtype)
+    c = np.zeros((n, 1), dtype=np.float32)
+    for r, i in enumerate(range(lo, hi)):
+        _, sl, ci = stack_indices(i, D, thickness)
+        for k, j in enumerate(sl):
+            if j is not None:
+                x[r, k] = vol[j]
+        c[r, 0] = ci
+    return x, c
+
+
+class VolumePredictor:
+    """Runs the generator over this rank's block of output slices of a volume.
+
+        pred = VolumePredictor(G, batch=32, rank=rank, world_size=world)
+        y_local, (lo, hi) = pred(volume_u8, thickness=5, seed=0)
+        full = pred.collect(y_local, (lo, hi), D)       # rank 0 gets [D,1,H,W], others None
+
+    `run` is any callable (z, c, x) -> y on the generator's device: the module itself, or an
+    inference.GraphedGenerator for fixed batch sizes."""
+
+    def __init__(self, G, batch=32, rank=0, world_size=1, run=None, device=None, z_dim=None):
+        self.G = G
+        self.batch = int(batch)
+        self.rank, self.world_size = int(rank), int(world_size)
+        self.run = run if run is not None else (lambda z, c, x: G(z, c, x, noise_mode='const'))
+        if device is None:
+            device = next(G.parameters()).device if G is not None else torch.device('cpu')
+        self.device = torch.device(device)
+        self.z_dim = z_dim if z_dim is not None else getattr(G, 'z_dim', 512)
+
+    def latents(self, lo, hi, seed):
+        """z of every output slice, a function of (seed, slice index) only, so the result does not depend on how
+        the volume is sharded."""
+        z = torch.empty([max(hi - lo, 0), self.z_dim], dtype=torch.float32)
+        for r, i in enumerate(range(lo, hi)):
+            g = torch.Generator().manual_seed(int(seed) * 1000003 + i)
+            z[r] = torch.randn(self.z_dim, generator=g)
+        return z
+
+    def __call__(self, volume, thickness=1, seed=0):
+        D = int(np.asarray(volume).shape[0])
+        lo, hi = slice_partition(D, self.world_size, self.rank)
+        x, c = build_stacks(volume, lo, hi, thickness)
+        z = self.latents(lo, hi, seed)
+        outs = []
+        with torch.no_grad():
+            for b0 in range(0, hi - lo, self.batch):
+                b1 = min(b0 + self.batch, hi - lo)
+                xb = torch.from_numpy(x[b0:b1]).to(self.device, non_blocking=True)
+                cb = torch.from_numpy(c[b0:b1]).to(self.device, non_blocking=True)
+                zb = z[b0:b1].to(self.device, non_blocking=True)
+                outs.append(self.run(zb, cb, xb).float().cpu())
+        H, W = np.asarray(volume).shape[1:]
+        y = torch.cat(outs) if outs else torch.empty([0, 1, H, W])
+        return y, (lo, hi)
+
+    def collect(self, y_local, block, num_slices):
+        """Gathers the per-rank blocks on rank 0 (plain scatter into the volume: every voxel is produced once)."""
+        import torch.distributed as dist
+        if self.world_size == 1:
+            return y_local
+        per = -(-num_slices // self.world_size)
+        pad = torch.zeros([per] + list(y_local.shape[1:]), dtype=y_local.dtype)
+        pad[:y_local.shape[0]] = y_local
+        backend = dist.get_backend()
+        buf = pad.to(self.device) if backend == 'nccl' else pad
+        parts = [torch.empty_like(buf) for _ in range(self.world_size)] if self.rank == 0 else None
+        dist.gather(buf, parts, dst=0)
+        if self.rank != 0:
+            return None
+        out = torch.empty([num_slices] + list(y_local.shape[1:]), dtype=y_local.dtype)
+        for r, part in enumerate(parts):
+            lo, hi = slice_partition(num_slices, self.world_size, r)
+            out[lo:hi] = part[:hi - lo].cpu()
+        return out

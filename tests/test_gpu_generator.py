@@ -135,3 +135,24 @@ def test_tiny_generator_fast_path(golden_tiny):
         assert err < FAST_TOL
     finally:
         inference.set_precision('fp32')
+
+
+def test_volume_predictor_matches_direct_call(golden_tiny):
+    """Volume runner (stack gather, fractional c, batching with a ragged last batch) == calling the generator on
+    the same stacks directly; uint8 upload == float32 upload of the normalised values."""
+    from afcm_b200.predictor import VolumePredictor, build_stacks
+    from afcm_b200.networks_stylegan3 import SynthesisNetwork
+    dev = torch.device('cuda:0')
+    G = _load_tiny(golden_tiny, dev)
+    rng = np.random.RandomState(3)
+    vol = rng.randint(0, 256, size=(6, 32, 32)).astype(np.uint8)
+    pred = VolumePredictor(G, batch=4)
+    y, blk = pred(vol, thickness=5, seed=1)
+    assert blk == (0, 6) and y.shape == (6, 1, 32, 32)
+    x, c = build_stacks(vol, 0, 6, 5)
+    z = pred.latents(0, 6, 1)
+    xf = torch.from_numpy(SynthesisNetwork.u8_lut()[x]).to(dev)
+    with torch.no_grad():
+        ref = G(z.to(dev), torch.from_numpy(c).to(dev), xf, noise_mode='const').cpu()
+    assert rel_err(y.numpy(), ref.numpy()) < 1e-5
+    assert np.allclose(c[:, 0], [0, .2, .4, .6, .8, 0])
