@@ -53,10 +53,10 @@ struct FlrTcParams {
     int xs_h, ys_h;                                      // row strides (host-checked to fit 32 bits)
     int C, xh, xw, yh, yw;
     int strips, segs, seg_wblocks;                        // 16-column strips, row segments of 8*seg_wblocks rows
-    long long total_warps;
+    int units;                                            // strips * segs: warps per plane
+    unsigned total_warps;
     int ix0, iy0, iy_step;                                // input origin: col = strip*IXS + ix0, row = seg*iy_step + iy0
     int sx, sy, dx;
-    int y_pairs;                                          // y (and skip) rows are pair aligned: vector stores allowed
     unsigned zero;                                        // always 0 (keeps duplicated constant fragments in registers of their own)
     float slope, out_scale, act_clamp;                    // act_clamp: clamp in the units of R2 (MINMAX mode)
     float kux[24], kuy[24], kdx[24], kdy[24];             // correlation-form taps (kuy, kdx carry gain and the clamp scale)
@@ -242,13 +242,10 @@ struct FtcWarp {
         h_ncl = pack_h2(-p.act_clamp, -p.act_clamp);
     }
 
-    __device__ void begin_strip(long long wid)
+    __device__ void begin_strip(int unit, int plane)
     {
-        const int strip = (int)(wid % p.strips);
-        const long long r = wid / p.strips;
-        const int seg = (int)(r % p.segs);
-        const long long plane = r / p.segs;
-        const int n = (int)(plane / p.C), c = (int)(plane - (long long)n * p.C);
+        const int seg = unit / p.strips, strip = unit - seg * p.strips;
+        const int n = plane / p.C, c = plane - n * p.C;
         const TIN* xplane = (const TIN*)p.x + n * p.xs_n + c * p.xs_c;
         bias = (!FAST && p.b) ? p.b[c] : 0.f;
         h_bias = pack_h2(bias, bias);
@@ -275,7 +272,7 @@ struct FtcWarp {
             csz[c8] = ok ? (uint32_t)RAW_BYTES : 0u;
             ccol[c8] = (ok ? col : 0) - (ix + 2 * t);
         }
-        interior = __all_sync(0xffffffffu, cm == (1u << Geo::NC) - 1u) && k0 + 16 <= p.yw && p.y_pairs;
+        interior = __all_sync(0xffffffffu, cm == (1u << Geo::NC) - 1u) && k0 + 16 <= p.yw;
 #pragma unroll
         for (int mb = 0; mb < MB; mb++) { P[0][mb][0] = P[0][mb][1] = P[1][mb][0] = P[1][mb][1] = 0u; }
 #pragma unroll
@@ -461,8 +458,8 @@ struct FtcWarp {
                 }
                 if (r0) store_pair(q0 + 8 * nb, c[0], c[1]);
                 if (r1) store_pair(q1 + 8 * nb, c[2], c[3]);
-            } else if (p.y_pairs) {
-                // yw is even and the strip origin is even: a column pair is inside or outside as a whole
+            } else {
+                // yw is even and the strip origin is even (host-checked): a column pair is inside or outside as a whole
                 const bool cok = k0 + 8 * nb + 2 * t < p.yw;
                 if (r0 && cok) {
                     if (has_skip) { c[0] += (float)q0[8 * nb + kofs] * p.out_scale; c[1] += (float)q0[8 * nb + kofs + 1] * p.out_scale; }
@@ -471,17 +468,6 @@ struct FtcWarp {
                 if (r1 && cok) {
                     if (has_skip) { c[2] += (float)q1[8 * nb + kofs] * p.out_scale; c[3] += (float)q1[8 * nb + kofs + 1] * p.out_scale; }
                     store_pair(q1 + 8 * nb, c[2], c[3]);
-                }
-            } else {
-                const int xx = k0 + 8 * nb + 2 * t;
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    if (((i >> 1) ? r1 : r0) && xx + (i & 1) < p.yw) {
-                        TOUT* q = ((i >> 1) ? q1 : q0) + 8 * nb + (i & 1);
-                        float v = c[i];
-                        if (has_skip) v += (float)q[kofs] * p.out_scale;
-                        *q = (TOUT)v;
-                    }
                 }
             }
         }
@@ -610,23 +596,28 @@ template <int U, int D, typename TIN, typename TOUT, int ACT, bool FAST>
 __global__ void __launch_bounds__(FTC_WARPS * 32, (U == 2 && D == 4) ? 2 : (U == 4 ? 4 : AFCM_FTC_MINB22))
 flr_tc_kernel(const __grid_constant__ FlrTcParams p)
 {
+    // zero-padded tap tables (index e + FTC_TAB_OFS): the fragments below index them with per-lane offsets
     __shared__ float tab[4][FTC_TAB];
-    for (int i = threadIdx.x; i < 4 * FTC_TAB; i += blockDim.x) {
-        const int k = i / FTC_TAB, e = i - k * FTC_TAB - FTC_TAB_OFS;
-        const float* src = k == 0 ? p.kux : (k == 1 ? p.kuy : (k == 2 ? p.kdx : p.kdy));
-        const int n = k < 2 ? 6 * U : 6 * D;
-        tab[k][i - k * FTC_TAB] = (e >= 0 && e < n) ? src[e] : 0.f;
+    for (int i = threadIdx.x; i < FTC_TAB; i += blockDim.x) {
+        const int e = i - FTC_TAB_OFS;
+        const bool u_ok = e >= 0 && e < 6 * U, d_ok = e >= 0 && e < 6 * D;
+        tab[0][i] = u_ok ? p.kux[e] : 0.f;
+        tab[1][i] = u_ok ? p.kuy[e] : 0.f;
+        tab[2][i] = d_ok ? p.kdx[e] : 0.f;
+        tab[3][i] = d_ok ? p.kdy[e] : 0.f;
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long wid = (long long)blockIdx.x * FTC_WARPS + warp;
+    const unsigned wid = blockIdx.x * FTC_WARPS + warp;              // warps run over (plane, segment, strip)
     if (wid >= p.total_warps) return;
+    const int plane = (int)(wid / (unsigned)p.units);                // n * C + c
+    const int unit = (int)(wid - (unsigned)plane * (unsigned)p.units);
     extern __shared__ __align__(16) uint8_t ring_smem[];
     typedef FtcWarp<U, D, TIN, TOUT, ACT, FAST> W;
     W w(p, lane);
     w.ring = (uint32_t)__cvta_generic_to_shared(ring_smem) + (uint32_t)(warp * W::WARP_RING_BYTES + lane * W::RAW_BYTES);
     w.load_consts(tab);
-    w.begin_strip(wid);
+    w.begin_strip(unit, plane);
     w.run();
 }
 
@@ -647,11 +638,12 @@ static int launch_tc(FlrTcParams& p, int N, cudaStream_t st)
     p.seg_wblocks = seg_wblocks;
     p.segs = ceil_div(wblocks, seg_wblocks);
     p.iy_step = seg_wblocks * 8 * D / U;
-    p.total_warps = planes * p.strips * p.segs;
-    const long long blocks = (p.total_warps + FTC_WARPS - 1) / FTC_WARPS;
-    if (blocks > 0x7fffffffLL) { set_error("filtered_lrelu_tc: too many strips"); return AFCM_ERR_INVALID; }
+    p.units = p.strips * p.segs;
+    if (planes * p.units > 0x7fffffffLL) { set_error("filtered_lrelu_tc: too many strips"); return AFCM_ERR_INVALID; }
+    p.total_warps = (unsigned)(planes * p.units);
+    const unsigned blocks = (p.total_warps + FTC_WARPS - 1) / FTC_WARPS;
     const int smem = FTC_WARPS * FtcWarp<U, D, TIN, TOUT, ACT, FAST>::WARP_RING_BYTES;
-    flr_tc_kernel<U, D, TIN, TOUT, ACT, FAST><<<(unsigned)blocks, FTC_WARPS * 32, smem, st>>>(p);
+    flr_tc_kernel<U, D, TIN, TOUT, ACT, FAST><<<blocks, FTC_WARPS * 32, smem, st>>>(p);
     AFCM_LAUNCH_CHECK();
     count_launch();
     return AFCM_OK;
@@ -724,8 +716,12 @@ extern "C" int afcm_filtered_lrelu_tc(const void* x, const int64_t* xs, int x_dt
     p.iy0 = (-p.sy - py0) / up;
     p.slope = slope; p.out_scale = out_scale;
     {
+        // the result is written as aligned column pairs
         const uintptr_t ypair = y_dtype == AFCM_F32 ? 8 : 4;
-        p.y_pairs = !((ys[0] & 1) || (ys[1] & 1) || (ys[2] & 1) || ((uintptr_t)y % ypair) || (skip && ((uintptr_t)skip % ypair)));
+        if ((yw & 1) || (ys[0] & 1) || (ys[1] & 1) || (ys[2] & 1) || ((uintptr_t)y % ypair) || (skip && ((uintptr_t)skip % ypair))) {
+            set_error("filtered_lrelu_tc: y (and skip) must have an even width, even strides and a pair-aligned base address");
+            return AFCM_ERR_UNSUPPORTED;
+        }
     }
     // activation scale: R2 is computed in units of `clamp` when the sat() form applies
     const bool finite_clamp = clamp > 0.f && clamp < 3.0e38f;
