@@ -31,7 +31,7 @@ namespace afcm {
 constexpr int TC_BM = 128;            // pixels per tile (UMMA M)
 constexpr int TC_BK = 64;             // channels per pipeline stage
 constexpr int TC_MAX_STAGES = 8;      // pipeline depth is chosen per launch: small channel tiles need more stages in flight
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 384;         // warps 0-3: TMA producer, MMA issuer, TMEM allocator, idle; warps 4-11: two epilogue groups
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;          // 16 KB
 constexpr int TC_AROW_PX = TC_BM + 8;                  // row-reuse mode: 128 pixels + the two pixels to the right, rounded to 8
 constexpr int TC_AROW_BYTES = TC_AROW_PX * TC_BK * 2;  // 17 KB
@@ -48,6 +48,7 @@ struct TcParams {
     int total_tiles;
     int stages;                            // TMA -> MMA ring depth (2 .. TC_MAX_STAGES)
     int rowreuse;                          // 1: one A tile of 136 pixels per (ky, channel block) serves the three kx taps
+    int bres;                              // 1 (row-reuse mode, single channel tile): all weight tiles stay resident in shared memory
     unsigned idesc;
     unsigned* dbg;          // mapped host memory for progress markers (AFCM_TC_DEBUG), or null
     int dbg_mode;           // debug bisection switches (see afcm_conv_tc_debug_buffer)
@@ -99,6 +100,16 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// One lane of a converged warp (elect.sync): the MMA warp runs its loops and barrier waits warp-uniformly and only the
+// issue itself is predicated.  Under a divergent `if (lane == 0)` the compiler keeps every operand in vector registers
+// and pays an ELECT + R2UR sequence of ~17 dependent instructions (~150 clocks) per tcgen05.mma -- measured as the
+// bottleneck of the whole kernel (profiles/r01_ncu_conv2d_tc_issue.txt).
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -110,6 +121,24 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// Same instruction with the two 64-bit descriptors given as (lo, hi) words: the issuing thread advances only the low
+// (address) words between MMAs, which keeps the issue loop to a couple of integer adds per instruction.  With N <= 64
+// an MMA executes in 32 clocks, so a fatter loop makes the single issuing thread the bottleneck.
+__device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, bool accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+// high word of the shared-memory descriptors used here (SBO 1024 B, version 1, SWIZZLE_128B) and the low word
+// (start address | LBO 16 B); see make_desc
+constexpr uint32_t TC_DESC_HI = (uint32_t)((1024u >> 4) & 0x3fff) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3fff) | ((16u >> 4) << 16); }
+
 __device__ __forceinline__ void umma_commit(uint64_t* bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -149,13 +178,16 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int b_bytes = p.BN * TC_BK * 2;
-    const int stage_bytes = p.rowreuse ? TC_AROW_BYTES + 3 * b_bytes : TC_A_BYTES + b_bytes;
-    uint8_t* tail = smem + p.stages * stage_bytes;
+    const int stage_bytes = p.bres ? TC_AROW_BYTES : (p.rowreuse ? TC_AROW_BYTES + 3 * b_bytes : TC_A_BYTES + b_bytes);
+    const int res_bytes = p.bres ? 9 * p.cblocks * b_bytes : 0;         // resident weights: tile (tap, cb) at (tap * cblocks + cb) * b_bytes
+    uint8_t* ring = smem + res_bytes;
+    uint8_t* tail = ring + p.stages * stage_bytes;
     uint64_t* full = reinterpret_cast<uint64_t*>(tail);                 // [TC_MAX_STAGES]
     uint64_t* empty = full + TC_MAX_STAGES;                             // [TC_MAX_STAGES]
     uint64_t* tfull = empty + TC_MAX_STAGES;                            // [2]
     uint64_t* tempty = tfull + 2;                                       // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* bfull = tempty + 2;                                       // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
     float* s_ocoef = reinterpret_cast<float*>(tail + 256);              // [2][256]
     float* s_bias = s_ocoef + 512;                                      // [2][256]
 
@@ -167,7 +199,8 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
+        mbar_init(bfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -186,18 +219,32 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // ================= TMA producer =================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
+            if (p.bres) {
+                mbar_expect_tx(bfull, (uint32_t)res_bytes);
+                for (int tap = 0; tap < 9; tap++)
+                    for (int cb = 0; cb < p.cblocks; cb++)
+                        tma_load_3d(smem + (tap * p.cblocks + cb) * b_bytes, &map_b, bfull, cb * TC_BK, 0, tap);
+            }
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int nt = tile % p.n_tiles;
                 const int r = tile / p.n_tiles;
                 const int mt = r % p.m_tiles, n = r / p.m_tiles;
                 const int p0 = mt * TC_BM, o0 = nt * p.BN;
                 for (int kb = 0; kb < ((p.dbg_mode & 8) ? min(kblocks, p.stages) : kblocks); kb++) {
+                    if (p.bres) {
+                        const int ky = kb / p.cblocks, cb = kb - ky * p.cblocks;
+                        mbar_wait(&empty[stage], phase ^ 1, p.dbg, 0x100u | (unsigned)stage);
+                        mbar_expect_tx(&full[stage], (uint32_t)TC_AROW_BYTES);
+                        tma_load_3d(ring + stage * stage_bytes, &map_a2, &full[stage], cb * TC_BK, p0 + (ky - p.pad) * p.Wp - p.pad, n);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     if (p.rowreuse) {
                         // stage = (ky, channel block): one A tile of 136 consecutive flat pixels starting at the kx = 0
                         // tap + the three B tiles of that kernel row; kx becomes a 128-byte offset of the A descriptor
                         const int ky = kb / p.cblocks, cb = kb - ky * p.cblocks;
                         mbar_wait(&empty[stage], phase ^ 1, p.dbg, 0x100u | (unsigned)stage);
-                        uint8_t* sa = smem + stage * stage_bytes;
+                        uint8_t* sa = ring + stage * stage_bytes;
                         mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
                         tma_load_3d(sa, &map_a2, &full[stage], cb * TC_BK, p0 + (ky - p.pad) * p.Wp - p.pad, n);
 #pragma unroll
@@ -212,7 +259,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     dbg_mark(p.dbg, 10, (unsigned)kb + 1);
                     mbar_wait(&empty[stage], phase ^ 1, p.dbg, 0x100u | (unsigned)stage);
                     dbg_mark(p.dbg, 11, (unsigned)kb + 1);
-                    uint8_t* sa = smem + stage * stage_bytes;
+                    uint8_t* sa = ring + stage * stage_bytes;
                     uint32_t bytes = (uint32_t)stage_bytes;
                     if (p.dbg_mode & 1) bytes -= TC_A_BYTES;
                     if (p.dbg_mode & 2) bytes -= (uint32_t)b_bytes;
@@ -234,49 +281,57 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0 && !(p.dbg_mode & 8)) {
+        // The whole warp runs the loops and the barrier waits (warp-uniform control flow); one elected lane issues.
+        if (!(p.dbg_mode & 8)) {
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
+            const uint32_t smem_base = smem_u32(smem), ring_base = smem_u32(ring);
+            const uint32_t b_step16 = (p.bres ? (uint32_t)(p.cblocks * b_bytes) : (uint32_t)b_bytes) >> 4;
+            if (p.bres) { mbar_wait(bfull, 0, p.dbg, 0x500u); tc_fence_after(); }
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 mbar_wait(&tempty[acc], acc_phase ^ 1, p.dbg, 0x200u | (unsigned)acc);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256);
+                int ky_ = 0, cb_ = 0;                                   // row-reuse mode: kb = ky_ * cblocks + cb_
                 for (int kb = 0; kb < kblocks; kb++) {
                     mbar_wait(&full[stage], phase, p.dbg, 0x300u | (unsigned)stage);
                     tc_fence_after();
-                    if (blockIdx.x == 0) dbg_mark(p.dbg, 1, (unsigned)(kb + 1) | ((unsigned)tile << 16));
-                    const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+                    const uint32_t sa = ring_base + (uint32_t)(stage * stage_bytes);
+                    const bool last = kb == kblocks - 1;
                     if (p.rowreuse) {
-                        const uint32_t sb3 = sa + TC_AROW_BYTES;
+                        // weights of kernel row ky: in the stage behind the A tile, or in the resident region
+                        const uint32_t sb3 = p.bres ? smem_base + (uint32_t)((ky_ * 3 * p.cblocks + cb_) * b_bytes) : sa + TC_AROW_BYTES;
+                        const uint32_t a_lo = desc_lo(sa), b_lo = desc_lo(sb3);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int kx = 0; kx < 3; kx++) {
+                            for (int kx = 0; kx < 3; kx++) {
 #pragma unroll
-                            for (int k = 0; k < TC_BK / 16; k++) {
-                                // the kx tap is the same tile read one pixel (= one 128-byte swizzled row) further on
-                                // (the swizzle is a function of the shared-memory address, so the descriptor's base-offset
-                                // field stays 0: measured bit-exact on B200, tests/test_gpu_tc.py)
-                                const uint64_t adesc = make_desc(sa + kx * 128 + k * 32, 16, 1024);
-                                const uint64_t bdesc = make_desc(sb3 + kx * b_bytes + k * 32, 16, 1024);
-                                umma_f16(tmem_d, adesc, bdesc, p.idesc, (kb | kx | k) != 0);
+                                for (int k = 0; k < TC_BK / 16; k++) {
+                                    // the kx tap is the same tile read one pixel (= one 128-byte swizzled row) further on
+                                    // (the swizzle is a function of the shared-memory address, so the descriptor's
+                                    // base-offset field stays 0: measured bit-exact on B200, tests/test_gpu_tc.py); one
+                                    // UMMA_K step of 16 channels = 32 bytes inside the swizzled row (16-byte units)
+                                    umma_f16_lohi(tmem_d, a_lo + (uint32_t)(kx * 8 + k * 2), b_lo + kx * b_step16 + (uint32_t)(k * 2),
+                                                  TC_DESC_HI, p.idesc, (kb | kx | k) != 0);
+                                }
                             }
+                            umma_commit(&empty[stage]);
+                            if (last) umma_commit(&tfull[acc]);
                         }
-                        umma_commit(&empty[stage]);
-                        if (kb == kblocks - 1) umma_commit(&tfull[acc]);
-                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
-                        continue;
-                    }
-                    const uint32_t sb = sa + TC_A_BYTES;
-#pragma unroll
-                    for (int k = 0; k < TC_BK / 16; k++) {
+                        if (++cb_ == p.cblocks) { cb_ = 0; ky_++; }
+                    } else {
                         // A and B are both K-major SWIZZLE_128B tiles of 128-byte rows: one UMMA_K step of 16
                         // channels = 32 bytes inside the swizzled row, 8-row groups 1024 B apart (SBO)
-                        const uint64_t adesc = make_desc(sa + k * 32, 16, 1024);
-                        const uint64_t bdesc = make_desc(sb + k * 32, 16, 1024);
-                        umma_f16(tmem_d, adesc, bdesc, p.idesc, (kb | k) != 0);
+                        const uint32_t a_lo = desc_lo(sa), b_lo = desc_lo(sa + TC_A_BYTES);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < TC_BK / 16; k++)
+                                umma_f16_lohi(tmem_d, a_lo + (uint32_t)(k * 2), b_lo + (uint32_t)(k * 2), TC_DESC_HI, p.idesc, (kb | k) != 0);
+                            umma_commit(&empty[stage]);
+                            if (last) umma_commit(&tfull[acc]);
+                        }
                     }
-                    umma_commit(&empty[stage]);
-                    if (kb == kblocks - 1) umma_commit(&tfull[acc]);
-                    if (blockIdx.x == 0) dbg_mark(p.dbg, 2, (unsigned)(kb + 1) | ((unsigned)tile << 16));
+                    __syncwarp();
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -284,45 +339,69 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
     } else if (warp >= 4 && !(p.dbg_mode & 8)) {
         // ================= epilogue =================
-        const int wq = warp & 3;
+        // Two groups of four warps (one warp per TMEM lane quadrant each) take alternate 32-channel column chunks of
+        // the accumulator: with small channel tiles the store loop, not the MMA, bounds the tile time.
+        const int wq = warp & 3, grp = (warp - 4) >> 2;
         const int et = threadIdx.x - 128;
         int acc = 0; uint32_t acc_phase = 0;
         const long long ohw = (long long)p.OH * p.OW;
+        const long long cstride = ohw * (p.y_half ? 2 : 4);          // bytes between output channels
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const int nt = tile % p.n_tiles;
             const int r = tile / p.n_tiles;
             const int mt = r % p.m_tiles, n = r / p.m_tiles;
             const int o0 = nt * p.BN;
-            for (int j = et; j < p.BN; j += 128) {
+            for (int j = et; j < p.BN; j += 256) {
                 const int o = o0 + j;
                 s_ocoef[acc * 256 + j] = (o < p.Co) ? (p.ocoef ? p.ocoef[(long long)n * p.Co + o] : 1.f) : 0.f;
                 s_bias[acc * 256 + j] = (o < p.Co && p.bias) ? p.bias[o] : 0.f;
             }
             mbar_wait(&tfull[acc], acc_phase, p.dbg, 0x400u | (unsigned)acc);
             tc_fence_after();
-            if (blockIdx.x == 0 && et == 0) dbg_mark(p.dbg, 3, (unsigned)tile + 1);
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             const int pix = mt * TC_BM + wq * 32 + lane;
             const int oy = pix / p.Wp, ox = pix - oy * p.Wp;
             const bool ok = oy < p.OH && ox < p.OW;
-            const long long yofs = ((long long)n * p.Co + o0) * ohw + (long long)oy * p.OW + ox;
-            float* yb = reinterpret_cast<float*>(p.y) + yofs;
-            __half* yh = reinterpret_cast<__half*>(p.y) + yofs;
-            for (int c0 = 0; c0 < p.BN; c0 += 32) {
+            char* ybase = reinterpret_cast<char*>(p.y) +
+                          (((long long)n * p.Co + o0) * ohw + (long long)oy * p.OW + ox) * (p.y_half ? 2 : 4);
+            for (int c0 = grp * 32; c0 < p.BN; c0 += 64) {
                 uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * 256 + c0), v);
-                tmem_ld_wait();
-                if (ok) {
-                    if (p.y_half) {
+                if (!(p.dbg_mode & 32)) {
+                    tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * 256 + c0), v);
+                    tmem_ld_wait();
+                }
+                if (ok && !(p.dbg_mode & 16)) {
+                    const float4* oc4 = reinterpret_cast<const float4*>(s_ocoef + acc * 256 + c0);
+                    const float4* bi4 = reinterpret_cast<const float4*>(s_bias + acc * 256 + c0);
+                    char* q = ybase + c0 * cstride;
+                    const int nch = min(32, p.Co - o0 - c0);               // channels of this chunk that exist
+                    if (nch >= 32) {
 #pragma unroll
-                        for (int j = 0; j < 32; j++)
-                            if (o0 + c0 + j < p.Co)
-                                yh[(long long)(c0 + j) * ohw] = __float2half_rn(fmaf(__uint_as_float(v[j]), s_ocoef[acc * 256 + c0 + j], s_bias[acc * 256 + c0 + j]));
+                        for (int j4 = 0; j4 < 8; j4++) {
+                            const float4 oc = oc4[j4], bi = bi4[j4];
+                            const float r0 = fmaf(__uint_as_float(v[4 * j4 + 0]), oc.x, bi.x), r1 = fmaf(__uint_as_float(v[4 * j4 + 1]), oc.y, bi.y);
+                            const float r2 = fmaf(__uint_as_float(v[4 * j4 + 2]), oc.z, bi.z), r3 = fmaf(__uint_as_float(v[4 * j4 + 3]), oc.w, bi.w);
+                            if (p.y_half) {
+                                *reinterpret_cast<__half*>(q) = __float2half_rn(r0); q += cstride;
+                                *reinterpret_cast<__half*>(q) = __float2half_rn(r1); q += cstride;
+                                *reinterpret_cast<__half*>(q) = __float2half_rn(r2); q += cstride;
+                                *reinterpret_cast<__half*>(q) = __float2half_rn(r3); q += cstride;
+                            } else {
+                                *reinterpret_cast<float*>(q) = r0; q += cstride;
+                                *reinterpret_cast<float*>(q) = r1; q += cstride;
+                                *reinterpret_cast<float*>(q) = r2; q += cstride;
+                                *reinterpret_cast<float*>(q) = r3; q += cstride;
+                            }
+                        }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 32; j++)
-                            if (o0 + c0 + j < p.Co)
-                                yb[(long long)(c0 + j) * ohw] = fmaf(__uint_as_float(v[j]), s_ocoef[acc * 256 + c0 + j], s_bias[acc * 256 + c0 + j]);
+                        for (int j = 0; j < 32; j++) {
+                            if (j < nch) {
+                                const float rj = fmaf(__uint_as_float(v[j]), s_ocoef[acc * 256 + c0 + j], s_bias[acc * 256 + c0 + j]);
+                                if (p.y_half) *reinterpret_cast<__half*>(q + j * cstride) = __float2half_rn(rj);
+                                else *reinterpret_cast<float*>(q + j * cstride) = rj;
+                            }
+                        }
                     }
                 }
             }
@@ -503,6 +582,7 @@ static unsigned* g_dbg_dev = nullptr;
 static int g_dbg_mode = 0;
 static int g_force_stages = 0;
 static int g_rowreuse = -1;          // -1 automatic, 0 / 1 forced
+static int g_bres = 1;               // resident weights allowed
 
 }  // namespace afcm
 
@@ -524,7 +604,13 @@ extern "C" void* afcm_conv_tc_debug_buffer(int enable)
 
 // Tuning aid (not part of the stable ABI): force the TMA->MMA ring depth (0 = automatic).
 extern "C" int afcm_conv_tc_set_stages(int stages) { g_force_stages = stages; return AFCM_OK; }
-extern "C" int afcm_conv_tc_set_rowreuse(int mode) { g_rowreuse = mode; return AFCM_OK; }
+// -1 automatic, 0 per-tap pipeline, 1 row-reuse (resident weights where they fit), 2 row-reuse with streamed weights
+extern "C" int afcm_conv_tc_set_rowreuse(int mode)
+{
+    g_rowreuse = mode < 0 ? -1 : (mode ? 1 : 0);
+    g_bres = mode != 2;
+    return AFCM_OK;
+}
 
 extern "C" int64_t afcm_conv_tc_plane_elems(int H, int W, int Ci)
 {
@@ -592,14 +678,17 @@ extern "C" int afcm_conv2d_tc(const void* xp, const void* w_tc, const float* oco
         rc = encode_3d(&map_a2, tc_dtype, xp, c_pad, rows, (uint64_t)N, c_pad * 2, rows * c_pad * 2, TC_BK, TC_AROW_PX);
         if (rc) return rc;
     }
-    const int stage_bytes = p.rowreuse ? TC_AROW_BYTES + 3 * p.BN * TC_BK * 2 : TC_A_BYTES + p.BN * TC_BK * 2;
     const int fixed = 256 + 4 * 256 * 4 + 1024;
-    int stages = (max_smem_optin() - fixed) / stage_bytes;
+    // a single channel tile whose 9 x cblocks weight tiles fit next to a 3-deep A ring: keep the weights resident
+    const int res_bytes = 9 * p.cblocks * p.BN * TC_BK * 2;
+    p.bres = p.rowreuse && g_bres != 0 && p.n_tiles == 1 && res_bytes + 3 * TC_AROW_BYTES + fixed <= max_smem_optin();
+    const int stage_bytes = p.bres ? TC_AROW_BYTES : (p.rowreuse ? TC_AROW_BYTES + 3 * p.BN * TC_BK * 2 : TC_A_BYTES + p.BN * TC_BK * 2);
+    int stages = (max_smem_optin() - fixed - (p.bres ? res_bytes : 0)) / stage_bytes;
     if (g_force_stages > 0) stages = g_force_stages;
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     if (stages < 2) { set_error("conv2d_tc: not enough shared memory for the pipeline"); return AFCM_ERR_UNSUPPORTED; }
     p.stages = stages;
-    const int smem = stages * stage_bytes + fixed;
+    const int smem = stages * stage_bytes + fixed + (p.bres ? res_bytes : 0);
     AFCM_CUDA(cudaFuncSetAttribute(conv2d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int grid = sm_count();
     if (grid > p.total_tiles) grid = p.total_tiles;

@@ -174,7 +174,7 @@ int afcm_conv2d_tc(const void* xp, const void* w_tc, const float* ocoef, const f
 /* Debug / tuning aids, not part of the stable ABI: progress markers of the tcgen05 kernel in mapped host memory;
  * forced TMA->MMA ring depth (0 = automatic: as many stages as fit, at most 8). */
 int afcm_conv_tc_set_stages(int stages);
-int afcm_conv_tc_set_rowreuse(int mode);   /* A-tile reuse across the three kx taps: -1 automatic, 0 off, 1 on */
+int afcm_conv_tc_set_rowreuse(int mode);   /* A-tile reuse across the kx taps: -1 automatic, 0 off, 1 on, 2 on without resident weights */
 void* afcm_conv_tc_debug_buffer(int enable);
 
 /* ---------------------------------------------------------------------------------------------- */

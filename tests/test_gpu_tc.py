@@ -118,10 +118,11 @@ def test_conv2d_tc_fp16_storage(shape):
     assert rel_err(got.float().cpu().numpy(), exact.cpu().numpy()) < 3e-3
 
 
-@pytest.mark.parametrize('mode', [0, 1])
+@pytest.mark.parametrize('mode', [0, 1, 2])
 def test_conv2d_tc_rowreuse_modes_exact(mode):
-    """Both pipelines of the tcgen05 kernel -- one A tile per tap, and one A tile per kernel row re-read at a
-    128-byte descriptor offset per kx tap -- are bit-identical to the fp32 kernel on representable inputs."""
+    """All pipelines of the tcgen05 kernel -- one A tile per tap (0); one A tile per kernel row re-read at a 128-byte
+    descriptor offset per kx tap, with the weights resident in shared memory where they fit (1) or streamed (2) -- are
+    bit-identical to the fp32 kernel on representable inputs."""
     from afcm_b200 import _lib
     from afcm_b200.torch_utils.ops import conv2d_gradfix
     dev = torch.device('cuda:0')
