@@ -168,9 +168,18 @@ def run_ours(args, rank, world):
     dev = torch.device('cuda', local)
     _lib.check(_lib.lib().afcm_device_check())
     if world > 1:
-        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
-            os.environ['NCCL_DEBUG'] = 'WARN'          # keep stdout to the one JSON line (NCCL prints its version there)
-        dist.init_process_group('nccl', device_id=dev)
+        # keep stdout to the one JSON line: NCCL prints its version banner there when the communicator is created
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     def barrier():
         if world > 1:
@@ -246,6 +255,16 @@ def run_ours(args, rank, world):
             dist.destroy_process_group()
         return
 
+    def ncu_traffic(pattern):
+        """DRAM read+write bytes per launch of the kernels whose name contains `pattern`, from the committed ncu pass over
+        this same command at batch 64 (profiles/traffic_bench_b64.json, written by tools/summarize_profiles.py)."""
+        path = os.path.join(ROOT, 'profiles', 'traffic_bench_b64.json')
+        if B != 64 or args.precision != 'fast' or not os.path.exists(path):
+            return None
+        ent = [v for k, v in json.load(open(path)).items() if pattern in k]
+        n = sum(v['launches'] for v in ent)
+        return sum(v['launches'] * v['dram_bytes_per_launch'] for v in ent) / n if n else None
+
     def roof(name, bound):
         d = prof.get(name)
         if not d or d['ms'] <= 0:
@@ -256,7 +275,9 @@ def run_ours(args, rank, world):
         else:
             ach = d['work'] / d['ms'] / 1e6          # GB/s
             peak, unit = peaks['hbm'], 'GB/s'
-        return dict(kernel=name, bound=bound, achieved=ach, peak=peak, unit=unit, frac=ach / peak, traffic=None,
+        return dict(kernel=name, bound=bound, achieved=ach, peak=peak, unit=unit, frac=ach / peak,
+                    traffic=ncu_traffic({'conv2d_tc': 'conv2d_tc_kernel', 'filtered_lrelu': 'flr_tc_kernel',
+                                         'conv_tc_pack': 'tc_pack_pairs_kernel'}.get(name, name)),
                     peak_source=peaks['source'] + (' (sustained bf16 cuBLAS)' if bound == 'tensor' else ' (copy)'),
                     launches_per_step=d['launches'] // max(min(args.steps, 3), 1),
                     ms_per_step=d['ms'] / max(min(args.steps, 3), 1),

@@ -33,26 +33,42 @@ def short(name):
 
 
 def launches(src, dst):
-    rows = []
+    """Launch list with device time (and, when the capture has them, DRAM bytes) per launch; also writes
+    <dst>.traffic.json = {kernel: average DRAM read+write bytes per launch}, which bench.py reports as roofline.traffic."""
+    import json
+    per_id = OrderedDict()
     with open(src) as f:
         lines = [l for l in f if l.startswith('"')]
     for r in csv.DictReader(lines):
+        e = per_id.setdefault(r['ID'], dict(k=short(r['Kernel Name']), g=r['Grid Size'], b=r['Block Size'], ns=0.0, dram=None))
+        v = float(r['Metric Value'].replace(',', ''))
+        unit = r.get('Metric Unit', '')
         if r.get('Metric Name') == 'gpu__time_duration.sum':
-            rows.append((short(r['Kernel Name']), float(r['Metric Value'].replace(',', '')), r['Grid Size'], r['Block Size']))
+            e['ns'] = v * {'ns': 1, 'us': 1e3, 'ms': 1e6, 'nsecond': 1, 'usecond': 1e3, 'msecond': 1e6}.get(unit, 1)
+        elif r.get('Metric Name') in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+            mult = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(unit, 1)
+            e['dram'] = (e['dram'] or 0.0) + v * mult
+    rows = list(per_id.values())
     agg = OrderedDict()
-    for k, ns, *_ in rows:
-        a = agg.setdefault(k, [0, 0.0])
-        a[0] += 1; a[1] += ns
+    for e in rows:
+        a = agg.setdefault(e['k'], [0, 0.0, 0.0, False])
+        a[0] += 1; a[1] += e['ns']
+        if e['dram'] is not None:
+            a[2] += e['dram']; a[3] = True
     total = sum(a[1] for a in agg.values())
     with open(dst, 'w') as f:
-        f.write(f'# per-kernel totals over {len(rows)} launches (ncu gpu__time_duration.sum, --clock-control none; cold-cache, serialised:\n')
-        f.write('# compare SHARES, not absolutes)\n')
-        f.write(f'{"kernel":60s} {"launches":>8s} {"total_ms":>10s} {"avg_us":>9s} {"share":>7s}\n')
-        for k, (n, ns) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-            f.write(f'{k:60s} {n:8d} {ns / 1e6:10.3f} {ns / n / 1e3:9.2f} {ns / total:7.3f}\n')
-        f.write(f'{"TOTAL":60s} {len(rows):8d} {total / 1e6:10.3f}\n\n# launch list (id, kernel, us, grid, block)\n')
-        for i, (k, ns, g, b) in enumerate(rows):
-            f.write(f'{i:5d} {k:60s} {ns / 1e3:10.2f} {g:>16s} {b:>14s}\n')
+        f.write(f'# per-kernel totals over {len(rows)} launches (ncu gpu__time_duration.sum [+ dram__bytes_read/write.sum], --clock-control none;\n')
+        f.write('# cold-cache, serialised: compare SHARES, not absolutes)\n')
+        f.write(f'{"kernel":60s} {"launches":>8s} {"total_ms":>10s} {"avg_us":>9s} {"share":>7s} {"dram_MB/launch":>15s}\n')
+        for k, (n, ns, dram, has) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f'{k:60s} {n:8d} {ns / 1e6:10.3f} {ns / n / 1e3:9.2f} {ns / total:7.3f} {(dram / n / 1e6 if has else float("nan")):15.2f}\n')
+        f.write(f'{"TOTAL":60s} {len(rows):8d} {total / 1e6:10.3f}\n\n# launch list (id, kernel, us, grid, block, dram MB)\n')
+        for i, e in enumerate(rows):
+            f.write(f'{i:5d} {e["k"]:60s} {e["ns"] / 1e3:10.2f} {e["g"]:>16s} {e["b"]:>14s} {(e["dram"] or 0) / 1e6:10.2f}\n')
+    traffic = {k: dict(launches=a[0], dram_bytes_per_launch=a[2] / a[0]) for k, a in agg.items() if a[3]}
+    if traffic:
+        with open(dst + '.traffic.json', 'w') as f:
+            json.dump(traffic, f, indent=1, sort_keys=True)
     print(open(dst).read().split('# launch list')[0])
 
 

@@ -48,9 +48,17 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
-            os.environ['NCCL_DEBUG'] = 'WARN'
-        dist.init_process_group('nccl', device_id=dev)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)                                   # NCCL's version banner goes to stderr, stdout keeps the JSON line
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     inference.set_precision(args.precision)
     G = afcm_generator(seed=0, device=dev)
     t = int(args.thickness) if float(args.thickness).is_integer() else args.thickness
