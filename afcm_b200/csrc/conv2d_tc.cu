@@ -47,7 +47,9 @@ struct TcParams {
     int BN, n_tiles, m_tiles, cblocks;     // channel tile, #channel tiles, #pixel tiles per sample, ceil(Ci/64)
     int total_tiles;
     int stages;                            // TMA -> MMA ring depth (2 .. TC_MAX_STAGES)
-    int rowreuse;                          // 1: one A tile of 136 pixels per (ky, channel block) serves the three kx taps
+    int rowreuse;                          // 1: one A tile of 136 pixels per (ky, channel block) serves the three kx taps;
+                                           // 2: the same with separate rings for the A rows and the per-tap weight tiles
+    int a_stages;                          // mode 2: depth of the A ring (`stages` is the depth of the B ring)
     int bres;                              // 1 (row-reuse mode, single channel tile): all weight tiles stay resident in shared memory
     unsigned idesc;
     unsigned* dbg;          // mapped host memory for progress markers (AFCM_TC_DEBUG), or null
@@ -178,8 +180,10 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int b_bytes = p.BN * TC_BK * 2;
-    const int stage_bytes = p.bres ? TC_AROW_BYTES : (p.rowreuse ? TC_AROW_BYTES + 3 * b_bytes : TC_A_BYTES + b_bytes);
-    const int res_bytes = p.bres ? 9 * p.cblocks * b_bytes : 0;         // resident weights: tile (tap, cb) at (tap * cblocks + cb) * b_bytes
+    const int stage_bytes = p.rowreuse == 2 ? b_bytes
+                          : (p.bres ? TC_AROW_BYTES : (p.rowreuse ? TC_AROW_BYTES + 3 * b_bytes : TC_A_BYTES + b_bytes));
+    // in front of the ring: the resident weights (tile (tap, cb) at (tap * cblocks + cb) * b_bytes), or the A ring of mode 2
+    const int res_bytes = p.rowreuse == 2 ? p.a_stages * TC_AROW_BYTES : (p.bres ? 9 * p.cblocks * b_bytes : 0);
     uint8_t* ring = smem + res_bytes;
     uint8_t* tail = ring + p.stages * stage_bytes;
     uint64_t* full = reinterpret_cast<uint64_t*>(tail);                 // [TC_MAX_STAGES]
@@ -187,7 +191,9 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint64_t* tfull = empty + TC_MAX_STAGES;                            // [2]
     uint64_t* tempty = tfull + 2;                                       // [2]
     uint64_t* bfull = tempty + 2;                                       // [1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
+    uint64_t* afull = bfull + 1;                                        // [4] mode 2: A ring
+    uint64_t* aempty = afull + 4;                                       // [4]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 4);
     float* s_ocoef = reinterpret_cast<float*>(tail + 256);              // [2][256]
     float* s_bias = s_ocoef + 512;                                      // [2][256]
 
@@ -201,6 +207,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
         mbar_init(bfull, 1);
+        for (int a = 0; a < 4; a++) { mbar_init(&afull[a], 1); mbar_init(&aempty[a], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -225,6 +232,30 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     for (int cb = 0; cb < p.cblocks; cb++)
                         tma_load_3d(smem + (tap * p.cblocks + cb) * b_bytes, &map_b, bfull, cb * TC_BK, 0, tap);
             }
+            if (p.rowreuse == 2) {
+                // separate rings: an A row tile per (ky, channel block), a weight tile per (tap, channel block)
+                int as = 0; uint32_t aph = 0;
+                for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                    const int nt = tile % p.n_tiles;
+                    const int r = tile / p.n_tiles;
+                    const int mt = r % p.m_tiles, n = r / p.m_tiles;
+                    const int p0 = mt * TC_BM, o0 = nt * p.BN;
+                    for (int ky = 0; ky < 3; ky++) {
+                        for (int cb = 0; cb < p.cblocks; cb++) {
+                            mbar_wait(&aempty[as], aph ^ 1, p.dbg, 0x600u | (unsigned)as);
+                            mbar_expect_tx(&afull[as], (uint32_t)TC_AROW_BYTES);
+                            tma_load_3d(smem + as * TC_AROW_BYTES, &map_a2, &afull[as], cb * TC_BK, p0 + (ky - p.pad) * p.Wp - p.pad, n);
+                            if (++as == p.a_stages) { as = 0; aph ^= 1; }
+                            for (int kx = 0; kx < 3; kx++) {
+                                mbar_wait(&empty[stage], phase ^ 1, p.dbg, 0x100u | (unsigned)stage);
+                                mbar_expect_tx(&full[stage], (uint32_t)b_bytes);
+                                tma_load_3d(ring + stage * b_bytes, &map_b, &full[stage], cb * TC_BK, o0, ky * 3 + kx);
+                                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                            }
+                        }
+                    }
+                }
+            } else
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int nt = tile % p.n_tiles;
                 const int r = tile / p.n_tiles;
@@ -288,6 +319,40 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const uint32_t smem_base = smem_u32(smem), ring_base = smem_u32(ring);
             const uint32_t b_step16 = (p.bres ? (uint32_t)(p.cblocks * b_bytes) : (uint32_t)b_bytes) >> 4;
             if (p.bres) { mbar_wait(bfull, 0, p.dbg, 0x500u); tc_fence_after(); }
+            if (p.rowreuse == 2) {
+                int as = 0; uint32_t aph = 0;
+                const int nrows = 3 * p.cblocks;
+                for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                    mbar_wait(&tempty[acc], acc_phase ^ 1, p.dbg, 0x200u | (unsigned)acc);
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256);
+                    for (int rb = 0; rb < nrows; rb++) {
+                        mbar_wait(&afull[as], aph, p.dbg, 0x700u | (unsigned)as);
+                        const uint32_t a_lo = desc_lo(smem_base + (uint32_t)(as * TC_AROW_BYTES));
+#pragma unroll
+                        for (int kx = 0; kx < 3; kx++) {
+                            mbar_wait(&full[stage], phase, p.dbg, 0x300u | (unsigned)stage);
+                            tc_fence_after();
+                            const uint32_t b_lo = desc_lo(ring_base + (uint32_t)(stage * b_bytes));
+                            if (elect_one()) {
+#pragma unroll
+                                for (int k = 0; k < TC_BK / 16; k++)
+                                    umma_f16_lohi(tmem_d, a_lo + (uint32_t)(kx * 8 + k * 2), b_lo + (uint32_t)(k * 2), TC_DESC_HI, p.idesc,
+                                                  (rb | kx | k) != 0);
+                                umma_commit(&empty[stage]);
+                                if (kx == 2) {
+                                    umma_commit(&aempty[as]);
+                                    if (rb == nrows - 1) umma_commit(&tfull[acc]);
+                                }
+                            }
+                            __syncwarp();
+                            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                        }
+                        if (++as == p.a_stages) { as = 0; aph ^= 1; }
+                    }
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+            } else
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 mbar_wait(&tempty[acc], acc_phase ^ 1, p.dbg, 0x200u | (unsigned)acc);
                 tc_fence_after();
@@ -604,10 +669,11 @@ extern "C" void* afcm_conv_tc_debug_buffer(int enable)
 
 // Tuning aid (not part of the stable ABI): force the TMA->MMA ring depth (0 = automatic).
 extern "C" int afcm_conv_tc_set_stages(int stages) { g_force_stages = stages; return AFCM_OK; }
-// -1 automatic, 0 per-tap pipeline, 1 row-reuse (resident weights where they fit), 2 row-reuse with streamed weights
+// -1 automatic, 0 per-tap pipeline, 1 row-reuse (resident weights where they fit), 2 row-reuse with streamed weights,
+// 4 row-reuse with separate A / B rings for every layer
 extern "C" int afcm_conv_tc_set_rowreuse(int mode)
 {
-    g_rowreuse = mode < 0 ? -1 : (mode ? 1 : 0);
+    g_rowreuse = mode < 0 ? -1 : (mode == 4 ? 2 : (mode ? 1 : 0));
     g_bres = mode != 2;
     return AFCM_OK;
 }
@@ -672,7 +738,10 @@ extern "C" int afcm_conv2d_tc(const void* xp, const void* w_tc, const float* oco
 
     // small channel tiles are bound by re-reading the activation tile once per tap from L2 (9 x 16 KB per 128 pixels):
     // there one tile per kernel ROW serves its three taps.  Large tiles keep the per-tap stages (B dominates).
-    p.rowreuse = g_rowreuse >= 0 ? g_rowreuse : (p.BN <= 192);
+    // BN <= 192: combined stages (A row + its three weight tiles); larger tiles: separate A / B rings (mode 2)
+    p.rowreuse = g_rowreuse >= 0 ? g_rowreuse : (p.BN <= 192 ? 1 : 2);
+    if (p.rowreuse == 1 && p.BN > 192) p.rowreuse = 2;
+    p.a_stages = 3;
     CUtensorMap map_a2 = map_a;
     if (p.rowreuse) {
         rc = encode_3d(&map_a2, tc_dtype, xp, c_pad, rows, (uint64_t)N, c_pad * 2, rows * c_pad * 2, TC_BK, TC_AROW_PX);
@@ -682,13 +751,16 @@ extern "C" int afcm_conv2d_tc(const void* xp, const void* w_tc, const float* oco
     // a single channel tile whose 9 x cblocks weight tiles fit next to a 3-deep A ring: keep the weights resident
     const int res_bytes = 9 * p.cblocks * p.BN * TC_BK * 2;
     p.bres = p.rowreuse && g_bres != 0 && p.n_tiles == 1 && res_bytes + 3 * TC_AROW_BYTES + fixed <= max_smem_optin();
-    const int stage_bytes = p.bres ? TC_AROW_BYTES : (p.rowreuse ? TC_AROW_BYTES + 3 * p.BN * TC_BK * 2 : TC_A_BYTES + p.BN * TC_BK * 2);
-    int stages = (max_smem_optin() - fixed - (p.bres ? res_bytes : 0)) / stage_bytes;
+    p.bres = p.bres && p.rowreuse == 1;
+    const int front = p.rowreuse == 2 ? p.a_stages * TC_AROW_BYTES : (p.bres ? res_bytes : 0);
+    const int stage_bytes = p.rowreuse == 2 ? p.BN * TC_BK * 2
+                          : (p.bres ? TC_AROW_BYTES : (p.rowreuse ? TC_AROW_BYTES + 3 * p.BN * TC_BK * 2 : TC_A_BYTES + p.BN * TC_BK * 2));
+    int stages = (max_smem_optin() - fixed - front) / stage_bytes;
     if (g_force_stages > 0) stages = g_force_stages;
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     if (stages < 2) { set_error("conv2d_tc: not enough shared memory for the pipeline"); return AFCM_ERR_UNSUPPORTED; }
     p.stages = stages;
-    const int smem = stages * stage_bytes + fixed + (p.bres ? res_bytes : 0);
+    const int smem = stages * stage_bytes + fixed + front;
     AFCM_CUDA(cudaFuncSetAttribute(conv2d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int grid = sm_count();
     if (grid > p.total_tiles) grid = p.total_tiles;

@@ -118,10 +118,11 @@ def test_conv2d_tc_fp16_storage(shape):
     assert rel_err(got.float().cpu().numpy(), exact.cpu().numpy()) < 3e-3
 
 
-@pytest.mark.parametrize('mode', [0, 1, 2])
+@pytest.mark.parametrize('mode', [0, 1, 2, 4])
 def test_conv2d_tc_rowreuse_modes_exact(mode):
     """All pipelines of the tcgen05 kernel -- one A tile per tap (0); one A tile per kernel row re-read at a 128-byte
-    descriptor offset per kx tap, with the weights resident in shared memory where they fit (1) or streamed (2) -- are
+    descriptor offset per kx tap, with the weights resident in shared memory where they fit (1), streamed (2), or streamed through a ring of their
+    own (4) -- are
     bit-identical to the fp32 kernel on representable inputs."""
     from afcm_b200 import _lib
     from afcm_b200.torch_utils.ops import conv2d_gradfix
@@ -129,7 +130,8 @@ def test_conv2d_tc_rowreuse_modes_exact(mode):
     g = torch.Generator(device='cpu').manual_seed(5)
     _lib.lib().afcm_conv_tc_set_rowreuse(mode)
     try:
-        for (N, Ci, Co, H, W) in [(2, 64, 64, 36, 36), (1, 192, 96, 30, 22), (2, 91, 128, 52, 52), (1, 200, 181, 20, 38)]:
+        for (N, Ci, Co, H, W) in [(2, 64, 64, 36, 36), (1, 192, 96, 30, 22), (2, 91, 128, 52, 52), (1, 200, 181, 20, 38), (1, 128, 256, 36, 36),
+                                  (1, 96, 300, 20, 20)]:
             x = torch.randint(-4, 5, (N, Ci, H, W), generator=g).float().to(dev)
             w = torch.randint(-2, 3, (Co, Ci, 3, 3), generator=g).float().to(dev)
             ref = conv2d_gradfix.conv2d_native(x, w, 2, impl='f32')

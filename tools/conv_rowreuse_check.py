@@ -42,7 +42,7 @@ def timeit(N, Ci, Co, H):
     return ms, 2.0 * N * Co * Ci * 9 * (H + 2) ** 2 / ms / 1e9
 
 
-for mode, bo in [(0, 0), (3, 0), (1, 0)]:
+for mode, bo in [(0, 0), (1, 0), (4, 0)]:
     L.afcm_conv_tc_set_rowreuse(mode)
     try:
         r = [exact(2, 64, 64, 36, 36), exact(1, 192, 96, 30, 22), exact(2, 91, 128, 52, 52)]
@@ -50,18 +50,18 @@ for mode, bo in [(0, 0), (3, 0), (1, 0)]:
         r = repr(e)
     print('rowreuse', mode, 'base_ofs', bo, 'exact:', r, flush=True)
 
-shapes = [(16, 4, 64, 276), (16, 64, 64, 276), (16, 64, 91, 276), (16, 91, 128, 276), (16, 128, 181, 276), (16, 181, 128, 148),
+shapes = [(16, 362, 512, 148), (16, 181, 256, 148), (16, 4, 64, 276), (16, 64, 64, 276), (16, 64, 91, 276), (16, 91, 128, 276), (16, 128, 181, 276), (16, 181, 128, 148),
           (16, 128, 91, 276), (16, 91, 64, 276), (16, 256, 181, 148), (16, 512, 512, 84), (16, 512, 512, 36)]
 good = int(os.environ.get('ROWREUSE_BO', '0'))
 for sh in shapes:
     out = []
-    for mode in (0, 3, 1):
+    for mode in (0, 1, 4):
         L.afcm_conv_tc_set_rowreuse(mode)
         try:
             out.append('%.3f ms %6.0f TF' % timeit(*sh))
         except RuntimeError as e:
             out.append('n/a')
-    print(sh, ' per-tap:', out[0], ' row-reuse no split:', out[1], ' row-reuse:', out[2], flush=True)
+    print(sh, ' per-tap:', out[0], ' row-reuse (combined stages):', out[1], ' row-reuse (split rings):', out[2], flush=True)
 
 L.afcm_conv_tc_set_rowreuse(-1)
 for mode in (0, 16, 48):
