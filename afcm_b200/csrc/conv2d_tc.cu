@@ -710,7 +710,8 @@ extern "C" int afcm_conv2d_tc(const void* xp, const void* w_tc, const float* oco
     AFCM_CHECK_ARG(y_dtype == AFCM_F32 || y_dtype == AFCM_F16, "y must be float32 or float16");
     AFCM_CHECK_ARG(N > 0 && Ci > 0 && Co > 0 && H > 0 && W > 0, "empty problem");
     AFCM_CHECK_ARG(tc_dtype == AFCM_F16 || tc_dtype == AFCM_BF16, "tc dtype must be F16 or BF16");
-    if (pad != 1 && pad != 2) { set_error("conv2d_tc: padding %d not supported (1 or 2)", pad); return AFCM_ERR_UNSUPPORTED; }
+    if (pad < 0 || pad > 2) { set_error("conv2d_tc: padding %d not supported (0, 1 or 2)", pad); return AFCM_ERR_UNSUPPORTED; }
+    if (H + 2 * pad - 2 <= 0 || W + 2 * pad - 2 <= 0) { set_error("conv2d_tc: empty output"); return AFCM_ERR_INVALID; }
     TcParams p;
     memset(&p, 0, sizeof(p));
     p.ocoef = ocoef; p.bias = bias; p.y = y; p.y_half = y_dtype == AFCM_F16; p.dbg = g_dbg_dev; p.dbg_mode = g_dbg_mode;

@@ -4,8 +4,9 @@ parameter / buffer names (so reference `*_net_G*.pth` state_dicts load unchanged
 and forward signatures; every tensor operation on the forward path is a hand-written sm_100a kernel
 reached through libafcm_b200.so.  PyTorch provides parameters, device memory and streams only.
 
-Forward (inference) only for the convolutions in this round; filtered_lrelu, bias_act and upfirdn2d also
-carry their autograd definitions.
+Every operator also carries its first-order autograd definition (the generator training step, BASELINE
+config 5): native kernels for the convolution data / weight gradients, the filtered_lrelu backward (sign tensor),
+bias_act and the FC products; tensor operations only on the small [N,C] / [O,I] coefficient tensors.
 """
 import numpy as np
 import scipy.signal
@@ -34,6 +35,8 @@ def modulated_conv2d(x, w, s, demodulate=True, padding=0, input_gain=None, impl=
     misc.assert_shape(w, [O, I, kh, kw])
     misc.assert_shape(x, [N, I, None, None])
     misc.assert_shape(s, [N, I])
+    if conv2d_gradfix.needs_grad(x, w, s):
+        return _modulated_conv2d_train(x, w, s, demodulate, padding, input_gain, impl, bias)
     L = _lib.lib()
     s = s.contiguous().float()
     gain_scalar = None
@@ -53,12 +56,78 @@ def modulated_conv2d(x, w, s, demodulate=True, padding=0, input_gain=None, impl=
                                         normalize=bool(demodulate), impl=impl, out_dtype=out_dtype, bias=bias)
 
 
+def _modulated_conv2d_train(x, w, s, demodulate, padding, input_gain, impl, bias):
+    """Differentiable modulated_conv2d (training step).  The coefficient algebra of NET:41-57 runs as tensor operations
+    on the small [N,I] / [O,I] tensors so that autograd carries it; the demodulation GEMV and the convolution with its
+    three gradients are native kernels (_FcLinearFn, conv2d_gradfix._ConvFn)."""
+    N, I = s.shape
+    s = s.float()
+    wp = w.float()
+    ocoef = None
+    if demodulate:
+        wp = wp * wp.square().mean([1, 2, 3], keepdim=True).rsqrt()                  # NET:42
+        s = s * s.square().mean().rsqrt()                                            # NET:43
+        wsq = wp.square().sum([2, 3])                                                # [O, I]
+        ocoef = (_FcLinearFn.apply(s.square(), wsq, 1.0) + 1e-8).rsqrt()             # NET:51  [N, O]
+    icoef = s if input_gain is None else s * input_gain.expand(N, I)                 # NET:55-57
+    y = conv2d_gradfix._ConvFn.apply(x, wp, icoef, ocoef, int(padding), impl or conv2d_gradfix.conv_impl)
+    if bias is not None:
+        y = y + bias.reshape(1, -1, 1, 1)
+    return y
+
+
 # ----------------------------------------------------------------------------------------------------
+
+
+class _FcLinearFn(torch.autograd.Function):
+    """y = x @ (w * weight_gain)^T with the native FC kernel for the product and for both gradients
+    (dx = dy @ w, dw = dy^T @ x): the matmul / addmm of NET:97-99 and its autograd."""
+
+    @staticmethod
+    def _mm(a, b, gain):                     # a [M,K], b [P,K] -> a @ b^T * gain
+        a = a.contiguous().float()
+        b = b.contiguous().float()
+        M, K = a.shape
+        P = b.shape[0]
+        y = torch.empty([M, P], dtype=torch.float32, device=a.device)
+        _lib.check(_lib.lib().afcm_fully_connected(_lib.ptr(a), a.stride(0), _lib.ptr(b), None, _lib.ptr(y), y.stride(0),
+                                                   M, K, P, float(gain), 1.0, 1, 0.0, 1.0, _lib.stream_ptr(a.device)))
+        return y
+
+    @staticmethod
+    def forward(ctx, x, w, weight_gain):
+        _lib.require_cuda(x, w)
+        ctx.save_for_backward(x, w)
+        ctx.gain = float(weight_gain)
+        return _FcLinearFn._mm(x, w, ctx.gain)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = _FcLinearFn._mm(dy, w.t(), ctx.gain)
+        if ctx.needs_input_grad[1]:
+            dw = _FcLinearFn._mm(dy.t(), x.t(), ctx.gain)
+        return dx, dw, None
+
+
+def _fc_train(x, weight, bias, weight_gain, bias_gain, activation):
+    """FullyConnectedLayer.forward with an autograd graph, structured like NET:89-101: product, then bias_act."""
+    y = _FcLinearFn.apply(x, weight, weight_gain)
+    b = bias
+    if b is not None and bias_gain != 1:
+        b = b * bias_gain
+    if activation == 'linear':
+        return y if b is None else y + b.unsqueeze(0)
+    return bias_act.bias_act(y, b, act=activation)
 
 
 def _fc_native(x, weight, bias, weight_gain, bias_gain, activation, out=None):
     spec = bias_act.activation_funcs[activation]
     _lib.require_cuda(x, weight)
+    if out is None and conv2d_gradfix.needs_grad(x, weight, bias):
+        return _fc_train(x, weight, bias, weight_gain, bias_gain, activation)
     assert x.ndim == 2 and x.dtype == torch.float32 and x.stride(1) == 1
     N, in_f = x.shape
     out_f = weight.shape[0]
@@ -118,6 +187,8 @@ class MappingNetwork(torch.nn.Module):
         N = z.shape[0]
         st = _lib.stream_ptr(z.device)
         width = self.z_dim + (self.w_dim if self.c_dim > 0 else 0)
+        if conv2d_gradfix.needs_grad(z, c, *self.parameters()):
+            return self._forward_train(z, c, truncation_psi, truncation_cutoff, update_emas)
         x = torch.empty([N, width], dtype=torch.float32, device=z.device)
         z = z.float().contiguous()
         _lib.check(L.afcm_normalize_2nd_moment(_lib.ptr(z), z.stride(0), _lib.ptr(x), x.stride(0), N, self.z_dim, 1e-8, st))
@@ -126,6 +197,23 @@ class MappingNetwork(torch.nn.Module):
             y = self.embed(c.float().contiguous())
             xv = x[:, self.z_dim:]
             _lib.check(L.afcm_normalize_2nd_moment(_lib.ptr(y), y.stride(0), _lib.ptr(xv), x.stride(0), N, self.w_dim, 1e-8, st))
+        for idx in range(self.num_layers):
+            x = getattr(self, f'fc{idx}')(x)
+        if update_emas:
+            self.w_avg.copy_(x.detach().mean(dim=0).lerp(self.w_avg, self.w_avg_beta))
+        x = x.unsqueeze(1).repeat([1, self.num_ws, 1])
+        if truncation_psi != 1:
+            x[:, :truncation_cutoff] = self.w_avg.lerp(x[:, :truncation_cutoff], truncation_psi)
+        return x
+
+    def _forward_train(self, z, c, truncation_psi, truncation_cutoff, update_emas):
+        """NET:141-158 with an autograd graph: the FC products and activations are native (_fc_train), the 2nd-moment
+        normalisation of the two [N,512] codes is written with tensor operations."""
+        def norm2(v):
+            return v * (v.square().mean(dim=1, keepdim=True) + 1e-8).rsqrt()
+        x = norm2(z.float())
+        if self.c_dim > 0:
+            x = torch.cat([x, norm2(self.embed(c.float().contiguous()))], dim=1)
         for idx in range(self.num_layers):
             x = getattr(self, f'fc{idx}')(x)
         if update_emas:
@@ -371,9 +459,12 @@ class EncoderLayer(_AliasFreeLayerBase):
             magnitude_cur = x.detach().to(torch.float32).square().mean()
             self.magnitude_ema.copy_(magnitude_cur.lerp(self.magnitude_ema, self.magnitude_ema_beta))
         fast = conv2d_gradfix.fast_path() and not torch.is_grad_enabled()
-        x = conv2d_gradfix.conv2d_native(x if fast else x.float(), self.weight, self.conv_kernel - 1, pre_scale=self.weight_gain,
-                                         out_dtype=conv2d_gradfix.act_dtype if fast else None,
-                                         bias=self.bias.detach().float() if fast else None)
+        if conv2d_gradfix.needs_grad(x, self.weight):
+            x = conv2d_gradfix.conv2d_train(x, self.weight, self.conv_kernel - 1, pre_scale=self.weight_gain)
+        else:
+            x = conv2d_gradfix.conv2d_native(x if fast else x.float(), self.weight, self.conv_kernel - 1, pre_scale=self.weight_gain,
+                                             out_dtype=conv2d_gradfix.act_dtype if fast else None,
+                                             bias=self.bias.detach().float() if fast else None)
         x = self._filtered_lrelu(x, np.sqrt(2), 0.2, bias_done=fast)
         misc.assert_shape(x, [None, self.out_channels, int(self.out_size[1]), int(self.out_size[0])])
         return x
@@ -409,12 +500,37 @@ class Conv2dLayer(torch.nn.Module):
                 self.bias = None
 
     def forward(self, x, gain=1):
-        x = conv2d_gradfix.conv2d_native(x if conv2d_gradfix.fast_path() else x.float(), self.weight, self.padding,
-                                         pre_scale=self.weight_gain)
+        if conv2d_gradfix.needs_grad(x, self.weight):
+            x = conv2d_gradfix.conv2d_train(x, self.weight, self.padding, pre_scale=self.weight_gain)
+        else:
+            x = conv2d_gradfix.conv2d_native(x if conv2d_gradfix.fast_path() else x.float(), self.weight, self.padding,
+                                             pre_scale=self.weight_gain)
         b = self.bias.to(x.dtype) if self.bias is not None else None
         act_gain = self.act_gain * gain
         act_clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
         return bias_act.bias_act(x, b, act=self.activation, gain=act_gain, clamp=act_clamp)
+
+
+class _AvgPool4Fn(torch.autograd.Function):
+    """AdaptiveAvgPool2d((4,4)) of NET:636,683: native forward; the gradient of a uniform window average is the
+    output gradient spread over each window (sizes divisible by 4, which is what the generator produces)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        N, C, H, W = x.shape
+        y = torch.empty([N, C, 4, 4], dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().afcm_adaptive_avgpool(_lib.ptr(x.contiguous().float()), _lib.ptr(y), N * C, H, W, 4, 4,
+                                                    _lib.stream_ptr(x.device)))
+        ctx.hw = (H, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        H, W = ctx.hw
+        if H % 4 or W % 4:
+            raise NotImplementedError('adaptive average pool gradient: plane size must be divisible by 4')
+        kh, kw = H // 4, W // 4
+        return (dy * (1.0 / (kh * kw))).repeat_interleave(kh, dim=2).repeat_interleave(kw, dim=3)
 
 
 class SynthesisNetwork(torch.nn.Module):
@@ -488,11 +604,7 @@ class SynthesisNetwork(torch.nn.Module):
             self.layer_names.append(name)
 
     def pool(self, x):
-        N, C, H, W = x.shape
-        y = torch.empty([N, C, 4, 4], dtype=torch.float32, device=x.device)
-        _lib.check(_lib.lib().afcm_adaptive_avgpool(_lib.ptr(x.contiguous()), _lib.ptr(y), N * C, H, W, 4, 4,
-                                                    _lib.stream_ptr(x.device)))
-        return y
+        return _AvgPool4Fn.apply(x)
 
     _u8_lut = None
 

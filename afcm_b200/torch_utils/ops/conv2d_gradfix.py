@@ -127,19 +127,146 @@ def conv2d_native(x, w, padding, icoef=None, ocoef=None, pre_scale=1.0, normaliz
     return y
 
 
+class _ConvFn(torch.autograd.Function):
+    """Differentiable  y[n,o] = ocoef[n,o] * conv(icoef[n,i] * x[n,i], wp)  (include/afcm_b200.h "convolution
+    gradients").  `wp` is the PREPARED weight (scaled / RMS-normalised by the caller with differentiable tensor
+    operations on the small weight tensor), icoef / ocoef are [N,Ci] / [N,Co] tensors or None.  This is the backward
+    the reference obtains from autograd of F.conv2d through conv2d_gradfix.conv2d (OPS/conv2d_gradfix.py:37-40)
+    inside modulated_conv2d (NET:46-63): the data gradient is the forward kernel on flipped, transposed weights,
+    the weight gradient one GEMM over the whole batch (no per-sample [N,O,I,k,k] weight gradient exists)."""
+
+    @staticmethod
+    def forward(ctx, x, wp, icoef, ocoef, padding, impl):
+        _lib.require_cuda(x, wp)
+        L = _lib.lib()
+        x = x.contiguous().float()
+        wp = wp.contiguous().float()
+        icoef = None if icoef is None else icoef.contiguous().float()
+        ocoef = None if ocoef is None else ocoef.contiguous().float()
+        N, Ci, H, W = x.shape
+        Co, Ci2, k, k2 = wp.shape
+        assert Ci == Ci2 and k == k2 and k in (1, 3)
+        OH, OW = H + 2 * padding - k + 1, W + 2 * padding - k + 1
+        use_tc = impl == 'tc' and k == 3 and 0 <= padding <= 2
+        st = _lib.stream_ptr(x.device)
+        y = torch.empty([N, Co, OH, OW], dtype=torch.float32, device=x.device)
+        xp = None
+        if use_tc:
+            xp = _pack(x, icoef, tc_dtype)
+            w_tc = _weight_tc(wp, tc_dtype)
+            _lib.timed('conv2d_tc', 2.0 * N * Co * Ci * 9 * OH * OW, lambda: _lib.check(
+                L.afcm_conv2d_tc(_lib.ptr(xp), _lib.ptr(w_tc), _lib.ptr(ocoef), None, _lib.ptr(y), _lib.F32,
+                                 _lib.dtype_code(tc_dtype), N, Ci, H, W, Co, padding, st)))
+        else:
+            _lib.check(L.afcm_conv2d_f32(_lib.ptr(x), _lib.ptr(wp), _lib.ptr(icoef), _lib.ptr(ocoef), _lib.ptr(y),
+                                         N, Ci, H, W, Co, k, padding, st))
+        ctx.padding, ctx.use_tc, ctx.tc_dtype = padding, use_tc, tc_dtype
+        need_y = ocoef is not None and ctx.needs_input_grad[3]
+        need_x = (not use_tc) or (icoef is not None and ctx.needs_input_grad[2])
+        ctx.save_for_backward(x if need_x else None, wp, icoef, ocoef, y if need_y else None, xp)
+        ctx.xshape = (N, Ci, H, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wp, icoef, ocoef, y, xp = ctx.saved_tensors
+        L = _lib.lib()
+        dy = dy.contiguous().float()
+        N, Ci, H, W = ctx.xshape
+        Co, _, k, _ = wp.shape
+        pad = ctx.padding
+        OH, OW = dy.shape[2], dy.shape[3]
+        st = _lib.stream_ptr(dy.device)
+        need_x, need_w, need_ic, need_oc = ctx.needs_input_grad[:4]
+        need_ic = need_ic and icoef is not None
+        need_oc = need_oc and ocoef is not None
+        dx = dw = d_icoef = d_ocoef = None
+        if need_oc:                                   # d_ocoef[n,o] = <dy, conv result before the scale> = <dy, y> / ocoef
+            d_ocoef = torch.empty_like(ocoef)
+            _lib.check(L.afcm_plane_dot_scale(_lib.ptr(dy), _lib.ptr(y), _lib.ptr(ocoef), None, _lib.ptr(d_ocoef),
+                                              N * Co, OH * OW, st))
+        dyp = None
+        code = _lib.dtype_code(ctx.tc_dtype)
+        if ctx.use_tc and (need_x or need_ic or need_w):
+            dyp = _pack(dy, ocoef, ctx.tc_dtype)      # ocoef folded while packing: serves both gradients
+        if need_x or need_ic:
+            wT = wp.flip(2, 3).transpose(0, 1).contiguous()                # [Ci, Co, k, k]
+            dx = torch.empty([N, Ci, H, W], dtype=torch.float32, device=dy.device)
+            if ctx.use_tc:
+                w_tc = _weight_tc(wT, ctx.tc_dtype)
+                _lib.timed('conv2d_tc_dgrad', 2.0 * N * Co * Ci * 9 * H * W, lambda: _lib.check(
+                    L.afcm_conv2d_tc(_lib.ptr(dyp), _lib.ptr(w_tc), None, None, _lib.ptr(dx), _lib.F32, code,
+                                     N, Co, OH, OW, Ci, k - 1 - pad, st)))
+            else:
+                _lib.check(L.afcm_conv2d_f32(_lib.ptr(dy), _lib.ptr(wT), _lib.ptr(ocoef), None, _lib.ptr(dx),
+                                             N, Co, OH, OW, Ci, k, k - 1 - pad, st))
+            if icoef is not None:                     # d_icoef = <dxm, x>, then dx = icoef * dxm (one launch)
+                if need_ic:
+                    d_icoef = torch.empty_like(icoef)
+                _lib.check(L.afcm_plane_dot_scale(_lib.ptr(dx), _lib.ptr(x), None, _lib.ptr(icoef), _lib.ptr(d_icoef),
+                                                  N * Ci, H * W, st))
+            if not need_x:
+                dx = None
+        if need_w:
+            dw = torch.empty_like(wp)
+            if ctx.use_tc:
+                _lib.timed('conv2d_wgrad_tc', 2.0 * N * Co * Ci * 9 * OH * OW, lambda: _lib.check(
+                    L.afcm_conv2d_wgrad_tc(_lib.ptr(dyp), _lib.ptr(xp), _lib.ptr(dw), code, N, Ci, H, W, Co, pad, st)))
+            else:
+                _lib.check(L.afcm_conv2d_wgrad_f32(_lib.ptr(dy), _lib.ptr(x), _lib.ptr(icoef), _lib.ptr(ocoef), _lib.ptr(dw),
+                                                   N, Ci, H, W, Co, k, pad, st))
+        return dx, dw, d_icoef, d_ocoef, None, None
+
+
+def _pack(x, coef, dtype):
+    """NCHW float32 -> 16-bit channel-innermost flat planes with the per-(n,channel) coefficient folded in."""
+    L = _lib.lib()
+    N, C, H, W = x.shape
+    xp = torch.empty([N, int(L.afcm_conv_tc_plane_elems(H, W, C))], dtype=dtype, device=x.device)
+    _lib.timed('conv_tc_pack', float(4 * x.numel() + 2 * xp.numel()), lambda: _lib.check(
+        L.afcm_conv_tc_pack(_lib.ptr(x), _lib.F32, _lib.ptr(coef), _lib.ptr(xp), _lib.dtype_code(dtype), N, C, H, W,
+                            _lib.stream_ptr(x.device))))
+    return xp
+
+
+def _weight_tc(wp, dtype):
+    """Prepared float32 weight [Co,Ci,3,3] -> the tap-major 16-bit tile source of the tcgen05 kernel."""
+    Co, Ci, k, _ = wp.shape
+    w_tc = torch.empty([k * k, (Co + 15) // 16 * 16, (Ci + 63) // 64 * 64], dtype=dtype, device=wp.device)
+    _lib.check(_lib.lib().afcm_conv_weight_prep(_lib.ptr(wp), Co, Ci, k, 1.0, 0, None, _lib.ptr(w_tc), _lib.dtype_code(dtype),
+                                                None, _lib.stream_ptr(wp.device)))
+    return w_tc
+
+
+def needs_grad(*tensors):
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
+def conv2d_train(x, w, padding, icoef=None, ocoef=None, pre_scale=1.0, normalize=False, impl=None):
+    """The differentiable counterpart of conv2d_native: weight preparation as tensor operations on the (small) weight
+    so that autograd carries it, then _ConvFn."""
+    wp = w.float()
+    if pre_scale != 1.0:
+        wp = wp * float(pre_scale)
+    if normalize:
+        wp = wp * wp.square().mean([1, 2, 3], keepdim=True).rsqrt()          # NET:42
+    return _ConvFn.apply(x, wp, icoef, ocoef, int(padding), impl or conv_impl)
+
+
 def conv2d(input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
     """Drop-in for conv2d_gradfix.conv2d (reference :37-40) for the configurations the generator uses:
-    stride 1, dilation 1, groups 1, square 1x1 / 3x3 kernels, symmetric integer padding.  Forward only --
-    gradients of the convolution are the training-step row of the scope table."""
+    stride 1, dilation 1, groups 1, square 1x1 / 3x3 kernels, symmetric integer padding.  Differentiable
+    (first order) with respect to input, weight and bias."""
     assert isinstance(input, torch.Tensor)
     if isinstance(padding, (tuple, list)):
         assert padding[0] == padding[1]
         padding = padding[0]
     if stride not in (1, (1, 1)) or dilation not in (1, (1, 1)) or groups != 1:
         raise NotImplementedError('afcm conv2d supports stride=1, dilation=1, groups=1 only')
-    if torch.is_grad_enabled() and (input.requires_grad or weight.requires_grad):
-        raise NotImplementedError('afcm conv2d: backward is not implemented yet (forward-only hot path)')
-    y = conv2d_native(input, weight, int(padding))
+    if needs_grad(input, weight, bias):
+        y = conv2d_train(input, weight, int(padding))
+    else:
+        y = conv2d_native(input, weight, int(padding))
     if bias is not None:
         y = y + bias.reshape(1, -1, 1, 1)
     return y

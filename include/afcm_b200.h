@@ -164,7 +164,8 @@ int afcm_modconv_coefs(const float* styles, const float* wsq, const float* input
  * y [N,Co,H+2*pad-2,W+2*pad-2] scaled by ocoef (y_dtype AFCM_F32 or AFCM_F16; x_dtype of the pack step
  * likewise: fp16 activations stay 16-bit between the layers of the fast inference path).  bias [Co] or NULL
  * is added after the scale: y = acc * ocoef + bias (the bias of the filtered_lrelu / bias_act that follows,
- * NET:371, NET:510, which then runs bias-free).  ksize must be 3, pad 1 or 2. */
+ * NET:371, NET:510, which then runs bias-free).  ksize must be 3, pad 0, 1 or 2 (pad 0 = the data gradient of a
+ * full-padding convolution, see afcm_conv2d_wgrad_tc below). */
 int64_t afcm_conv_tc_plane_elems(int H, int W, int Ci);
 int afcm_conv_tc_pack(const void* x, int x_dtype, const float* icoef, void* xp, int tc_dtype,
                       int N, int Ci, int H, int W, void* stream);
@@ -176,6 +177,39 @@ int afcm_conv2d_tc(const void* xp, const void* w_tc, const float* ocoef, const f
 int afcm_conv_tc_set_stages(int stages);
 int afcm_conv_tc_set_rowreuse(int mode);   /* A-tile reuse across the kx taps: -1 automatic, 0 off, 1 on, 2 on without resident weights */
 void* afcm_conv_tc_debug_buffer(int enable);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* convolution gradients -- the backward pass the reference obtains from autograd of F.conv2d (cuDNN)  */
+/* through conv2d_gradfix.conv2d (OPS/conv2d_gradfix.py:37-40) inside modulated_conv2d (NET:25-64), the */
+/* encoder conv (NET:503-505) and Conv2dLayer.  (afcm_b200/csrc/conv2d_bwd.cu)                        */
+/*
+ * With y[n,o] = ocoef[n,o] * conv(icoef[n,i] * x[n,i], w, pad):
+ *   data gradient   : dxm = conv(ocoef * dy, flip(w)^T, pad' = k-1-pad) is a FORWARD call (afcm_conv2d_f32 or
+ *                     afcm_conv_tc_pack + afcm_conv2d_tc) on transposed, flipped weights with icoef := ocoef;
+ *                     dx = icoef * dxm.
+ *   afcm_plane_dot_scale : out[p] = <a[p,:], b[p,:]> (/ div[p] when div != NULL), then a[p,:] *= coef[p] in place when
+ *                     coef != NULL; a, b [planes, hw] dense fp32.  Gives d_icoef = <dxm, x> followed by dx = icoef*dxm
+ *                     in one launch, and d_ocoef = <dy, y> / ocoef.
+ *   weight gradient : dw[o,i,ky,kx] = sum_{n,p} (ocoef dy)[n,o,p] * (icoef x)[n,i,p+(ky-pad,kx-pad)], fp32 [Co,Ci,k,k]
+ *                     (overwritten).  _f32: exact SIMT path from the NCHW fp32 tensors (ksize 1 or 3).  _tc: mma.sync
+ *                     tensor-core path (fp32 accumulation) from the two 16-bit flat-plane tensors of
+ *                     afcm_conv_tc_pack: dyp = pack(dy [N,Co,OH,OW], ocoef), xp = pack(x [N,Ci,H,W], icoef) -- the
+ *                     same xp the forward consumed and the same dyp the data gradient consumes; ksize 3, pad 0..2.
+ */
+int afcm_plane_dot_scale(float* a, const float* b, const float* div, const float* coef, float* out,
+                         int64_t planes, int64_t hw, void* stream);
+int afcm_conv2d_wgrad_f32(const float* dy, const float* x, const float* icoef, const float* ocoef, float* dw,
+                          int N, int Ci, int H, int W, int Co, int ksize, int pad, void* stream);
+int afcm_conv2d_wgrad_tc(const void* dyp, const void* xp, float* dw, int tc_dtype,
+                         int N, int Ci, int H, int W, int Co, int pad, void* stream);
+
+/* Fused Adam step on flat fp32 buffers (the generator optimiser of the reference training loop, train.py /
+ * models/base_model.py: torch.optim.Adam; scrub != 0 applies the reference's gradient scrub
+ * nan_to_num(nan=0, posinf=1e5, neginf=-1e5), train.py:67-77, before the update).  grad_scale multiplies the
+ * gradient first (1/world_size after a sum all-reduce).  step counts from 1. */
+int afcm_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                   float lr, float beta1, float beta2, float eps, int step, float grad_scale, int scrub,
+                   void* stream);
 
 /* ---------------------------------------------------------------------------------------------- */
 /* small fused kernels                                                                              */

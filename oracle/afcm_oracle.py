@@ -399,10 +399,12 @@ def synthesis_forward(P, ws, img, cfg=None, taps=None):
     return x
 
 
-def generator_forward(P, z, c, cond_img, cfg=None, taps=None):
-    """Stylegan3Generator.forward, NET:737-740 (eval mode, noise_mode='const', truncation_psi=1)."""
+def generator_forward(P, z, c, cond_img, cfg=None, taps=None, grad=False):
+    """Stylegan3Generator.forward, NET:737-740 (eval mode, noise_mode='const', truncation_psi=1).  grad=True keeps the
+    autograd graph: the restatement is built from differentiable tensor operations only, so torch's autograd over it is
+    the CPU checker of the training-step path (pinned by tests/golden/tiny_gen_grads.npz)."""
     import torch
-    with torch.no_grad():
+    with torch.set_grad_enabled(bool(grad)):
         ws = mapping_forward(P, z, c, cfg)
         return synthesis_forward(P, ws, cond_img, cfg, taps)
 

@@ -37,3 +37,9 @@ def rel_err(a, b):
     import numpy as np
     a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.fixture(scope='session')
+def golden_tiny_grads():
+    import numpy as np
+    return np.load(os.path.join(GOLDEN, 'tiny_gen_grads.npz'))

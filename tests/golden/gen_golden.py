@@ -3,7 +3,7 @@
 files are what pins both the oracle (oracle/) and the CUDA path.  /root/reference does not exist on
 the GPU box -- only the committed .npz files travel.
 
-    python tests/golden/gen_golden.py            # writes ops.npz, tiny_gen.npz, full_gen.npz
+    python tests/golden/gen_golden.py            # writes ops.npz, tiny_gen.npz, tiny_gen_grads.npz, full_gen.npz
 
 Seeds are fixed; re-running reproduces the files bit-for-bit with the same torch build.
 """
@@ -127,6 +127,11 @@ def gen_ops():
         t = 'modconv.' + name
         out[t + '.x'] = x.numpy(); out[t + '.w'] = w.numpy(); out[t + '.s'] = s.numpy(); out[t + '.y'] = y.numpy()
         out[t + '.cfg'] = np.asarray([int(demod), k - 1, 0.8])
+        # gradients of sum(y * r) through the reference's autograd (grouped-conv backward of NET:60-63)
+        xg = x.clone().requires_grad_(True); wg = w.clone().requires_grad_(True); sg = s.clone().requires_grad_(True)
+        r = rn(*y.shape)
+        (modulated_conv2d(x=xg, w=wg, s=sg, demodulate=demod, padding=k - 1, input_gain=ig) * r).sum().backward()
+        out[t + '.r'] = r.numpy(); out[t + '.dx'] = xg.grad.numpy(); out[t + '.dw'] = wg.grad.numpy(); out[t + '.ds'] = sg.grad.numpy()
 
     # ---- FullyConnectedLayer / MappingNetwork / SynthesisInput ----
     torch.manual_seed(7)
@@ -231,6 +236,33 @@ def gen_tiny():
     print('tiny_gen.npz', y.shape, float(y.abs().max()))
 
 
+def gen_tiny_grads():
+    """Gradients of the L1 training loss mean|G(z,c,x) - target| with respect to every generator parameter, from the
+    reference's own autograd on its CPU `_ref` operators (pins the training-step path, BASELINE config 5)."""
+    G = build_ref(TINY, seed=0)
+    g = torch.Generator().manual_seed(99)
+    with torch.no_grad():                      # same perturbation as gen_tiny
+        for n, p in G.named_parameters():
+            if n.endswith('.bias') and 'affine' not in n:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+        for n, buf in G.named_buffers():
+            if n.endswith('magnitude_ema'):
+                buf.copy_(torch.rand([], generator=g) * 1.5 + 0.5)
+    z, c, x, u8 = synth_inputs(TINY, 3, seed=5)
+    tg = torch.Generator().manual_seed(17)
+    target = torch.rand(3, 1, TINY['img_resolution'], TINY['img_resolution'], generator=tg) * 2 - 1
+    for p in G.parameters():
+        p.requires_grad_(True)
+    y = G(z, c, x, noise_mode='const')
+    loss = (y - target).abs().mean()
+    loss.backward()
+    out = {'target': target.numpy(), 'loss': np.asarray(loss.item())}
+    for n, p in G.named_parameters():
+        out['G.' + n] = (p.grad if p.grad is not None else torch.zeros_like(p)).numpy()
+    np.savez_compressed(os.path.join(HERE, 'tiny_gen_grads.npz'), **out)
+    print('tiny_gen_grads.npz', float(loss), len(out))
+
+
 def gen_full():
     G = build_ref(FULL, seed=0)
     out = {}
@@ -259,10 +291,12 @@ def gen_full():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['ops', 'tiny', 'full']
+    which = sys.argv[1:] or ['ops', 'tiny', 'tiny_grads', 'full']
     if 'ops' in which:
         gen_ops()
     if 'tiny' in which:
         gen_tiny()
+    if 'tiny_grads' in which:
+        gen_tiny_grads()
     if 'full' in which:
         gen_full()

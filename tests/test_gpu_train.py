@@ -1,0 +1,219 @@
+"""GPU parity of the training-step path (BASELINE config 5): gradients of the native convolution / modulated
+convolution / FC / whole generator against the gradients the reference's autograd produced (golden files) -- fp32
+path within 1e-4 of the per-tensor maximum, tensor-core path (bf16 operands, fp32 accumulation) within 3e-2."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TINY = dict(z_dim=64, c_dim=1, w_dim=64, img_resolution=32, mapping_layers=3, channel_base=512, channel_max=48,
+            num_layers=6, skip_resolution=16)
+
+
+@pytest.fixture(autouse=True)
+def _restore_impl():
+    from afcm_b200.torch_utils.ops import conv2d_gradfix
+    yield
+    conv2d_gradfix.set_conv_impl('f32', torch.float16)
+
+
+def _modconv_case(g, name, dev):
+    t = 'modconv.' + name
+    demod, pad, ig = int(g[t + '.cfg'][0]), int(g[t + '.cfg'][1]), float(g[t + '.cfg'][2])
+    x = torch.as_tensor(g[t + '.x'], device=dev).requires_grad_(True)
+    w = torch.as_tensor(g[t + '.w'], device=dev).requires_grad_(True)
+    s = torch.as_tensor(g[t + '.s'], device=dev).requires_grad_(True)
+    r = torch.as_tensor(g[t + '.r'], device=dev)
+    return t, demod, pad, torch.tensor(ig, device=dev), x, w, s, r
+
+
+@pytest.mark.parametrize('name', ['demod3', 'torgb1', 'demod3b'])
+def test_modulated_conv2d_grads_fp32(golden_ops, name):
+    from afcm_b200.networks_stylegan3 import modulated_conv2d
+    dev = torch.device('cuda:0')
+    g = golden_ops
+    t, demod, pad, ig, x, w, s, r = _modconv_case(g, name, dev)
+    y = modulated_conv2d(x=x, w=w, s=s, demodulate=bool(demod), padding=pad, input_gain=ig, impl='f32')
+    assert rel_err(y.detach().cpu().numpy(), g[t + '.y']) < 1e-4
+    (y * r).sum().backward()
+    assert rel_err(x.grad.cpu().numpy(), g[t + '.dx']) < 1e-4
+    assert rel_err(w.grad.cpu().numpy(), g[t + '.dw']) < 1e-4
+    assert rel_err(s.grad.cpu().numpy(), g[t + '.ds']) < 1e-4
+
+
+@pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize('name', ['demod3', 'demod3b'])
+def test_modulated_conv2d_grads_tc(golden_ops, name, dtype):
+    from afcm_b200.networks_stylegan3 import modulated_conv2d
+    from afcm_b200.torch_utils.ops import conv2d_gradfix
+    dev = torch.device('cuda:0')
+    g = golden_ops
+    conv2d_gradfix.set_conv_impl('tc', dtype)
+    t, demod, pad, ig, x, w, s, r = _modconv_case(g, name, dev)
+    y = modulated_conv2d(x=x, w=w, s=s, demodulate=bool(demod), padding=pad, input_gain=ig, impl='tc')
+    tol = 3e-2 if dtype == torch.bfloat16 else 5e-3
+    assert rel_err(y.detach().cpu().numpy(), g[t + '.y']) < tol
+    (y * r).sum().backward()
+    assert rel_err(x.grad.cpu().numpy(), g[t + '.dx']) < tol
+    assert rel_err(w.grad.cpu().numpy(), g[t + '.dw']) < tol
+    assert rel_err(s.grad.cpu().numpy(), g[t + '.ds']) < tol
+
+
+@pytest.mark.parametrize('shape', [(2, 5, 7, 9, 10, 3, 2), (3, 70, 130, 38, 38, 3, 2), (2, 64, 64, 36, 36, 3, 1),
+                                   (1, 24, 3, 20, 22, 1, 0), (2, 181, 91, 150, 150, 3, 2)])
+def test_conv_grads_vs_torch_fp32(shape):
+    """_ConvFn (exact path) against autograd of torch.nn.functional.conv2d in float64 on the same operands."""
+    from afcm_b200.torch_utils.ops import conv2d_gradfix
+    N, Ci, Co, H, W, k, pad = shape
+    dev = torch.device('cuda:0')
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(N, Ci, H, W, generator=gen).to(dev).requires_grad_(True)
+    w = (torch.randn(Co, Ci, k, k, generator=gen) / np.sqrt(Ci * k * k)).to(dev).requires_grad_(True)
+    ic = (torch.rand(N, Ci, generator=gen) + 0.5).to(dev).requires_grad_(True)
+    oc = (torch.rand(N, Co, generator=gen) + 0.5).to(dev).requires_grad_(True)
+    y = conv2d_gradfix._ConvFn.apply(x, w, ic, oc, pad, 'f32')
+    r = torch.randn(y.shape, generator=gen).to(dev)
+    (y * r).sum().backward()
+    xd, wd, icd, ocd = [t.detach().double().requires_grad_(True) for t in (x, w, ic, oc)]
+    yd = torch.nn.functional.conv2d(xd * icd[:, :, None, None], wd, padding=pad) * ocd[:, :, None, None]
+    (yd * r.double()).sum().backward()
+    assert rel_err(y.detach().cpu(), yd.detach().cpu()) < 1e-5
+    for a, b, n in ((x, xd, 'dx'), (w, wd, 'dw'), (ic, icd, 'dicoef'), (oc, ocd, 'docoef')):
+        assert rel_err(a.grad.cpu(), b.grad.cpu()) < 2e-5, n
+
+
+@pytest.mark.parametrize('shape', [(2, 16, 24, 12, 14, 2), (3, 70, 130, 38, 38, 2), (2, 64, 64, 36, 36, 1),
+                                   (2, 181, 91, 150, 150, 2), (1, 512, 512, 54, 54, 2), (2, 4, 64, 276, 276, 2)])
+@pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float16])
+def test_conv_grads_tc_vs_fp32(shape, dtype):
+    """Tensor-core gradients (tcgen05 data gradient with pad 0/1, mma.sync weight gradient) against the exact path on
+    operands that are exactly representable in the 16-bit type (small integers / powers of two): there the only
+    difference is the fp32 summation order, so the bound is tight (1e-5)."""
+    from afcm_b200.torch_utils.ops import conv2d_gradfix
+    N, Ci, Co, H, W, pad = shape
+    dev = torch.device('cuda:0')
+    gen = torch.Generator().manual_seed(5)
+    conv2d_gradfix.set_conv_impl('tc', dtype)
+
+    def ints(*s, lo=-3, hi=4):
+        return torch.randint(lo, hi, s, generator=gen).float()
+    x0 = ints(N, Ci, H, W)
+    w0 = ints(Co, Ci, 3, 3, lo=-2, hi=3) * 0.25
+    r = ints(N, Co, H + 2 * pad - 2, W + 2 * pad - 2).to(dev)
+    ic0 = 2.0 ** torch.randint(-1, 2, (N, Ci), generator=gen).float()
+    oc0 = 2.0 ** torch.randint(-1, 2, (N, Co), generator=gen).float()
+    res = {}
+    for impl in ('f32', 'tc'):
+        x, w, ic, oc = [t.clone().to(dev).requires_grad_(True) for t in (x0, w0, ic0, oc0)]
+        y = conv2d_gradfix._ConvFn.apply(x, w, ic, oc, pad, impl)
+        (y * r).sum().backward()
+        res[impl] = [y.detach().cpu()] + [t.grad.cpu() for t in (x, w, ic, oc)]
+    for a, b, n in zip(res['tc'], res['f32'], ('y', 'dx', 'dw', 'dicoef', 'docoef')):
+        assert rel_err(a, b) < 1e-5, n
+
+
+def test_fc_grads(golden_ops):
+    from afcm_b200.networks_stylegan3 import FullyConnectedLayer
+    dev = torch.device('cuda:0')
+    gen = torch.Generator().manual_seed(11)
+    for act, lr_mul in (('lrelu', 0.01), ('linear', 1.0)):
+        fc = FullyConnectedLayer(37, 19, activation=act, lr_multiplier=lr_mul, bias_init=0.3).to(dev)
+        x = torch.randn(5, 37, generator=gen).to(dev).requires_grad_(True)
+        r = torch.randn(5, 19, generator=gen).to(dev)
+        (fc(x) * r).sum().backward()
+        xd = x.detach().double().requires_grad_(True)
+        wd = fc.weight.detach().double().requires_grad_(True)
+        bd = fc.bias.detach().double().requires_grad_(True)
+        yd = xd @ (wd * fc.weight_gain).t() + bd * fc.bias_gain
+        if act == 'lrelu':
+            yd = torch.nn.functional.leaky_relu(yd, 0.2) * np.sqrt(2)
+        (yd * r.double()).sum().backward()
+        assert rel_err(x.grad.cpu(), xd.grad.cpu()) < 1e-5
+        assert rel_err(fc.weight.grad.cpu(), wd.grad.cpu()) < 1e-5
+        assert rel_err(fc.bias.grad.cpu(), bd.grad.cpu()) < 1e-5
+
+
+def _tiny(g, dev):
+    from afcm_b200.networks_stylegan3 import afcm_generator
+    G = afcm_generator(seed=0, device=None, **TINY)
+    sd = {k[2:]: torch.as_tensor(g[k]) for k in g.files if k.startswith('P.')}
+    G.load_state_dict(sd, strict=False)
+    G = G.to(dev)
+    for p in G.parameters():
+        p.requires_grad_(True)
+    return G
+
+
+def _grads(G, g, gg, dev):
+    y = G(torch.as_tensor(g['z'], device=dev), torch.as_tensor(g['c'], device=dev), torch.as_tensor(g['x'], device=dev),
+          noise_mode='const')
+    loss = (y - torch.as_tensor(gg['target'], device=dev)).abs().mean()
+    loss.backward()
+    return y, loss
+
+
+def test_tiny_generator_grads_fp32(golden_tiny, golden_tiny_grads):
+    """Every parameter gradient of the L1 training loss equals the reference's (its CPU autograd) within 1e-4."""
+    dev = torch.device('cuda:0')
+    g, gg = golden_tiny, golden_tiny_grads
+    G = _tiny(g, dev)
+    y, loss = _grads(G, g, gg, dev)
+    assert rel_err(y.detach().cpu().numpy(), g['y']) < 1e-4
+    assert abs(loss.item() - float(gg['loss'])) < 1e-5
+    worst = 0.0
+    for n, p in G.named_parameters():
+        ref = gg['G.' + n]
+        got = p.grad.cpu().numpy() if p.grad is not None else np.zeros_like(ref)
+        if np.abs(ref).max() == 0:
+            assert np.abs(got).max() < 1e-9, n
+            continue
+        e = rel_err(got, ref)
+        worst = max(worst, e)
+        assert e < 2e-4, (n, e)
+    print('worst gradient rel err', worst)
+
+
+def test_tiny_generator_grads_tc(golden_tiny, golden_tiny_grads):
+    """Tensor-core training path (bf16 operands): gradients within 5e-2 of the reference per tensor, cosine > 0.999."""
+    from afcm_b200.torch_utils.ops import conv2d_gradfix
+    dev = torch.device('cuda:0')
+    g, gg = golden_tiny, golden_tiny_grads
+    conv2d_gradfix.set_conv_impl('tc', torch.bfloat16)
+    G = _tiny(g, dev)
+    y, loss = _grads(G, g, gg, dev)
+    assert rel_err(y.detach().cpu().numpy(), g['y']) < 3e-2
+    for n, p in G.named_parameters():
+        ref = gg['G.' + n]
+        if np.abs(ref).max() == 0:
+            continue
+        got = p.grad.cpu().numpy()
+        cos = float((got * ref).sum() / (np.linalg.norm(got) * np.linalg.norm(ref) + 1e-30))
+        assert rel_err(got, ref) < 8e-2 and cos > 0.995, (n, rel_err(got, ref), cos)
+
+
+def test_trainer_step_single_gpu(golden_tiny, golden_tiny_grads):
+    """GeneratorTrainer: flat buffers alias the parameters, the fused Adam step equals torch.optim.Adam."""
+    from afcm_b200.training import GeneratorTrainer
+    dev = torch.device('cuda:0')
+    g, gg = golden_tiny, golden_tiny_grads
+    G = _tiny(g, dev)
+    before = {n: p.detach().clone() for n, p in G.named_parameters()}
+    tr = GeneratorTrainer(G, lr=1e-3, betas=(0.0, 0.99))
+    args = [torch.as_tensor(g[k], device=dev) for k in ('z', 'c', 'x')] + [torch.as_tensor(gg['target'], device=dev)]
+    loss = tr.forward_backward(*args)
+    assert abs(loss.item() - float(gg['loss'])) < 1e-5
+    grads = {n: p.grad.detach().clone() for n, p in G.named_parameters()}
+    for n, p in G.named_parameters():
+        assert rel_err(grads[n].cpu().numpy(), gg['G.' + n]) < 2e-4 or np.abs(gg['G.' + n]).max() == 0, n
+    tr.opt.step()
+    for n, p in G.named_parameters():
+        ref = before[n].clone().requires_grad_(True)
+        opt = torch.optim.Adam([ref], lr=1e-3, betas=(0.0, 0.99), eps=1e-8)
+        ref.grad = grads[n]
+        opt.step()
+        assert torch.allclose(p.detach(), ref.detach(), rtol=1e-5, atol=1e-7), n
+    l2 = tr.step(*args)
+    assert l2.item() < loss.item()          # the step reduces the loss on the same batch
