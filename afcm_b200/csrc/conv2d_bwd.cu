@@ -184,27 +184,47 @@ wgrad_tc_kernel(const WtParams p)
 #pragma unroll
                 for (int c = 0; c < 4; c++) acc[t][a][b][c] = 0.f;
 
+    // Per-thread copy pattern, fixed for the whole kernel: 16-byte channel chunk c8 = tid & 7, pixel slots tid >> 3 (+32, +64).
+    // Only the tile origin changes from stage to stage, so the address arithmetic per cp.async is one add.
+    const int c8 = (tid & 7) * 8, j0 = tid >> 3;
+    const bool a_ch_ok = o0 + c8 < p.co_pad, b_ch_ok = i0 + c8 < p.ci_pad;
+    const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(wt_smem);
+    const uint32_t a_dst0 = (uint32_t)((j0 * WT_PITCH + c8) * 2);
+    const long long a_src0 = (long long)j0 * p.co_pad + o0 + c8;
+    const long long b_rowstep = (long long)(p.W + 2) * p.ci_pad;
+    auto cp16 = [&](uint32_t dst, const uint16_t* src, bool ok) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
+    };
     auto load_stage = [&](int it) {
         const long long s = s0 + it;
         const int ch = (int)(s % p.nchunk);
         const long long r = s / p.nchunk;
         const int oy = (int)(r % p.OH), n = (int)(r / p.OH);
         const int x0 = ch * WT_KB;
-        uint16_t* As = wt_smem + (size_t)(it % WT_STAGES) * WT_STAGE_ELEMS;
-        uint16_t* Bs = As + WT_A_ELEMS;
-        const uint16_t* an = p.dyp + ((long long)n * rowsA + (long long)oy * (p.OW + 2) + x0) * p.co_pad;
-        for (int idx = tid; idx < WT_KB * 8; idx += 256) {
-            const int k = idx >> 3, c8 = (idx & 7) * 8;
-            const bool ok = (x0 + k < p.OW) && (o0 + c8 < p.co_pad);
-            cp_async16_zfill(As + k * WT_PITCH + c8, ok ? an + (long long)k * p.co_pad + o0 + c8 : p.dyp, ok);
+        const uint32_t sA = smem0 + (uint32_t)((it % WT_STAGES) * WT_STAGE_ELEMS * 2), sB = sA + WT_A_ELEMS * 2;
+        const uint16_t* an = p.dyp + ((long long)n * rowsA + (long long)oy * (p.OW + 2) + x0) * p.co_pad + a_src0;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const bool ok = a_ch_ok && (x0 + j0 + h * 32 < p.OW);
+            cp16(sA + a_dst0 + (uint32_t)(h * 32 * WT_PITCH * 2), ok ? an + (long long)h * 32 * p.co_pad : p.dyp, ok);
         }
-        const uint16_t* bn = p.xp + (long long)n * rowsB * p.ci_pad;
-        for (int idx = tid; idx < 3 * WT_BPX * 8; idx += 256) {
-            const int c8 = (idx & 7) * 8, rj = idx >> 3, j = rj % WT_BPX, ky = rj / WT_BPX;
-            const int iy = oy + ky - p.pad, xi = x0 + j - p.pad;
-            const long long flat = (long long)iy * (p.W + 2) + xi;
-            const bool ok = iy >= 0 && iy < p.H && flat >= 0 && xi < p.W + 2 && (i0 + c8 < p.ci_pad);
-            cp_async16_zfill(Bs + (ky * WT_BPX + j) * WT_PITCH + c8, ok ? bn + flat * p.ci_pad + i0 + c8 : p.xp, ok);
+        // B: rows iy = oy + ky - pad, pixels xi = x0 - pad + j, j = j0 + 32 h (h = 2 only for j0 < 2)
+        const int xi0 = x0 - p.pad + j0;
+        const long long flat0 = (long long)(oy - p.pad) * (p.W + 2) + xi0;
+        const uint16_t* bn = p.xp + ((long long)n * rowsB + flat0) * p.ci_pad + i0 + c8;
+#pragma unroll
+        for (int ky = 0; ky < 3; ky++) {
+            const int iy = oy + ky - p.pad;
+            const bool row_ok = b_ch_ok && iy >= 0 && iy < p.H;
+            const uint16_t* br = bn + ky * b_rowstep;
+            const uint32_t d = sB + (uint32_t)(((ky * WT_BPX + j0) * WT_PITCH + c8) * 2);
+#pragma unroll
+            for (int h = 0; h < 3; h++) {
+                if (h == 2 && j0 >= WT_BPX - 64) break;
+                const int xi = xi0 + h * 32;
+                const bool ok = row_ok && (flat0 + ky * (p.W + 2) + h * 32 >= 0) && xi < p.W + 2;
+                cp16(d + (uint32_t)(h * 32 * WT_PITCH * 2), ok ? br + (long long)h * 32 * p.ci_pad : p.xp, ok);
+            }
         }
     };
 

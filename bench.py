@@ -307,8 +307,136 @@ def run_ours(args, rank, world):
         dist.destroy_process_group()
 
 
+def run_train(args, rank, world):
+    """BASELINE configs[4]: generator training step (forward + backward + gradient all-reduce + fused Adam), synthetic
+    256x256 slices, batch 32 per GPU, weak scaling.  `python bench.py --workload train [--batch 32]`."""
+    import torch
+    import torch.distributed as dist
+    from afcm_b200 import _lib
+    from afcm_b200.networks_stylegan3 import afcm_generator
+    from afcm_b200.torch_utils.ops import conv2d_gradfix
+    from afcm_b200.training import GeneratorTrainer
+
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    _lib.check(_lib.lib().afcm_device_check())
+    if world > 1:
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B = args.batch if args.batch != 64 else 32                       # config 5: batch 32 per GPU
+    if args.precision == 'fp32':
+        conv2d_gradfix.set_conv_impl('f32')
+    else:
+        conv2d_gradfix.set_conv_impl('tc', torch.bfloat16)           # bf16 operands (gradient range), fp32 accumulation/storage
+    G = afcm_generator(seed=0, device=dev).train()
+    tr = GeneratorTrainer(G, lr=0.0025, betas=(0.0, 0.99))
+    z, c, x = synthetic_inputs(B, seed=rank, as_uint8=True)
+    tgt = torch.rand(B, 1, 256, 256, generator=torch.Generator().manual_seed(100 + rank)) * 2 - 1
+    hz, hc, hx, ht = z.pin_memory(), c.pin_memory(), x.pin_memory(), tgt.pin_memory()
+    hl = torch.empty([1], dtype=torch.float32).pin_memory()
+    dz, dc, dx, dt = hz.to(dev), hc.to(dev), hx.to(dev), ht.to(dev)
+
+    def step_resident():
+        return tr.step(dz, dc, dx, dt)
+
+    def step_e2e():
+        loss = tr.step(hz.to(dev, non_blocking=True), hc.to(dev, non_blocking=True), hx.to(dev, non_blocking=True),
+                       ht.to(dev, non_blocking=True))
+        hl.copy_(loss.reshape(1), non_blocking=True)
+
+    def timed_region(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    losses = []
+    for _ in range(max(args.warmup, 3)):
+        losses.append(float(step_resident()))
+    sampler = ClockSampler(local)
+    sampler.start()
+    n0 = _lib.launch_count()
+    ms_total = timed_region(step_resident, args.steps)
+    launches = _lib.launch_count() - n0
+    clocks = sampler.finish()
+    step_e2e()
+    ms_e2e = timed_region(step_e2e, args.steps)
+    nprof = min(args.steps, 2)
+    _lib.profile_begin()
+    for _ in range(nprof):
+        step_resident()
+    prof = _lib.profile_end()
+    peak_mem = torch.cuda.max_memory_allocated(dev)
+    peaks = load_peaks()
+    slices = float(B * world * args.steps)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    def roof(name, bound):
+        d = prof.get(name)
+        if not d or d['ms'] <= 0:
+            return None
+        if bound == 'tensor':
+            ach, peak, unit = d['work'] / d['ms'] / 1e9, peaks['tf_sustained'], 'TFLOP/s'
+        else:
+            ach, peak, unit = d['work'] / d['ms'] / 1e6, peaks['hbm'], 'GB/s'
+        return dict(kernel=name, bound=bound, achieved=ach, peak=peak, unit=unit, frac=ach / peak, traffic=None,
+                    peak_source=peaks['source'] + (' (sustained bf16 cuBLAS)' if bound == 'tensor' else ' (copy)'),
+                    launches_per_step=d['launches'] // nprof, ms_per_step=d['ms'] / nprof,
+                    work_per_launch=d['work'] / max(d['launches'], 1))
+
+    rf = {k: roof(k, b) for k, b in (('conv2d_tc', 'tensor'), ('conv2d_tc_dgrad', 'tensor'), ('conv2d_wgrad_tc', 'tensor'),
+                                     ('filtered_lrelu', 'hbm'), ('conv_tc_pack', 'hbm'))}
+    line = dict(metric='generator_train_slices_per_sec_256x256', value=slices / (ms_total * 1e-3), unit=UNIT, n_gpus=world,
+                steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_total / args.steps, higher_is_better=True,
+                scaling='weak', vs_baseline=None,
+                dtype='bf16 conv operands / f32 accumulate, f32 storage and filtered_lrelu' if args.precision != 'fp32' else 'f32',
+                data='synthetic',
+                config=dict(workload='AFCM generator training step (forward + backward + gradient all-reduce + Adam), synthetic '
+                                     '256x256 slices, batch 32 per GPU', batch_per_gpu=B, global_batch=B * world, resolution=256,
+                            loss='L1 against a synthetic target (discriminator outside the path)', parameters=tr.flat.flat.numel(),
+                            allreduce_bytes_per_step=(tr.flat.grad.numel() * 4 if world > 1 else 0),
+                            allreduce='torch.distributed NCCL sum, %d buckets launched from post-accumulate-grad hooks' % len(tr.flat.buckets),
+                            peak_memory_gb=peak_mem / 2 ** 30, first_losses=losses[:3],
+                            l2='working set per step (tens of GB of saved activations) exceeds the 126 MB L2; no explicit flush'),
+                clocks=clocks, gpu_launches=int(launches),
+                e2e=dict(value=slices / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=int(hz.nbytes + hc.nbytes + hx.nbytes + ht.nbytes),
+                         d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps),
+                roofline=max([r for r in rf.values() if r], key=lambda r: r['ms_per_step'], default=None), rooflines=rf)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument('--workload', default='forward', choices=['forward', 'train'],
+                    help='forward = BASELINE configs[1] (the headline metric); train = configs[4] (training step)')
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
@@ -322,6 +450,8 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', 1))
     if args.impl == 'reference':
         run_reference(args, rank)
+    elif args.workload == 'train':
+        run_train(args, rank, world)
     else:
         run_ours(args, rank, world)
 
