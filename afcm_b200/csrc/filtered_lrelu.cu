@@ -22,6 +22,7 @@ flr_fused_kernel(const __grid_constant__ FlrParams p)
     const FlrTile t = flr_tile<UP, DOWN>(p, blockIdx.x);
 
     flr_pass_load<T>(tid, FLR_THREADS, p, t, buf_a);
+    if (SIGN == 2) flr_pass_sign_load(tid, FLR_THREADS, p, t, s_sign);
     __syncthreads();
     flr_pass_hup<UP, FU, G>(tid, FLR_THREADS, p, buf_a, buf_b);
     __syncthreads();
@@ -94,14 +95,14 @@ static int g_tile_override[2] = {0, 0};
 struct TileChoice { int tow, toh; size_t smem; double score; };
 
 template <int UP, int FU, int DOWN, int FD>
-static TileChoice choose_tile(FlrParams& p, bool sign_write)
+static TileChoice choose_tile(FlrParams& p, int sign_stage)
 {
     const int smem_cap = max_smem_optin();
     TileChoice best = {0, 0, 0, -1.0};
     auto try_tile = [&](int tow, int toh) {
         if ((tow * DOWN) % 4) return;
         FlrParams q = p;
-        size_t bytes = flr_make_geom<UP, FU, DOWN, FD, FLR_G>(q, tow, toh, sign_write);
+        size_t bytes = flr_make_geom<UP, FU, DOWN, FD, FLR_G>(q, tow, toh, sign_stage);
         if ((long long)bytes > smem_cap - 1024) return;
         // useful outputs / computed up-res samples, derated by occupancy (CTAs per SM that fit)
         const double useful = (double)p.yw * p.yh;
@@ -128,9 +129,10 @@ static TileChoice choose_tile(FlrParams& p, bool sign_write)
 template <typename T, int UP, int FU, int DOWN, int FD>
 static int launch_fused(FlrParams& p, int sign_mode, cudaStream_t stream)
 {
-    TileChoice tc = choose_tile<UP, FU, DOWN, FD>(p, sign_mode == AFCM_SIGN_WRITE);
+    const int sign_stage = sign_mode == AFCM_SIGN_WRITE ? 1 : (sign_mode == AFCM_SIGN_READ ? 2 : 0);
+    TileChoice tc = choose_tile<UP, FU, DOWN, FD>(p, sign_stage);
     if (tc.score < 0) { set_error("filtered_lrelu: no tile fits in shared memory"); return AFCM_ERR_UNSUPPORTED; }
-    const size_t smem = flr_make_geom<UP, FU, DOWN, FD, FLR_G>(p, tc.tow, tc.toh, sign_mode == AFCM_SIGN_WRITE);
+    const size_t smem = flr_make_geom<UP, FU, DOWN, FD, FLR_G>(p, tc.tow, tc.toh, sign_stage);
     const long long tiles = (long long)p.N * p.C * p.tiles_x * p.tiles_y;
     if (tiles > 0x7fffffffLL) { set_error("filtered_lrelu: too many tiles"); return AFCM_ERR_INVALID; }
     void (*kern)(const FlrParams) = nullptr;

@@ -60,8 +60,12 @@ AFCM_HD int flr_floor_mod(int a, int m) { int r = a % m; return r < 0 ? r + m : 
 AFCM_HD int flr_floor_div(int a, int m) { int q = a / m; return (a % m != 0 && ((a < 0) != (m < 0))) ? q - 1 : q; }
 
 // Fills the geometry fields for an output tile of tow x toh.  G = register-blocking factor.
+AFCM_HD int flr_sign_pitch(int uwt) { return ((((uwt + 3) >> 2) + 2) + 3) & ~3; }   // staged sign bytes per row (read mode)
+
+// sign_stage: 0 = no sign staging area, 1 = sign-write mode (one code byte per element), 2 = sign-read mode (the
+// tile's part of the packed sign tensor).
 template <int UP, int FU, int DOWN, int FD, int G>
-inline size_t flr_make_geom(FlrParams& p, int tow, int toh, bool sign_write)
+inline size_t flr_make_geom(FlrParams& p, int tow, int toh, int sign_stage)
 {
     constexpr int R = FU / UP;
     p.tow = tow; p.toh = toh;
@@ -85,7 +89,8 @@ inline size_t flr_make_geom(FlrParams& p, int tow, int toh, bool sign_write)
     p.off_b = (int)a;
     size_t bytes = (a + b) * sizeof(float);
     p.off_sign = 0;
-    if (sign_write) { p.off_sign = (int)bytes; bytes += (size_t)p.uht * (size_t)((p.uwt + 3) & ~3); }
+    if (sign_stage == 1) { p.off_sign = (int)bytes; bytes += (size_t)p.uht * (size_t)((p.uwt + 3) & ~3); }
+    if (sign_stage == 2) { p.off_sign = (int)bytes; bytes += (size_t)p.uht * (size_t)flr_sign_pitch(p.uwt); }
     return bytes;
 }
 
@@ -130,6 +135,23 @@ AFCM_HD void flr_pass_load(int tid, int nthr, const FlrParams& p, const FlrTile&
         if (ix < p.inw && gy >= 0 && gy < p.xh && gx >= 0 && gx < p.xw)
             v = (float)xp[gy * p.xs_h + gx * p.xs_w] + bias;
         s_in[i] = v;
+    }
+}
+
+// ---- pass 0b (sign-read mode): stage the tile's part of the packed sign tensor (4 codes per byte) in shared memory
+// with coalesced byte loads; bytes outside the tensor read as 0 = "leave the value alone" (same as the bounds test of
+// the reference kernel, filtered_lrelu.cu:562-572).  Staged byte (ly, b) = sign byte (uy0 + ly + s_oy, eb0 + b).
+AFCM_HD void flr_pass_sign_load(int tid, int nthr, const FlrParams& p, const FlrTile& t, uint8_t* s_sign)
+{
+    const int nbp = flr_sign_pitch(p.uwt);
+    const int eb0 = flr_floor_div(t.ux0 + p.s_ox, 4);
+    const int items = p.uht * nbp;
+    for (int it = tid; it < items; it += nthr) {
+        const int ly = it / nbp, b = it - ly * nbp;
+        const int ey = t.uy0 + ly + p.s_oy, eb = eb0 + b;
+        uint8_t v = 0;
+        if (ey >= 0 && ey < p.s_h && eb >= 0 && eb < p.s_wb) v = p.si[((long long)t.plane * p.s_h + ey) * p.s_wb + eb];
+        s_sign[it] = v;
     }
 }
 
@@ -194,6 +216,11 @@ AFCM_HD void flr_pass_vup(int tid, int nthr, const FlrParams& p, const FlrTile& 
 #pragma unroll
         for (int j = 0; j < G + R; j++) w[j] = src[j * p.p_uh];
         const bool col_ok = lx >= 0 && lx < p.uwt;
+        // sign-read mode: element lx of a staged row sits in byte (se >> 2), bit pair (se & 3)
+        const int se = SIGN == 2 ? t.ux0 + p.s_ox - 4 * flr_floor_div(t.ux0 + p.s_ox, 4) + lx : 0;
+        const uint8_t* srow = s_sign + (se >> 2);
+        const int sshift = (se & 3) << 1;
+        const int nbp = SIGN == 2 ? flr_sign_pitch(p.uwt) : 0;
 #pragma unroll
         for (int g = 0; g < G; g++) {
 #pragma unroll
@@ -205,9 +232,8 @@ AFCM_HD void flr_pass_vup(int tid, int nthr, const FlrParams& p, const FlrTile& 
                 const int ly = (ch * G + g) * UP + q - t.sys;
                 float v = acc * p.gain;
                 if (SIGN == 2) {
-                    const int ex = t.ux0 + lx + p.s_ox, ey = t.uy0 + ly + p.s_oy;
-                    if (col_ok && ly >= 0 && ly < p.uht && ex >= 0 && ex < (p.s_wb << 2) && ey >= 0 && ey < p.s_h) {
-                        const int s = p.si[((long long)t.plane * p.s_h + ey) * p.s_wb + (ex >> 2)] >> ((ex & 3) << 1);
+                    if (col_ok && ly >= 0 && ly < p.uht) {
+                        const int s = srow[ly * nbp] >> sshift;
                         if (s & 1) v *= p.slope;
                         if (s & 2) v = 0.f;
                     }
@@ -236,10 +262,11 @@ AFCM_HD void flr_pass_sign_flush(int tid, int nthr, const FlrParams& p, const Fl
         const int ey = t.uy0 + ly + p.s_oy;
         const int eb = ((t.ux0 + p.s_ox) >> 2) + bx;
         if (ey < 0 || ey >= p.s_h || eb < 0 || eb >= p.s_wb) continue;
-        const uint8_t* s = s_sign + ly * uwt4 + bx * 4;
-        int code = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) code |= (bx * 4 + k < p.uwt ? (int)s[k] : 0) << (2 * k);
+        // four staged code bytes (values 0..2) as one aligned word; bytes at or beyond uwt were never written
+        uint32_t w = *reinterpret_cast<const uint32_t*>(s_sign + ly * uwt4 + bx * 4);
+        const int nvalid = p.uwt - bx * 4;
+        if (nvalid < 4) w &= (1u << (8 * nvalid)) - 1u;
+        const int code = (int)((w & 3u) | ((w >> 6) & 0xcu) | ((w >> 12) & 0x30u) | ((w >> 18) & 0xc0u));
         // elements beyond this tile's uwt belong to the next tile; tiles overlap by FD-DOWN >= 4 samples,
         // so only whole bytes that this tile fully owns or that are the ragged end of the row are partial.
         // Partial bytes at a tile's right edge are skipped unless this is the last tile column.

@@ -11,7 +11,7 @@ using namespace afcm;
 template <int UP, int FU, int DOWN, int FD, int G>
 static int run(FlrParams p, int tow, int toh, int sign_mode, int nthr)
 {
-    size_t bytes = flr_make_geom<UP, FU, DOWN, FD, G>(p, tow, toh, sign_mode == 1);
+    size_t bytes = flr_make_geom<UP, FU, DOWN, FD, G>(p, tow, toh, sign_mode);
     std::vector<float> smem(bytes / 4 + 64);
     const long long tiles = (long long)p.N * p.C * p.tiles_x * p.tiles_y;
     for (long long tile = 0; tile < tiles; tile++) {
@@ -21,6 +21,7 @@ static int run(FlrParams p, int tow, int toh, int sign_mode, int nthr)
         uint8_t* ss = reinterpret_cast<uint8_t*>(smem.data()) + p.off_sign;
         FlrTile t = flr_tile<UP, DOWN>(p, (int)tile);
         for (int tid = 0; tid < nthr; tid++) flr_pass_load<float>(tid, nthr, p, t, a);
+        if (sign_mode == 2) for (int tid = 0; tid < nthr; tid++) flr_pass_sign_load(tid, nthr, p, t, ss);
         for (int tid = 0; tid < nthr; tid++) flr_pass_hup<UP, FU, G>(tid, nthr, p, a, b);
         for (int tid = 0; tid < nthr; tid++) {
             if (sign_mode == 0) flr_pass_vup<UP, FU, G, 0>(tid, nthr, p, t, b, a, ss);

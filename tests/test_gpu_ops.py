@@ -207,11 +207,17 @@ def test_fully_connected_mapping_fourier(dev, golden_ops):
     assert rel_err(y.cpu().numpy(), g['fc2.y']) < TIGHT
     mp = net.MappingNetwork(z_dim=48, c_dim=1, w_dim=40, num_ws=6, num_layers=3)
     mp.load_state_dict({k[len('map.P.'):]: torch.as_tensor(g[k]) for k in g.files if k.startswith('map.P.')})
-    ws = mp.to(dev)(_t(g['map.z'], dev), _t(g['map.c'], dev))
+    mp = mp.to(dev)
+    with torch.no_grad():                                     # inference path: fused native kernels
+        ws = mp(_t(g['map.z'], dev), _t(g['map.c'], dev))
     assert rel_err(ws.cpu().numpy(), g['map.ws']) < TIGHT
+    ws = mp(_t(g['map.z'], dev), _t(g['map.c'], dev))         # parameters require grad: the autograd (training) path
+    assert ws.requires_grad
+    assert rel_err(ws.detach().cpu().numpy(), g['map.ws']) < TIGHT
     si = net.SynthesisInput(w_dim=40, channels=12, size=20, sampling_rate=16, bandwidth=2)
     si.load_state_dict({k[len('synin.P.'):]: torch.as_tensor(g[k]) for k in g.files if k.startswith('synin.P.')})
-    y = si.to(dev)(_t(g['synin.w'], dev))
+    with torch.no_grad():
+        y = si.to(dev)(_t(g['synin.w'], dev))
     assert rel_err(y.cpu().numpy(), g['synin.y']) < 5e-5
 
 
