@@ -199,6 +199,41 @@ AFCM_HD void flr_pass_hup(int tid, int nthr, const FlrParams& p, const float* s_
 // ---- pass 2: vertical polyphase up-FIR + gain + leaky ReLU + clamp (+ signs) ---------------------
 // s_uh[inh][p_uh] -> s_u[uht][p_u], storing at (ly - sys, lx - sxs).
 // SIGN: 0 none, 1 write (2-bit codes staged as bytes in s_sign[uht][uwt4]), 2 read from p.si.
+// One item of pass 2: G*UP consecutive up-res rows of one column.  CHECK = the rows may fall outside [0, uht).
+template <int UP, int FU, int G, int SIGN, bool CHECK>
+AFCM_HD void flr_vup_rows(const FlrParams& p, const float* w, int ly0, float* dst, uint8_t* sdst, const uint8_t* srow,
+                          int sshift, int nbp, int uwt4)
+{
+    constexpr int R = FU / UP;
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+#pragma unroll
+        for (int q = 0; q < UP; q++) {
+            float acc = 0.f;
+#pragma unroll
+            for (int r = 0; r < R; r++)
+                acc += (q == 0 ? p.ku[UP * r] : p.ku[UP - q + UP * r]) * w[g + (q == 0 ? 0 : 1) + r];
+            const int e = g * UP + q;                       // row offset inside the item (compile time)
+            const bool ok = !CHECK || (ly0 + e >= 0 && ly0 + e < p.uht);
+            float v = acc * p.gain;
+            if (SIGN == 2) {
+                if (ok) {
+                    const int s = srow[e * nbp] >> sshift;
+                    if (s & 1) v *= p.slope;
+                    if (s & 2) v = 0.f;
+                }
+            } else {
+                int s = 0;
+                if (v < 0.f) { v *= p.slope; s = 1; }
+                if (v > p.clamp) { v = p.clamp; s = 2; }
+                if (v < -p.clamp) { v = -p.clamp; s = 2; }
+                if (SIGN == 1 && ok) sdst[e * uwt4] = (uint8_t)s;
+            }
+            if (ok) dst[e * p.p_u] = v;
+        }
+    }
+}
+
 template <int UP, int FU, int G, int SIGN>
 AFCM_HD void flr_pass_vup(int tid, int nthr, const FlrParams& p, const FlrTile& t,
                           const float* s_uh, float* s_u, uint8_t* s_sign)
@@ -208,45 +243,27 @@ AFCM_HD void flr_pass_vup(int tid, int nthr, const FlrParams& p, const FlrTile& 
     const int nchunk = p.ngy / G;
     const int items = nchunk * ncols;
     const int uwt4 = (p.uwt + 3) & ~3;
+    const int nbp = SIGN == 2 ? flr_sign_pitch(p.uwt) : 0;
+    // sign-read mode: element lx of a staged row sits in byte ((se0 + lx) >> 2), bit pair ((se0 + lx) & 3)
+    const int se0 = SIGN == 2 ? t.ux0 + p.s_ox - 4 * flr_floor_div(t.ux0 + p.s_ox, 4) : 0;
     for (int it = tid; it < items; it += nthr) {
         const int ch = it / ncols, col = it - ch * ncols;
         const int lx = col - t.sxs;
+        if (lx < 0 || lx >= p.uwt) continue;            // column outside the region the down passes consume
         const float* src = s_uh + (ch * G) * p.p_uh + col;
         float w[G + R];
 #pragma unroll
         for (int j = 0; j < G + R; j++) w[j] = src[j * p.p_uh];
-        const bool col_ok = lx >= 0 && lx < p.uwt;
-        // sign-read mode: element lx of a staged row sits in byte (se >> 2), bit pair (se & 3)
-        const int se = SIGN == 2 ? t.ux0 + p.s_ox - 4 * flr_floor_div(t.ux0 + p.s_ox, 4) + lx : 0;
-        const uint8_t* srow = s_sign + (se >> 2);
-        const int sshift = (se & 3) << 1;
-        const int nbp = SIGN == 2 ? flr_sign_pitch(p.uwt) : 0;
-#pragma unroll
-        for (int g = 0; g < G; g++) {
-#pragma unroll
-            for (int q = 0; q < UP; q++) {
-                float acc = 0.f;
-#pragma unroll
-                for (int r = 0; r < R; r++)
-                    acc += (q == 0 ? p.ku[UP * r] : p.ku[UP - q + UP * r]) * w[g + (q == 0 ? 0 : 1) + r];
-                const int ly = (ch * G + g) * UP + q - t.sys;
-                float v = acc * p.gain;
-                if (SIGN == 2) {
-                    if (col_ok && ly >= 0 && ly < p.uht) {
-                        const int s = srow[ly * nbp] >> sshift;
-                        if (s & 1) v *= p.slope;
-                        if (s & 2) v = 0.f;
-                    }
-                } else {
-                    int s = 0;
-                    if (v < 0.f) { v *= p.slope; s = 1; }
-                    if (v > p.clamp) { v = p.clamp; s = 2; }
-                    if (v < -p.clamp) { v = -p.clamp; s = 2; }
-                    if (SIGN == 1 && col_ok && ly >= 0 && ly < p.uht) s_sign[ly * uwt4 + lx] = (uint8_t)s;
-                }
-                if (col_ok && ly >= 0 && ly < p.uht) s_u[ly * p.p_u + lx] = v;
-            }
-        }
+        const int ly0 = ch * G * UP - t.sys;            // first up-res row of the item (tile-local)
+        // the pointers below are only dereferenced at rows that pass the range test
+        float* dst = s_u + ly0 * p.p_u + lx;
+        uint8_t* sdst = s_sign + ly0 * uwt4 + lx;
+        const uint8_t* srow = s_sign + ly0 * nbp + ((se0 + lx) >> 2);
+        const int sshift = ((se0 + lx) & 3) << 1;
+        if (ly0 >= 0 && ly0 + G * UP <= p.uht)
+            flr_vup_rows<UP, FU, G, SIGN, false>(p, w, ly0, dst, sdst, srow, sshift, nbp, uwt4);
+        else
+            flr_vup_rows<UP, FU, G, SIGN, true>(p, w, ly0, dst, sdst, srow, sshift, nbp, uwt4);
     }
 }
 
@@ -321,19 +338,22 @@ AFCM_HD void flr_pass_vdown(int tid, int nthr, const FlrParams& p, const FlrTile
     const T* kp = p.skip ? (const T*)p.skip + t.n * p.ys_n + t.c * p.ys_c : nullptr;
     for (int it = tid; it < items; it += nthr) {
         const int ch = it / towp, ox = it - ch * towp;
+        const int gx = t.ox0 + ox;
+        if (ox >= p.tow || gx >= p.yw) continue;         // padded tile column / beyond the plane: nothing to store
         const float* src = s_dh + (ch * G * DOWN) * p.p_dh + ox;
         float w[NW];
 #pragma unroll
         for (int j = 0; j < NW; j++) w[j] = src[j * p.p_dh];
-        const int gx = t.ox0 + ox;
+        const int r0 = ch * G, gy0 = t.oy0 + r0;
+        const int nrow = (p.toh - r0 < p.yh - gy0 ? p.toh - r0 : p.yh - gy0);      // rows of this item that exist
+        const long long o0 = gy0 * p.ys_h + gx * p.ys_w;
 #pragma unroll
         for (int g = 0; g < G; g++) {
             float acc = 0.f;
 #pragma unroll
             for (int k = 0; k < FD; k++) acc += p.kd[k] * w[g * DOWN + k];
-            const int gy = t.oy0 + ch * G + g;
-            if (ox < p.tow && ch * G + g < p.toh && gx < p.yw && gy < p.yh) {
-                const long long o = gy * p.ys_h + gx * p.ys_w;
+            if (g < nrow) {
+                const long long o = o0 + g * p.ys_h;
                 if (kp) acc += (float)kp[o];
                 yp[o] = (T)(acc * p.out_scale);
             }
