@@ -1,0 +1,140 @@
+// tc_ptx.cuh -- PTX wrappers shared by the tcgen05 kernels of this library (conv2d_tc.cu: forward / data gradient,
+// conv2d_wgrad_tc5.cu: weight gradient): mbarrier, TMA tensor loads, tcgen05.mma / commit / ld, shared-memory matrix
+// descriptors, and the host-side tensor-map encoder.
+#pragma once
+#include <cuda.h>
+#include "afcm_common.cuh"
+
+namespace afcm {
+
+constexpr long long TC_WATCHDOG_CYCLES = 4000000000LL; // ~2 s: trap instead of hanging the GPU
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned* dbg = nullptr, unsigned code = 0)
+{
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    long long t0 = 0;
+    for (unsigned spin = 0; !done; spin++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (!done && (spin & 1023) == 1023) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > TC_WATCHDOG_CYCLES) {
+                if (dbg) { dbg[48 + (code >> 8)] = code | 0x80000000u; __threadfence_system(); }
+                __trap();
+            }
+        }
+    }
+}
+__device__ __forceinline__ void dbg_mark(unsigned* dbg, int slot, unsigned v)
+{
+    if (dbg) { dbg[slot] = v; __threadfence_system(); }
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// One lane of a converged warp (elect.sync): the MMA warp runs its loops and barrier waits warp-uniformly and only the
+// issue itself is predicated.  Under a divergent `if (lane == 0)` the compiler keeps every operand in vector registers
+// and pays an ELECT + R2UR sequence of ~17 dependent instructions (~150 clocks) per tcgen05.mma -- measured as the
+// bottleneck of the whole kernel (profiles/r01_ncu_conv2d_tc_issue.txt).
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Same instruction with the two 64-bit descriptors given as (lo, hi) words: the issuing thread advances only the low
+// (address) words between MMAs, which keeps the issue loop to a couple of integer adds per instruction.  With N <= 64
+// an MMA executes in 32 clocks, so a fatter loop makes the single issuing thread the bottleneck.
+__device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, bool accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+// high word of the shared-memory descriptors used here (SBO 1024 B, version 1, SWIZZLE_128B) and the low word
+// (start address | LBO 16 B); see make_desc
+constexpr uint32_t TC_DESC_HI = (uint32_t)((1024u >> 4) & 0x3fff) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3fff) | ((16u >> 4) << 16); }
+
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, leading / stride byte
+// offsets in 16-byte units, version 1 (Blackwell), SWIZZLE_128B layout.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+// Host: cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link dependency).  16-bit elements,
+// SWIZZLE_128B, rank 3..4; strides[] are the byte strides of dimensions 1..rank-1.
+int encode_tiled(CUtensorMap* map, int tc_dtype, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                 const uint32_t* box);
+
+}  // namespace afcm

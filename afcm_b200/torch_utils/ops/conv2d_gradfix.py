@@ -18,6 +18,7 @@ from ... import _lib
 conv_impl = 'f32'
 tc_dtype = torch.float16
 act_dtype = torch.float32
+wgrad_impl = 'tcgen05'               # tensor-core weight gradient: 'tcgen05' (TMEM accumulators) | 'mma' (mma.sync + atomics)
 enabled = False                      # kept for API compatibility with the reference module
 weight_gradients_disabled = False
 
@@ -210,8 +211,15 @@ class _ConvFn(torch.autograd.Function):
         if need_w:
             dw = torch.empty_like(wp)
             if ctx.use_tc:
-                _lib.timed('conv2d_wgrad_tc', 2.0 * N * Co * Ci * 9 * OH * OW, lambda: _lib.check(
-                    L.afcm_conv2d_wgrad_tc(_lib.ptr(dyp), _lib.ptr(xp), _lib.ptr(dw), code, N, Ci, H, W, Co, pad, st)))
+                if wgrad_impl == 'tcgen05':
+                    nbytes = int(L.afcm_conv2d_wgrad_tc_workspace(N, Ci, H, W, Co, pad))
+                    ws = torch.empty([nbytes // 4], dtype=torch.float32, device=dy.device)
+                    _lib.timed('conv2d_wgrad_tc', 2.0 * N * Co * Ci * 9 * OH * OW, lambda: _lib.check(
+                        L.afcm_conv2d_wgrad_tc5(_lib.ptr(dyp), _lib.ptr(xp), _lib.ptr(dw), _lib.ptr(ws), nbytes, code,
+                                                N, Ci, H, W, Co, pad, st)))
+                else:
+                    _lib.timed('conv2d_wgrad_tc', 2.0 * N * Co * Ci * 9 * OH * OW, lambda: _lib.check(
+                        L.afcm_conv2d_wgrad_tc(_lib.ptr(dyp), _lib.ptr(xp), _lib.ptr(dw), code, N, Ci, H, W, Co, pad, st)))
             else:
                 _lib.check(L.afcm_conv2d_wgrad_f32(_lib.ptr(dy), _lib.ptr(x), _lib.ptr(icoef), _lib.ptr(ocoef), _lib.ptr(dw),
                                                    N, Ci, H, W, Co, k, pad, st))

@@ -202,6 +202,14 @@ int afcm_conv2d_wgrad_f32(const float* dy, const float* x, const float* icoef, c
                           int N, int Ci, int H, int W, int Co, int ksize, int pad, void* stream);
 int afcm_conv2d_wgrad_tc(const void* dyp, const void* xp, float* dw, int tc_dtype,
                          int N, int Ci, int H, int W, int Co, int pad, void* stream);
+/* The same weight gradient on tcgen05 / TMEM (afcm_b200/csrc/conv2d_wgrad_tc5.cu): pixels are the reduction dimension,
+ * both operands are TMA-fed MN-major tiles of the packed planes, three accumulators (kx) of 128 x 128 per CTA in tensor
+ * memory, split over pixels with per-split partial sums in `workspace` (device memory, at least
+ * afcm_conv2d_wgrad_tc_workspace() bytes) reduced in a fixed order -- deterministic, unlike the atomics of the mma.sync
+ * variant.  Same arguments otherwise. */
+int64_t afcm_conv2d_wgrad_tc_workspace(int N, int Ci, int H, int W, int Co, int pad);
+int afcm_conv2d_wgrad_tc5(const void* dyp, const void* xp, float* dw, void* workspace, int64_t workspace_bytes,
+                          int tc_dtype, int N, int Ci, int H, int W, int Co, int pad, void* stream);
 
 /* Fused Adam step on flat fp32 buffers (the generator optimiser of the reference training loop, train.py /
  * models/base_model.py: torch.optim.Adam; scrub != 0 applies the reference's gradient scrub

@@ -23,6 +23,7 @@ def _restore_impl():
     from afcm_b200.torch_utils.ops import conv2d_gradfix
     yield
     conv2d_gradfix.set_conv_impl('f32', torch.float16)
+    conv2d_gradfix.wgrad_impl = 'tcgen05'
 
 
 def _modconv_case(g, name, dev):
@@ -93,7 +94,8 @@ def test_conv_grads_vs_torch_fp32(shape):
 @pytest.mark.parametrize('shape', [(2, 16, 24, 12, 14, 2), (3, 70, 130, 38, 38, 2), (2, 64, 64, 36, 36, 1),
                                    (2, 181, 91, 150, 150, 2), (1, 512, 512, 54, 54, 2), (2, 4, 64, 276, 276, 2)])
 @pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float16])
-def test_conv_grads_tc_vs_fp32(shape, dtype):
+@pytest.mark.parametrize('wgrad', ['tcgen05', 'mma'])
+def test_conv_grads_tc_vs_fp32(shape, dtype, wgrad):
     """Tensor-core gradients (tcgen05 data gradient with pad 0/1, mma.sync weight gradient) against the exact path on
     operands that are exactly representable in the 16-bit type (small integers / powers of two): there the only
     difference is the fp32 summation order, so the bound is tight (1e-5)."""
@@ -102,6 +104,7 @@ def test_conv_grads_tc_vs_fp32(shape, dtype):
     dev = torch.device('cuda:0')
     gen = torch.Generator().manual_seed(5)
     conv2d_gradfix.set_conv_impl('tc', dtype)
+    conv2d_gradfix.wgrad_impl = wgrad
 
     def ints(*s, lo=-3, hi=4):
         return torch.randint(lo, hi, s, generator=gen).float()
