@@ -122,14 +122,31 @@ AFCM_HD FlrTile flr_tile(const FlrParams& p, int tile_linear)
 }
 
 // ---- pass 0: global -> s_in, bias added to real pixels only, zeros elsewhere -------------------
+// Flat item index -> (row, column) without a division per item: one division at the start, then the pair advances by
+// the (constant) thread count.
+struct FlrRowCol {
+    int row, col, drow, dcol, pitch;
+    AFCM_HD FlrRowCol(int first, int step, int pitch_) : pitch(pitch_)
+    {
+        row = first / pitch_; col = first - row * pitch_;
+        drow = step / pitch_; dcol = step - drow * pitch_;
+    }
+    AFCM_HD void next()
+    {
+        row += drow; col += dcol;
+        if (col >= pitch) { col -= pitch; row++; }
+    }
+};
+
 template <typename T>
 AFCM_HD void flr_pass_load(int tid, int nthr, const FlrParams& p, const FlrTile& t, float* s_in)
 {
     const T* xp = (const T*)p.x + t.n * p.xs_n + t.c * p.xs_c;
     const float bias = p.b ? (float)((const T*)p.b)[t.c] : 0.f;
     const int n = p.inh * p.p_in;
-    for (int i = tid; i < n; i += nthr) {
-        const int iy = i / p.p_in, ix = i - iy * p.p_in;
+    FlrRowCol rc(tid, nthr, p.p_in);
+    for (int i = tid; i < n; i += nthr, rc.next()) {
+        const int iy = rc.row, ix = rc.col;
         const int gy = t.iby + iy, gx = t.ibx + ix;
         float v = 0.f;
         if (ix < p.inw && gy >= 0 && gy < p.xh && gx >= 0 && gx < p.xw)
@@ -146,11 +163,12 @@ AFCM_HD void flr_pass_sign_load(int tid, int nthr, const FlrParams& p, const Flr
     const int nbp = flr_sign_pitch(p.uwt);
     const int eb0 = flr_floor_div(t.ux0 + p.s_ox, 4);
     const int items = p.uht * nbp;
-    for (int it = tid; it < items; it += nthr) {
-        const int ly = it / nbp, b = it - ly * nbp;
-        const int ey = t.uy0 + ly + p.s_oy, eb = eb0 + b;
+    const uint8_t* base = p.si + (long long)t.plane * p.s_h * p.s_wb;
+    FlrRowCol rc(tid, nthr, nbp);
+    for (int it = tid; it < items; it += nthr, rc.next()) {
+        const int ey = t.uy0 + rc.row + p.s_oy, eb = eb0 + rc.col;
         uint8_t v = 0;
-        if (ey >= 0 && ey < p.s_h && eb >= 0 && eb < p.s_wb) v = p.si[((long long)t.plane * p.s_h + ey) * p.s_wb + eb];
+        if (ey >= 0 && ey < p.s_h && eb >= 0 && eb < p.s_wb) v = base[ey * p.s_wb + eb];
         s_sign[it] = v;
     }
 }
@@ -166,8 +184,9 @@ AFCM_HD void flr_pass_hup(int tid, int nthr, const FlrParams& p, const float* s_
     constexpr int NW = (G + R + 3) / 4 * 4;
     const int nchunk = p.ngx / G;
     const int items = nchunk * p.inh;
-    for (int it = tid; it < items; it += nthr) {
-        const int ch = it / p.inh, iy = it - ch * p.inh;
+    FlrRowCol rc(tid, nthr, p.inh);
+    for (int it = tid; it < items; it += nthr, rc.next()) {
+        const int ch = rc.row, iy = rc.col;
         const float* src = s_in + iy * p.p_in + ch * G;
         float w[NW];
 #pragma unroll
@@ -246,8 +265,9 @@ AFCM_HD void flr_pass_vup(int tid, int nthr, const FlrParams& p, const FlrTile& 
     const int nbp = SIGN == 2 ? flr_sign_pitch(p.uwt) : 0;
     // sign-read mode: element lx of a staged row sits in byte ((se0 + lx) >> 2), bit pair ((se0 + lx) & 3)
     const int se0 = SIGN == 2 ? t.ux0 + p.s_ox - 4 * flr_floor_div(t.ux0 + p.s_ox, 4) : 0;
-    for (int it = tid; it < items; it += nthr) {
-        const int ch = it / ncols, col = it - ch * ncols;
+    FlrRowCol rc(tid, nthr, ncols);
+    for (int it = tid; it < items; it += nthr, rc.next()) {
+        const int ch = rc.row, col = rc.col;
         const int lx = col - t.sxs;
         if (lx < 0 || lx >= p.uwt) continue;            // column outside the region the down passes consume
         const float* src = s_uh + (ch * G) * p.p_uh + col;
@@ -274,22 +294,24 @@ AFCM_HD void flr_pass_sign_flush(int tid, int nthr, const FlrParams& p, const Fl
     const int uwt4 = (p.uwt + 3) & ~3;          // ux0 is a multiple of 4 (tow*DOWN % 4 == 0 enforced by the host)
     const int nb = uwt4 >> 2;
     const int items = p.uht * nb;
-    for (int it = tid; it < items; it += nthr) {
-        const int ly = it / nb, bx = it - ly * nb;
-        const int ey = t.uy0 + ly + p.s_oy;
-        const int eb = ((t.ux0 + p.s_ox) >> 2) + bx;
+    const int eb0 = (t.ux0 + p.s_ox) >> 2;
+    const bool last_col = t.ox0 + p.tow >= p.yw;
+    uint8_t* base = p.so + (long long)t.plane * p.s_h * p.s_wb;
+    FlrRowCol rc(tid, nthr, nb);
+    for (int it = tid; it < items; it += nthr, rc.next()) {
+        const int bx = rc.col;
+        const int ey = t.uy0 + rc.row + p.s_oy, eb = eb0 + bx;
         if (ey < 0 || ey >= p.s_h || eb < 0 || eb >= p.s_wb) continue;
-        // four staged code bytes (values 0..2) as one aligned word; bytes at or beyond uwt were never written
-        uint32_t w = *reinterpret_cast<const uint32_t*>(s_sign + ly * uwt4 + bx * 4);
+        // four staged code bytes (values 0..2) as one aligned word (it * 4 == ly * uwt4 + bx * 4); bytes at or beyond
+        // uwt were never written
+        uint32_t w = *reinterpret_cast<const uint32_t*>(s_sign + it * 4);
         const int nvalid = p.uwt - bx * 4;
         if (nvalid < 4) w &= (1u << (8 * nvalid)) - 1u;
         const int code = (int)((w & 3u) | ((w >> 6) & 0xcu) | ((w >> 12) & 0x30u) | ((w >> 18) & 0xc0u));
-        // elements beyond this tile's uwt belong to the next tile; tiles overlap by FD-DOWN >= 4 samples,
-        // so only whole bytes that this tile fully owns or that are the ragged end of the row are partial.
-        // Partial bytes at a tile's right edge are skipped unless this is the last tile column.
-        const bool full = bx * 4 + 3 < p.uwt;
-        if (full || t.ox0 + p.tow >= p.yw)
-            p.so[((long long)t.plane * p.s_h + ey) * p.s_wb + eb] = (uint8_t)code;
+        // elements beyond this tile's uwt belong to the next tile; tiles overlap by FD-DOWN >= 4 samples, so only whole
+        // bytes that this tile fully owns or that are the ragged end of the row are partial: partial bytes at a tile's
+        // right edge are skipped unless this is the last tile column.
+        if (nvalid >= 4 || last_col) base[ey * p.s_wb + eb] = (uint8_t)code;
     }
 }
 
@@ -300,8 +322,9 @@ AFCM_HD void flr_pass_hdown(int tid, int nthr, const FlrParams& p, const float* 
     constexpr int NW = ((G - 1) * DOWN + FD + 3) / 4 * 4;
     const int nchunk = flr_ceil_div(p.tow, G);
     const int items = nchunk * p.uht;
-    for (int it = tid; it < items; it += nthr) {
-        const int ch = it / p.uht, uy = it - ch * p.uht;
+    FlrRowCol rc(tid, nthr, p.uht);
+    for (int it = tid; it < items; it += nthr, rc.next()) {
+        const int ch = rc.row, uy = rc.col;
         const float* src = s_u + uy * p.p_u + ch * G * DOWN;
         float w[NW];
 #pragma unroll
@@ -336,8 +359,9 @@ AFCM_HD void flr_pass_vdown(int tid, int nthr, const FlrParams& p, const FlrTile
     const int items = nchunk * towp;
     T* yp = (T*)p.y + t.n * p.ys_n + t.c * p.ys_c;
     const T* kp = p.skip ? (const T*)p.skip + t.n * p.ys_n + t.c * p.ys_c : nullptr;
-    for (int it = tid; it < items; it += nthr) {
-        const int ch = it / towp, ox = it - ch * towp;
+    FlrRowCol rc(tid, nthr, towp);
+    for (int it = tid; it < items; it += nthr, rc.next()) {
+        const int ch = rc.row, ox = rc.col;
         const int gx = t.ox0 + ox;
         if (ox >= p.tow || gx >= p.yw) continue;         // padded tile column / beyond the plane: nothing to store
         const float* src = s_dh + (ch * G * DOWN) * p.p_dh + ox;
