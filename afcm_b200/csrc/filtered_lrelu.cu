@@ -19,7 +19,7 @@ flr_fused_kernel(const __grid_constant__ FlrParams p)
     float* buf_b = smem + p.off_b;
     uint8_t* s_sign = reinterpret_cast<uint8_t*>(smem) + p.off_sign;
     const int tid = threadIdx.x;
-    const FlrTile t = flr_tile<UP, DOWN>(p, blockIdx.x);
+    const FlrTile t = flr_tile3<UP, DOWN>(p, blockIdx.x, blockIdx.y, blockIdx.z);     // grid = (planes, tiles_x, tiles_y)
 
     flr_pass_load<T>(tid, FLR_THREADS, p, t, buf_a);
     if (SIGN == 2) flr_pass_sign_load(tid, FLR_THREADS, p, t, s_sign);
@@ -133,14 +133,19 @@ static int launch_fused(FlrParams& p, int sign_mode, cudaStream_t stream)
     TileChoice tc = choose_tile<UP, FU, DOWN, FD>(p, sign_stage);
     if (tc.score < 0) { set_error("filtered_lrelu: no tile fits in shared memory"); return AFCM_ERR_UNSUPPORTED; }
     const size_t smem = flr_make_geom<UP, FU, DOWN, FD, FLR_G>(p, tc.tow, tc.toh, sign_stage);
-    const long long tiles = (long long)p.N * p.C * p.tiles_x * p.tiles_y;
-    if (tiles > 0x7fffffffLL) { set_error("filtered_lrelu: too many tiles"); return AFCM_ERR_INVALID; }
+    const long long planes = (long long)p.N * p.C;
+    if (planes > 0x7fffffffLL || p.tiles_x > 65535 || p.tiles_y > 65535) { set_error("filtered_lrelu: too many tiles"); return AFCM_ERR_INVALID; }
+    // offsets inside one plane are computed in 32 bits by the load / store passes
+    auto labs64 = [](long long v) { return v < 0 ? -v : v; };
+    const long long xspan = (long long)(p.xh + 256) * labs64(p.xs_h) + (long long)(p.xw + 256) * labs64(p.xs_w);   // + tile halo
+    const long long yspan = (long long)p.yh * labs64(p.ys_h) + (long long)p.yw * labs64(p.ys_w);
+    if (xspan > 0x3fffffffLL || yspan > 0x3fffffffLL) { set_error("filtered_lrelu: plane too large for 32-bit offsets"); return AFCM_ERR_UNSUPPORTED; }
     void (*kern)(const FlrParams) = nullptr;
     if (sign_mode == AFCM_SIGN_NONE)  kern = flr_fused_kernel<T, UP, FU, DOWN, FD, FLR_G, 0>;
     if (sign_mode == AFCM_SIGN_WRITE) kern = flr_fused_kernel<T, UP, FU, DOWN, FD, FLR_G, 1>;
     if (sign_mode == AFCM_SIGN_READ)  kern = flr_fused_kernel<T, UP, FU, DOWN, FD, FLR_G, 2>;
     AFCM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)tiles, FLR_THREADS, smem, stream>>>(p);
+    kern<<<dim3((unsigned)planes, (unsigned)p.tiles_x, (unsigned)p.tiles_y), FLR_THREADS, smem, stream>>>(p);
     AFCM_LAUNCH_CHECK();
     count_launch();
     return AFCM_OK;

@@ -104,13 +104,10 @@ struct FlrTile {
 };
 
 template <int UP, int DOWN>
-AFCM_HD FlrTile flr_tile(const FlrParams& p, int tile_linear)
+AFCM_HD FlrTile flr_tile3(const FlrParams& p, int plane, int tx, int ty)
 {
     FlrTile t;
-    const int tx = tile_linear % p.tiles_x;
-    const int r  = tile_linear / p.tiles_x;
-    const int ty = r % p.tiles_y;
-    t.plane = r / p.tiles_y;
+    t.plane = plane;
     t.n = t.plane / p.C; t.c = t.plane - t.n * p.C;
     t.ox0 = tx * p.tow; t.oy0 = ty * p.toh;
     t.ux0 = t.ox0 * DOWN; t.uy0 = t.oy0 * DOWN;
@@ -119,6 +116,14 @@ AFCM_HD FlrTile flr_tile(const FlrParams& p, int tile_linear)
     t.ibx = flr_floor_div(t.ux0 - t.sxs - p.px0, UP);
     t.iby = flr_floor_div(t.uy0 - t.sys - p.py0, UP);
     return t;
+}
+
+template <int UP, int DOWN>
+AFCM_HD FlrTile flr_tile(const FlrParams& p, int tile_linear)
+{
+    const int tx = tile_linear % p.tiles_x;
+    const int r  = tile_linear / p.tiles_x;
+    return flr_tile3<UP, DOWN>(p, r / p.tiles_y, tx, r % p.tiles_y);
 }
 
 // ---- pass 0: global -> s_in, bias added to real pixels only, zeros elsewhere -------------------
@@ -145,13 +150,24 @@ AFCM_HD void flr_pass_load(int tid, int nthr, const FlrParams& p, const FlrTile&
     const float bias = p.b ? (float)((const T*)p.b)[t.c] : 0.f;
     const int n = p.inh * p.p_in;
     FlrRowCol rc(tid, nthr, p.p_in);
-    for (int i = tid; i < n; i += nthr, rc.next()) {
-        const int iy = rc.row, ix = rc.col;
-        const int gy = t.iby + iy, gx = t.ibx + ix;
-        float v = 0.f;
-        if (ix < p.inw && gy >= 0 && gy < p.xh && gx >= 0 && gx < p.xw)
-            v = (float)xp[gy * p.xs_h + gx * p.xs_w] + bias;
-        s_in[i] = v;
+    const T* x0 = xp + t.iby * p.xs_h + t.ibx * p.xs_w;          // element (0,0) of the tile (may lie outside the plane)
+    const int sh = (int)p.xs_h, sw = (int)p.xs_w;                // offsets inside a plane fit 32 bits (checked by the host)
+    if (t.iby >= 0 && t.iby + p.inh <= p.xh && t.ibx >= 0 && t.ibx + p.inw <= p.xw) {
+        // interior tile: every input sample exists, only the pitch padding columns are zero
+        for (int i = tid; i < n; i += nthr, rc.next()) {
+            float v = 0.f;
+            if (rc.col < p.inw) v = (float)x0[rc.row * sh + rc.col * sw] + bias;
+            s_in[i] = v;
+        }
+    } else {
+        for (int i = tid; i < n; i += nthr, rc.next()) {
+            const int iy = rc.row, ix = rc.col;
+            const int gy = t.iby + iy, gx = t.ibx + ix;
+            float v = 0.f;
+            if (ix < p.inw && gy >= 0 && gy < p.xh && gx >= 0 && gx < p.xw)
+                v = (float)x0[iy * sh + ix * sw] + bias;
+            s_in[i] = v;
+        }
     }
 }
 
@@ -370,14 +386,15 @@ AFCM_HD void flr_pass_vdown(int tid, int nthr, const FlrParams& p, const FlrTile
         for (int j = 0; j < NW; j++) w[j] = src[j * p.p_dh];
         const int r0 = ch * G, gy0 = t.oy0 + r0;
         const int nrow = (p.toh - r0 < p.yh - gy0 ? p.toh - r0 : p.yh - gy0);      // rows of this item that exist
-        const long long o0 = gy0 * p.ys_h + gx * p.ys_w;
+        const int ysh = (int)p.ys_h;
+        const int o0 = gy0 * ysh + gx * (int)p.ys_w;
 #pragma unroll
         for (int g = 0; g < G; g++) {
             float acc = 0.f;
 #pragma unroll
             for (int k = 0; k < FD; k++) acc += p.kd[k] * w[g * DOWN + k];
             if (g < nrow) {
-                const long long o = o0 + g * p.ys_h;
+                const int o = o0 + g * ysh;
                 if (kp) acc += (float)kp[o];
                 yp[o] = (T)(acc * p.out_scale);
             }
