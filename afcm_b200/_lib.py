@@ -51,6 +51,7 @@ SIGNATURES = {
     'afcm_conv_tc_pack': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'afcm_conv2d_tc': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'afcm_plane_dot_scale': (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
+    'afcm_plane_sum': (_i, [_vp, _vp, _i64, _i64, _vp]),
     'afcm_conv2d_wgrad_f32': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'afcm_conv2d_wgrad_tc': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'afcm_conv2d_wgrad_tc_workspace': (_i64, [_i, _i, _i, _i, _i, _i]),

@@ -55,6 +55,18 @@ plane_dot_scale_kernel(float* __restrict__ a, const float* __restrict__ b, const
     }
 }
 
+// out[p] = sum_j a[p,j]  (the per-plane part of the bias gradient db = sum_{n,h,w} dx of filtered_lrelu / bias_act)
+__global__ void __launch_bounds__(256)
+plane_sum_kernel(const float* __restrict__ a, float* __restrict__ out, long long hw)
+{
+    __shared__ float red[8];
+    const float* ap = a + (long long)blockIdx.x * hw;
+    float s = 0.f;
+    for (long long j = threadIdx.x; j < hw; j += 256) s += ap[j];
+    const float t = block_sum_256(s, red);
+    if (threadIdx.x == 0) out[blockIdx.x] = t;
+}
+
 // ---- exact fp32 weight gradient ------------------------------------------------------------------------
 constexpr int WG_TO = 16, WG_TI = 16, WG_KB = 32;
 
@@ -311,6 +323,16 @@ extern "C" int afcm_plane_dot_scale(float* a, const float* b, const float* div, 
     AFCM_CHECK_ARG(planes <= 0x7fffffffLL, "too many planes");
     if (!out && !coef) return AFCM_OK;
     plane_dot_scale_kernel<<<(unsigned)planes, 256, 0, (cudaStream_t)stream>>>(a, b, div, coef, out, (long long)hw);
+    AFCM_LAUNCH_CHECK();
+    count_launch();
+    return AFCM_OK;
+}
+
+extern "C" int afcm_plane_sum(const float* a, float* out, int64_t planes, int64_t hw, void* stream)
+{
+    AFCM_CHECK_ARG(a && out && planes > 0 && hw > 0, "empty problem");
+    AFCM_CHECK_ARG(planes <= 0x7fffffffLL, "too many planes");
+    plane_sum_kernel<<<(unsigned)planes, 256, 0, (cudaStream_t)stream>>>(a, out, (long long)hw);
     AFCM_LAUNCH_CHECK();
     count_launch();
     return AFCM_OK;

@@ -157,6 +157,16 @@ def _act_(y, si, sx, sy, gain, slope, clamp, write_signs):
     return so
 
 
+def _channel_sum(dx):
+    """db = dx.sum([0, 2, 3]) (reference filtered_lrelu.py:264-265): native per-plane sums, then the tiny sum over N."""
+    if dx.dtype != torch.float32 or not dx.is_contiguous() or dx.numel() == 0:
+        return dx.sum([0, 2, 3])
+    N, C, H, W = dx.shape
+    part = torch.empty([N, C], dtype=torch.float32, device=dx.device)
+    _lib.check(_lib.lib().afcm_plane_sum(_lib.ptr(dx), _lib.ptr(part), N * C, H * W, _lib.stream_ptr(dx.device)))
+    return part.sum(0)
+
+
 _filtered_lrelu_cuda_cache = dict()
 
 
@@ -224,7 +234,7 @@ def _filtered_lrelu_cuda(up=1, down=1, padding=0, gain=np.sqrt(2), slope=0.2, cl
                 dx = _filtered_lrelu_cuda(up=down, down=up, padding=pp, gain=gg, slope=slope, clamp=None,
                                           flip_filter=ff).apply(dy, fd, fu, None, si, sx, sy)
             if ctx.needs_input_grad[3] and ctx.has_b:
-                db = dx.sum([0, 2, 3])
+                db = _channel_sum(dx)
             return dx, None, None, db, None, None, None
 
     _filtered_lrelu_cuda_cache[key] = FilteredLReluCuda

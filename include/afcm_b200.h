@@ -198,6 +198,9 @@ void* afcm_conv_tc_debug_buffer(int enable);
  */
 int afcm_plane_dot_scale(float* a, const float* b, const float* div, const float* coef, float* out,
                          int64_t planes, int64_t hw, void* stream);
+/* out[p] = sum over the plane a[p,:] (fp32, dense [planes, hw]): the per-plane part of the bias gradient
+ * db = dx.sum([0,2,3]) of filtered_lrelu (OPS/filtered_lrelu.py:264-265) and bias_act (OPS/bias_act.py:169-170). */
+int afcm_plane_sum(const float* a, float* out, int64_t planes, int64_t hw, void* stream);
 int afcm_conv2d_wgrad_f32(const float* dy, const float* x, const float* icoef, const float* ocoef, float* dw,
                           int N, int Ci, int H, int W, int Co, int ksize, int pad, void* stream);
 int afcm_conv2d_wgrad_tc(const void* dyp, const void* xp, float* dw, int tc_dtype,
