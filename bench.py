@@ -142,6 +142,23 @@ def cpu_reference_slices_per_sec(steps, warmup, seed=0):
     return 1.0 / dt, dt * 1e3, cores, f'{steps} timed + {warmup} warm-up forwards of 1 slice (batch 1) of the same workload'
 
 
+def cpu_reference_train_slices_per_sec(seed=0):
+    """The oracle's torch-CPU restatement differentiated by torch autograd: one forward + backward of the L1 training loss
+    on ONE slice, all host threads (bounded sample of the training workload)."""
+    import torch
+    from oracle import afcm_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    P = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and not k.endswith(('_filter', 'magnitude_ema', 'w_avg')) else v)
+         for k, v in orc.init_params(seed=0).items()}
+    z, c, x = synthetic_inputs(1, seed)
+    tgt = torch.rand(1, 1, 256, 256, generator=torch.Generator().manual_seed(100)) * 2 - 1
+    t0 = time.perf_counter()
+    (orc.generator_forward(P, z, c, x, grad=True) - tgt).abs().mean().backward()
+    dt = time.perf_counter() - t0
+    return 1.0 / dt, cores, '1 forward + backward of 1 slice (batch 1) of the same workload, no warm-up'
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -428,6 +445,9 @@ def run_train(args, rank, world):
                 e2e=dict(value=slices / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=int(hz.nbytes + hc.nbytes + hx.nbytes + ht.nbytes),
                          d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps),
                 roofline=max([r for r in rf.values() if r], key=lambda r: r['ms_per_step'], default=None), rooflines=rf)
+    if world == 1 and not args.no_cpu_baseline:
+        sps, cores, sample = cpu_reference_train_slices_per_sec()
+        line['cpu_baseline'] = dict(value=sps, unit=UNIT, cores=cores, kind='port', sample=sample)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
