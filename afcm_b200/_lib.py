@@ -34,6 +34,8 @@ SIGNATURES = {
                                  _i, _i, _i, _i, _i, _i,                       # up down px0 px1 py0 py1
                                  _f, _f, _f, _f, _i,                           # gain slope clamp out_scale flip
                                  _i, _vp, _i, _i, _i, _i, _vp]),               # sign_mode signs sh swb sx sy stream
+    'afcm_filtered_lrelu_tcs': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i,
+                                     _i, _i, _i, _i, _i, _i, _f, _f, _f, _f, _i, _i, _vp, _i, _i, _i, _i, _vp]),
     'afcm_filtered_lrelu_tc': (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp,           # x xs xdt y ys ydt b skip
                                     _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i,        # N C xh xw yh yw fu n fd n
                                     _i, _i, _i, _i, _i, _i, _f, _f, _f, _f, _i, _vp]),  # up down pads gain slope clamp scale flip stream

@@ -9,6 +9,18 @@ from ... import _lib
 from . import upfirdn2d as _upfirdn2d
 
 
+# Implementation of the autograd (training) path: 'exact' = the fp32 kernel (afcm_filtered_lrelu, the parity path),
+# 'tc' = the tensor-core kernel with the same sign tensor (afcm_filtered_lrelu_tcs: fp16 operands in the forward,
+# bf16 in the backward, fp32 accumulation and activation).  Inference without a graph is not affected.
+train_impl = 'exact'
+
+
+def set_train_impl(impl):
+    global train_impl
+    assert impl in ('exact', 'tc')
+    train_impl = impl
+
+
 def _get_filter_size(f):
     if f is None:
         return 1, 1
@@ -86,6 +98,18 @@ def _run_fused(x, fu, fd, b, si, up, down, px0, px1, py0, py1, sx, sy, gain, slo
         skip = skip.contiguous()
     # algorithmic bytes: x read once + y written once (+ the skip read when fused)
     nbytes = x.element_size() * (x.numel() + y.numel() * (2 if skip is not None else 1))
+    use_tc = (train_impl == 'tc' and mode != _lib.SIGN_NONE and x.dtype == torch.float32 and fu_h is not None and
+              fd_h is not None and (up, down) in ((2, 2), (2, 4), (4, 2)) and fu_n == 6 * up and fd_n == 6 * down)
+    if use_tc:
+        # forward (sign write): fp16 operands; backward (sign read): bf16 operands keep the gradients' exponent range
+        op = _lib.F16 if mode == _lib.SIGN_WRITE else _lib.BF16
+        rc = _lib.timed('filtered_lrelu', nbytes, lambda: L.afcm_filtered_lrelu_tcs(
+            _lib.ptr(x), _lib.i64x4(x.stride()), _lib.ptr(y), _lib.i64x4(y.stride()), _lib.ptr(b), _lib.ptr(skip), op,
+            N, C, xh, xw, yh, yw, _lib.np_ptr(fu_h), fu_n, _lib.np_ptr(fd_h), fd_n, up, down, px0, px1, py0, py1,
+            gain, slope, clamp, out_scale, int(bool(flip_filter)), mode, _lib.ptr(s), sh, swb, int(sx), int(sy),
+            _lib.stream_ptr(x.device)))
+        _lib.check(rc)
+        return y, so, 0
     rc = _lib.timed('filtered_lrelu', nbytes, lambda: L.afcm_filtered_lrelu(
         _lib.ptr(x), _lib.i64x4(x.stride()), _lib.ptr(y), _lib.i64x4(y.stride()), _lib.ptr(b), _lib.ptr(skip),
         _lib.dtype_code(x.dtype), N, C, xh, xw, yh, yw,

@@ -357,10 +357,12 @@ def run_train(args, rank, world):
         torch.cuda.synchronize()
 
     B = args.batch if args.batch != 64 else 32                       # config 5: batch 32 per GPU
+    from afcm_b200.torch_utils.ops import filtered_lrelu as flr_op
     if args.precision == 'fp32':
         conv2d_gradfix.set_conv_impl('f32')
     else:
         conv2d_gradfix.set_conv_impl('tc', torch.bfloat16)           # bf16 operands (gradient range), fp32 accumulation/storage
+        flr_op.set_train_impl('exact' if args.precision == 'tc' else 'tc')   # 'fast': tensor-core filtered_lrelu with sign tensor
     G = afcm_generator(seed=0, device=dev).train()
     tr = GeneratorTrainer(G, lr=0.0025, betas=(0.0, 0.99))
     z, c, x = synthetic_inputs(B, seed=rank, as_uint8=True)
@@ -432,7 +434,7 @@ def run_train(args, rank, world):
     line = dict(metric='generator_train_slices_per_sec_256x256', value=slices / (ms_total * 1e-3), unit=UNIT, n_gpus=world,
                 steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_total / args.steps, higher_is_better=True,
                 scaling='weak', vs_baseline=None,
-                dtype='bf16 conv operands / f32 accumulate, f32 storage and filtered_lrelu' if args.precision != 'fp32' else 'f32',
+                dtype={'fast': 'bf16 conv operands, fp16/bf16 filtered_lrelu operands / f32 accumulate, f32 storage', 'tc': 'bf16 conv operands / f32 accumulate, f32 storage and filtered_lrelu', 'fp32': 'f32'}[args.precision],
                 data='synthetic',
                 config=dict(workload='AFCM generator training step (forward + backward + gradient all-reduce + Adam), synthetic '
                                      '256x256 slices, batch 32 per GPU', batch_per_gpu=B, global_batch=B * world, resolution=256,

@@ -98,6 +98,21 @@ int afcm_filtered_lrelu_tc(const void* x, const int64_t* xs, int x_dtype, void* 
                            float gain, float slope, float clamp, float out_scale, int flip_filter,
                            void* stream);
 
+/* Tensor-core filtered_lrelu WITH the sign tensor (afcm_b200/csrc/flr_tcs.cu): the training-step variant.  Same
+ * arguments, sign-tensor format and sign_mode meaning as afcm_filtered_lrelu, so forward (SIGN_WRITE) and backward
+ * (SIGN_READ, up/down exchanged by the caller as in OPS/filtered_lrelu.py:252-266) interoperate with the exact kernel.
+ * x, y, b, skip are float32; `op_dtype` (AFCM_F16 / AFCM_BF16) is the operand type of the four banded-Toeplitz
+ * m16n8k16 products (fp32 accumulation, fp32 activation).  Geometries: (up,down) in {(2,2),(2,4),(4,2)} with 6*up /
+ * 6*down taps, else AFCM_ERR_UNSUPPORTED.  Tolerance: 2e-3 of max|y| with F16 operands (tests/test_gpu_flr_tcs.py). */
+int afcm_filtered_lrelu_tcs(const void* x, const int64_t* xs, void* y, const int64_t* ys,
+                            const void* b, const void* skip, int op_dtype,
+                            int N, int C, int xh, int xw, int yh, int yw,
+                            const float* fu_host, int fu_taps, const float* fd_host, int fd_taps,
+                            int up, int down, int px0, int px1, int py0, int py1,
+                            float gain, float slope, float clamp, float out_scale, int flip_filter,
+                            int sign_mode, void* signs, int sign_h, int sign_wb, int sx, int sy,
+                            void* stream);
+
 /* filtered_lrelu_act_ -- replaces filtered_lrelu_plugin.filtered_lrelu_act_ (OPS/filtered_lrelu.cpp:213-290):
  * in-place gain / lrelu / clamp with optional sign write or read on a dense [planes,h,w] tensor.     */
 int afcm_filtered_lrelu_act(void* x, int dtype, int64_t planes, int h, int w,

@@ -8,6 +8,7 @@ from afcm_b200.networks_stylegan3 import design_lowpass_filter
 from afcm_b200.torch_utils.ops import filtered_lrelu
 
 dev = torch.device('cuda:0')
+if len(sys.argv) > 1: filtered_lrelu.set_train_impl(sys.argv[1])
 fu = design_lowpass_filter(12, 64.0, 30.0, 512).to(dev)
 fd = design_lowpass_filter(12, 64.0, 30.0, 512).to(dev)
 x = torch.randn(8, 64, 278, 278, device=dev, requires_grad=True)
