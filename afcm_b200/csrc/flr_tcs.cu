@@ -110,61 +110,37 @@ flr_tcs_kernel(const __grid_constant__ FlrParams p)
     const int c0x = U * ibx + p.px0 - t.ux0, c0y = U * iby + p.py0 - t.uy0;
 
     // ---- pass 0: global -> X (bias on real samples only, zero outside the plane), sign staging (backward) ----
-    // rows go to warps, columns to lanes, RB rows per batch so that RB * ceil(P_X/32) loads are in flight per thread
+    // Items are column PAIRS of a 64-column grid (power-of-two decode, one packed store per pair); columns >= P_X idle.
     {
+        static_assert(G::P_X <= 64 && G::P_X % 2 == 0, "load pass assumes at most 64 columns");
         const float* xp = (const float*)p.x + t.n * p.xs_n + t.c * p.xs_c;
         const float bias = p.b ? ((const float*)p.b)[t.c] : 0.f;
         const int sh = (int)p.xs_h, sw = (int)p.xs_w;
-        constexpr int NW = TS_THREADS / 32, RB = 3, CB = (G::P_X + 31) / 32;
-        for (int r0 = warp; r0 < G::IHP; r0 += NW * RB) {
-            float v[RB][CB];
+        const float* x0 = xp + iby * sh + ibx * sw;                 // sample (0,0) of the tile (may lie outside the plane)
+        constexpr int NIT = (G::IHP * 32 + TS_THREADS - 1) / TS_THREADS;
 #pragma unroll
-            for (int r = 0; r < RB; r++) {
-                const int iy = r0 + r * NW, gy = iby + iy;
-                const bool rok = iy < G::IH && (unsigned)gy < (unsigned)p.xh;
-                const float* src = xp + gy * sh + ibx * sw;
-#pragma unroll
-                for (int c = 0; c < CB; c++) {
-                    const int ix = lane + 32 * c;
-                    v[r][c] = (rok && ix < G::IW && (unsigned)(ibx + ix) < (unsigned)p.xw) ? src[ix * sw] + bias : 0.f;
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < RB; r++) {
-                const int iy = r0 + r * NW;
-#pragma unroll
-                for (int c = 0; c < CB; c++) {
-                    const int ix = lane + 32 * c;
-                    if (iy < G::IHP && ix < G::P_X) bufA[iy * G::P_X + ix] = Op::cvt(v[r][c]);
-                }
-            }
+        for (int it = 0; it < NIT; it++) {
+            const int i = tid + it * TS_THREADS;
+            const int iy = i >> 5, ix = (i & 31) * 2;
+            const bool rok = iy < G::IH && (unsigned)(iby + iy) < (unsigned)p.xh;
+            const float* src = x0 + iy * sh + ix * sw;
+            float v0 = 0.f, v1 = 0.f;
+            if (rok && ix < G::IW && (unsigned)(ibx + ix) < (unsigned)p.xw) v0 = src[0] + bias;
+            if (rok && ix + 1 < G::IW && (unsigned)(ibx + ix + 1) < (unsigned)p.xw) v1 = src[sw] + bias;
+            if (iy < G::IHP && ix < G::P_X) *reinterpret_cast<uint32_t*>(bufA + iy * G::P_X + ix) = Op::pack(v0, v1);
         }
         if (SIGN == 2) {
-            // the tile's part of the packed sign tensor: staged byte (ly, b) = sign byte (uy0 + ly + s_oy, eb0 + b)
-            const int nbp = flr_sign_pitch(p.uwt);              // <= 48 bytes per row
-            const int eb0 = flr_floor_div(t.ux0 + p.s_ox, 4);
+            // the tile's part of the packed sign tensor as aligned 32-bit words: staged row = 8 words = 32 bytes starting at
+            // the sign byte eb0a (a multiple of 4) of sign row uy0 + ly + s_oy; words outside the tensor read as 0 = "leave
+            // the value alone" (the tensor's row pitch s_wb is a multiple of 4, so a word is inside or outside as a whole)
+            const int eb0a = flr_floor_div(t.ux0 + p.s_ox, 16) * 4;
             const uint8_t* base = p.si + (long long)t.plane * p.s_h * p.s_wb;
-            for (int ly0 = warp; ly0 < p.uht; ly0 += NW * 4) {
-                uint8_t sv[4][2];
-#pragma unroll
-                for (int r = 0; r < 4; r++) {
-                    const int ly = ly0 + r * NW, ey = t.uy0 + ly + p.s_oy;
-                    const bool rok = ly < p.uht && (unsigned)ey < (unsigned)p.s_h;
-#pragma unroll
-                    for (int c = 0; c < 2; c++) {
-                        const int bb = lane + 32 * c, eb = eb0 + bb;
-                        sv[r][c] = (rok && bb < nbp && (unsigned)eb < (unsigned)p.s_wb) ? base[ey * p.s_wb + eb] : (uint8_t)0;
-                    }
-                }
-#pragma unroll
-                for (int r = 0; r < 4; r++) {
-                    const int ly = ly0 + r * NW;
-#pragma unroll
-                    for (int c = 0; c < 2; c++) {
-                        const int bb = lane + 32 * c;
-                        if (ly < p.uht && bb < nbp) s_sign[ly * nbp + bb] = sv[r][c];
-                    }
-                }
+            uint32_t* sw32 = reinterpret_cast<uint32_t*>(s_sign);
+            for (int i = tid; i < p.uht * 8; i += TS_THREADS) {
+                const int ly = i >> 3, ey = t.uy0 + ly + p.s_oy, eb = eb0a + (i & 7) * 4;
+                uint32_t v = 0;
+                if ((unsigned)ey < (unsigned)p.s_h && (unsigned)eb < (unsigned)p.s_wb) v = *reinterpret_cast<const uint32_t*>(base + ey * p.s_wb + eb);
+                sw32[i] = v;
             }
         }
     }
@@ -208,12 +184,12 @@ flr_tcs_kernel(const __grid_constant__ FlrParams p)
             const int m = g + (r & 1) * 8, k = 2 * t4 + (r >> 1) * 8;
             av[r] = Op::pack(ts_tap(s_ku, G::FU, c0y + U * k - m) * p.gain, ts_tap(s_ku, G::FU, c0y + U * (k + 1) - m) * p.gain);
         }
-        const int nbp = SIGN == 2 ? flr_sign_pitch(p.uwt) : 0;
-        const int se0 = SIGN == 2 ? t.ux0 + p.s_ox - 4 * flr_floor_div(t.ux0 + p.s_ox, 4) : 0;
+        constexpr int nbp = 32;                                     // staged sign bytes per row (backward)
+        const int se0 = SIGN == 2 ? t.ux0 + p.s_ox - 16 * flr_floor_div(t.ux0 + p.s_ox, 16) : 0;   // 0..15
         // forward: extent of the codes this tile owns, and the sign-tensor origin of the tile
         const int own_w = (t.ox0 + G::TW >= p.yw) ? p.uwt : G::TW * D, own_h = (t.oy0 + G::TH >= p.yh) ? p.uht : G::TH * D;
         uint8_t* so = SIGN == 1 ? p.so + ((long long)t.plane * p.s_h + t.uy0) * p.s_wb + (t.ux0 >> 2) : nullptr;
-        const int s_rows = p.s_h - t.uy0, s_bytes = p.s_wb - (t.ux0 >> 2);
+        const int s_bytes = p.s_wb - (t.ux0 >> 2), row_lim = min(own_h, p.s_h - t.uy0);
         const float nclamp = -p.clamp;
         constexpr int NB2 = G::UWC / 16, NJ = G::MTV * NB2;
         for (int job = warp; job < NJ; job += TS_THREADS / 32) {
@@ -225,6 +201,7 @@ flr_tcs_kernel(const __grid_constant__ FlrParams p)
                 float d[4] = {0.f, 0.f, 0.f, 0.f};
                 Op::mma(d, av, b[2 * h], b[2 * h + 1]);
                 const int lx = 16 * nb + 8 * h + 2 * t4;
+                const bool col_st = SIGN == 1 && !(t4 & 1) && lx < own_w && (lx >> 2) < s_bytes;   // this lane stores the byte
 #pragma unroll
                 for (int rr = 0; rr < 2; rr++) {
                     const int ly = 16 * mt + g + 8 * rr;
@@ -249,8 +226,7 @@ flr_tcs_kernel(const __grid_constant__ FlrParams p)
                             const int c0 = (w0 != v0) ? 2 : (int)n0, c1 = (w1 != v1) ? 2 : (int)n1;
                             int c = c0 | (c1 << 2);
                             c |= __shfl_xor_sync(0xffffffffu, c, 1) << 4;
-                            const int bx = lx >> 2;
-                            if (!(t4 & 1) && ly < own_h && lx < own_w && ly < s_rows && bx < s_bytes) so[ly * p.s_wb + bx] = (uint8_t)c;
+                            if (col_st && ly < row_lim) so[ly * p.s_wb + (lx >> 2)] = (uint8_t)c;
                         }
                         v0 = w0; v1 = w1;
                     }
@@ -344,7 +320,7 @@ static int launch_tcs(FlrParams& p, int op_dtype, int sign_mode, cudaStream_t st
     const long long yspan = (long long)p.yh * labs64(p.ys_h) + (long long)p.yw * labs64(p.ys_w);
     if (xspan > 0x3fffffffLL || yspan > 0x3fffffffLL) { set_error("filtered_lrelu_tcs: plane too large for 32-bit offsets"); return AFCM_ERR_UNSUPPORTED; }
     size_t smem = (size_t)(G::A_ELEMS + G::B_ELEMS) * 2;
-    if (sign_mode == AFCM_SIGN_READ) smem += (size_t)p.uht * (size_t)flr_sign_pitch(p.uwt);
+    if (sign_mode == AFCM_SIGN_READ) smem += (size_t)p.uht * 32;
     smem = (smem + 15) & ~(size_t)15;
     void (*kern)(const FlrParams) = nullptr;
     const bool bf = op_dtype == AFCM_BF16;

@@ -99,7 +99,8 @@ def _run_fused(x, fu, fd, b, si, up, down, px0, px1, py0, py1, sx, sy, gain, slo
     # algorithmic bytes: x read once + y written once (+ the skip read when fused)
     nbytes = x.element_size() * (x.numel() + y.numel() * (2 if skip is not None else 1))
     use_tc = (train_impl == 'tc' and mode != _lib.SIGN_NONE and x.dtype == torch.float32 and fu_h is not None and
-              fd_h is not None and (up, down) in ((2, 2), (2, 4), (4, 2)) and fu_n == 6 * up and fd_n == 6 * down)
+              fd_h is not None and (up, down) in ((2, 2), (2, 4), (4, 2)) and fu_n == 6 * up and fd_n == 6 * down and
+              min(yh, yw) >= 48)      # its 32x32 / 16x16 tiles waste most of a small plane: the exact kernel is faster there
     if use_tc:
         # forward (sign write): fp16 operands; backward (sign read): bf16 operands keep the gradients' exponent range
         op = _lib.F16 if mode == _lib.SIGN_WRITE else _lib.BF16
