@@ -26,6 +26,9 @@ KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__warp_issue_stalled_wait_per_warp_active.pct', 'smsp__warp_issue_stalled_not_selected_per_warp_active.pct',
         'smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct']
 
+EXTRA = re.compile(r'issue_stalled.*(ratio|pct)$|smsp__issue_active\.avg\.pct|smsp__inst_executed\.sum$|sm__inst_executed_pipe_[a-z0-9_]+\.sum$|'
+                   r'smsp__warps_eligible\.avg\.per_cycle_active|smsp__thread_inst_executed_per_inst_executed')
+
 
 def short(name):
     name = re.sub(r'\(.*', '', name)
@@ -84,6 +87,10 @@ def rep(src, dst):
             f.write(f'\n== {short(d["Kernel Name"])}  grid {d.get("Grid Size")} block {d.get("Block Size")}\n')
             for k in KEYS:
                 if k in d:
+                    f.write(f'  {k:80s} {d[k]:>18s} {units[hdr.index(k)]}\n')
+            # warp-state breakdown (why the issue slots idle) and per-pipe instruction counts, whatever this ncu calls them
+            for k in hdr:
+                if k not in KEYS and EXTRA.search(k) and d.get(k) not in (None, '', 'n/a'):
                     f.write(f'  {k:80s} {d[k]:>18s} {units[hdr.index(k)]}\n')
     print(open(dst).read())
 
