@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libafcm_b200.so')
+# AFCM_B200_LIB: another build of the same library (A/B timing of kernel variants with tools/layer_bench.py)
+LIB_PATH = os.environ.get('AFCM_B200_LIB') or os.path.join(_HERE, 'libafcm_b200.so')
 
 OK, ERR_UNSUPPORTED, ERR_INVALID = 0, -1, -2
 F32, F16, BF16 = 0, 1, 2
@@ -42,6 +43,7 @@ SIGNATURES = {
     'afcm_filtered_lrelu_out_size': (_i, [_i] * 10 + [_pi, _pi]),
     'afcm_filtered_lrelu_sign_size': (_i, [_i] * 4 + [_pi, _pi]),
     'afcm_filtered_lrelu_set_tile': (_i, [_i, _i]),
+    'afcm_filtered_lrelu_tc_set_waves': (_i, [_i]),
     'afcm_filtered_lrelu_act': (_i, [_vp, _i, _i64, _i, _i, _f, _f, _f, _i, _vp, _i, _i, _i, _i, _vp]),
     'afcm_upfirdn2d': (_i, [_vp, _vp, _i, _i64, _i, _i, _i, _i, _vp, _i, _i,
                             _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
@@ -82,6 +84,8 @@ def lib():
                                f'(run `python -m afcm_b200.build`). There is no CPU fallback.')
         L = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
+            if not hasattr(L, name) and 'AFCM_B200_LIB' in os.environ:
+                continue                                   # an older build lacks the newest tuning switches
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args

@@ -473,6 +473,8 @@ struct FtcWarp {
         }
         if (ADV) { yq += ADV * 8 * p.ys_h; eb += ADV; }
     }
+    // an emit whose blocks all lie outside the segment: only the output cursor moves
+    template <int ADV> __device__ __forceinline__ void skip_emit() { yq += ADV * 8 * p.ys_h; eb += ADV; }
     static __device__ __forceinline__ void store_pair(float* q, float a, float b) { *reinterpret_cast<float2*>(q) = make_float2(a, b); }
     static __device__ __forceinline__ void store_pair(__half* q, float a, float b) { *reinterpret_cast<__half2*>(q) = __floats2half2_rn(a, b); }
 
@@ -484,15 +486,24 @@ struct FtcWarp {
     __device__ __forceinline__ void super22(int s, uint32_t (&X0)[JB], uint32_t (&X1)[JB])
     {
         uint32_t in[Geo::NC], win[JB][2];
+        // Pipeline fill / drain (EDGE supers only; the interior supers emit both blocks by construction):
+        //  * s == 0 produces blocks -2 and -1, which do not exist.  The first chunk only reaches block -1 (through the
+        //    carry), so it is skipped together with the emit; the second chunk stays (its carry is part of block 0).
+        //  * a last super whose second block lies beyond the segment (odd number of row blocks) stops after the first.
         convert<EDGE>(2 * s, in); step1<0>(in); fetch<EDGE>();
-        chunk<0, 0, 0>(0, win, X0);                                     // block 2s-2
-        convert<EDGE>(2 * s + 1, in); step1<1>(in); fetch<EDGE>();
-        chunk<1, 0, 0>(0, win, X1);                                     // block 2s-1
-        emit<EDGE, 2>(X0, X1, 3);                                       // EDGE: blocks < 0 are masked by the row test
+        if (!EDGE || s > 0) chunk<0, 0, 0>(0, win, X0);                 // block 2s-2
+        if (!EDGE || eb + 1 < nwb) {
+            convert<EDGE>(2 * s + 1, in); step1<1>(in); fetch<EDGE>();
+            chunk<1, 0, 0>(0, win, X1);                                 // block 2s-1
+        }
+        if (!EDGE || s > 0) emit<EDGE, 2>(X0, X1, 3);                   // EDGE: rows outside the segment are masked
+        else skip_emit<2>();
     }
     __device__ void run22()
     {
         uint32_t X0[JB], X1[JB];
+#pragma unroll
+        for (int jb = 0; jb < JB; jb++) X0[jb] = X1[jb] = 0u;
         const int S = ((nwb - 1) >> 1) + 2;
         int lo = 0, hi = 0;
         if (interior) {
@@ -515,10 +526,18 @@ struct FtcWarp {
     __device__ __forceinline__ void iter42(int it, uint32_t (&X0)[JB])
     {
         uint32_t in[Geo::NC], win[JB][2], X1[JB];
+        // eb == 2it-4.  Pipeline fill / drain (EDGE iterations only): a chunk is needed if its block or the block its
+        // carry reaches exists, the emit if one block of its pair exists; an iteration past the segment does nothing.
+        if (EDGE && eb >= nwb) { skip_emit<2>(); return; }
         convert<EDGE>(it, in); step1<CUR>(in); fetch<EDGE>();
-        chunk<CUR, 0, 0>(0, win, X1);                                   // block 2it-3
-        emit<EDGE, 2>(X0, X1, 3);                                       // pair (2it-4, 2it-3)
-        chunk<CUR, 2, 0>(0, win, X0);                                   // block 2it-2
+        if (EDGE) {
+#pragma unroll
+            for (int jb = 0; jb < JB; jb++) X1[jb] = 0u;
+        }
+        if (!EDGE || (it >= 1 && eb + 1 < nwb)) chunk<CUR, 0, 0>(0, win, X1);   // block 2it-3 (carry: 2it-2)
+        if (!EDGE || it >= 2) emit<EDGE, 2>(X0, X1, 3);                         // pair (2it-4, 2it-3)
+        else skip_emit<2>();
+        if (!EDGE || (it >= 1 && eb < nwb)) chunk<CUR, 2, 0>(0, win, X0);       // block 2it-2 (== eb after the emit)
     }
     __device__ void run42()
     {
@@ -550,13 +569,23 @@ struct FtcWarp {
     __device__ __forceinline__ void iter24(int it, uint32_t (&win)[JB][2], uint32_t (&Xp)[JB])
     {
         uint32_t in[Geo::NC], X[JB];
+        // eb == it-3.  Pipeline fill / drain (EDGE iterations only): iteration 0 has no block of its own (its first chunk
+        // only reaches block -1), iteration 1 emits block -1; the last iteration's second chunk opens a window past the
+        // segment.
         convert<EDGE>(2 * it, in); step1<0>(in); fetch<EDGE>();
-        chunk<0, 0, 2>(1, win, X);                                      // block it-2
-        emit<EDGE, 1>(Xp, X, 2);                                        // pair (it-3, it-2), second half only
+        if (EDGE) {
+#pragma unroll
+            for (int jb = 0; jb < JB; jb++) X[jb] = 0u;
+        }
+        if (!EDGE || it >= 1) chunk<0, 0, 2>(1, win, X);                // block it-2 (carry: it-1)
+        if (!EDGE || it >= 2) emit<EDGE, 1>(Xp, X, 2);                  // pair (it-3, it-2), second half only
+        else skip_emit<1>();
 #pragma unroll
         for (int jb = 0; jb < JB; jb++) Xp[jb] = X[jb];
-        convert<EDGE>(2 * it + 1, in); step1<1>(in); fetch<EDGE>();
-        chunk<1, 0, 1>(0, win, X);
+        if (!EDGE || it - 1 < nwb) {
+            convert<EDGE>(2 * it + 1, in); step1<1>(in); fetch<EDGE>();
+            chunk<1, 0, 1>(0, win, X);
+        }
     }
     __device__ void run24()
     {
@@ -608,20 +637,26 @@ flr_tc_kernel(const __grid_constant__ FlrTcParams p)
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned wid = blockIdx.x * FTC_WARPS + warp;              // warps run over (plane, segment, strip)
-    if (wid >= p.total_warps) return;
-    const int plane = (int)(wid / (unsigned)p.units);                // n * C + c
-    const int unit = (int)(wid - (unsigned)plane * (unsigned)p.units);
     extern __shared__ __align__(16) uint8_t ring_smem[];
     typedef FtcWarp<U, D, TIN, TOUT, ACT, FAST> W;
     W w(p, lane);
     w.ring = (uint32_t)__cvta_generic_to_shared(ring_smem) + (uint32_t)(warp * W::WARP_RING_BYTES + lane * W::RAW_BYTES);
     w.load_consts(tab);
-    w.begin_strip(unit, plane);
-    w.run();
+    // Persistent warps: the grid is one resident wave, every warp walks over (plane, segment, strip) units with the tap
+    // fragments built once (the table fill, the barrier and load_consts are ~250 of the ~500 instructions a warp used to
+    // spend before its first product -- a third of all instructions on the 36-pixel planes).  Consecutive units are
+    // neighbouring strips of one plane, so the warps of a CTA still share their halo columns in L1/L2.
+    for (unsigned wid = blockIdx.x * FTC_WARPS + warp; wid < p.total_warps; wid += gridDim.x * FTC_WARPS) {
+        const int plane = (int)(wid / (unsigned)p.units);            // n * C + c
+        const int unit = (int)(wid - (unsigned)plane * (unsigned)p.units);
+        w.begin_strip(unit, plane);
+        w.run();
+    }
 }
 
 static int floor_mod(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
+
+static int g_ftc_waves = 16;          // 0: one warp per unit (no persistence); n: at most n resident waves of CTAs (8..16 measured best)
 
 template <int U, int D, typename TIN, typename TOUT, int ACT, bool FAST>
 static int launch_tc(FlrTcParams& p, int N, cudaStream_t st)
@@ -641,8 +676,18 @@ static int launch_tc(FlrTcParams& p, int N, cudaStream_t st)
     p.units = p.strips * p.segs;
     if (planes * p.units > 0x7fffffffLL) { set_error("filtered_lrelu_tc: too many strips"); return AFCM_ERR_INVALID; }
     p.total_warps = (unsigned)(planes * p.units);
-    const unsigned blocks = (p.total_warps + FTC_WARPS - 1) / FTC_WARPS;
+    unsigned blocks = (p.total_warps + FTC_WARPS - 1) / FTC_WARPS;
     const int smem = FTC_WARPS * FtcWarp<U, D, TIN, TOUT, ACT, FAST>::WARP_RING_BYTES;
+    // one resident wave (persistent warps); g_ftc_waves > 1 launches that many waves' worth of CTAs (tuning switch)
+    static int resident = 0;                  // per instantiation: CTAs per SM x SMs
+    if (!resident) {
+        int per_sm = 0, sms = 0, dev = 0;
+        AFCM_CUDA(cudaGetDevice(&dev));
+        AFCM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        AFCM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flr_tc_kernel<U, D, TIN, TOUT, ACT, FAST>, FTC_WARPS * 32, smem));
+        resident = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 148);
+    }
+    if (g_ftc_waves > 0 && blocks > (unsigned)(resident * g_ftc_waves)) blocks = (unsigned)(resident * g_ftc_waves);
     flr_tc_kernel<U, D, TIN, TOUT, ACT, FAST><<<blocks, FTC_WARPS * 32, smem, st>>>(p);
     AFCM_LAUNCH_CHECK();
     count_launch();
@@ -668,6 +713,8 @@ static int dispatch_act(FlrTcParams& p, int N, int up, int down, int act, cudaSt
 }  // namespace afcm
 
 using namespace afcm;
+
+extern "C" int afcm_filtered_lrelu_tc_set_waves(int waves) { g_ftc_waves = waves < 0 ? 0 : waves; return AFCM_OK; }
 
 extern "C" int afcm_filtered_lrelu_tc(const void* x, const int64_t* xs, int x_dtype, void* y, const int64_t* ys, int y_dtype,
                                       const float* b, const void* skip,

@@ -97,6 +97,9 @@ int afcm_filtered_lrelu_tc(const void* x, const int64_t* xs, int x_dtype, void* 
                            int up, int down, int px0, int px1, int py0, int py1,
                            float gain, float slope, float clamp, float out_scale, int flip_filter,
                            void* stream);
+/* Scheduling of afcm_filtered_lrelu_tc for tuning (process-global, not part of the stable ABI): n >= 1 = persistent warps,
+ * at most n resident waves of CTAs (default 16, the measured optimum); 0 = one warp per 16-column strip. */
+int afcm_filtered_lrelu_tc_set_waves(int waves);
 
 /* Tensor-core filtered_lrelu WITH the sign tensor (afcm_b200/csrc/flr_tcs.cu): the training-step variant.  Same
  * arguments, sign-tensor format and sign_mode meaning as afcm_filtered_lrelu, so forward (SIGN_WRITE) and backward

@@ -63,6 +63,8 @@ def main():
              [(n, getattr(S, n)) for n in S.layer_names]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     B = args.batch
+    if os.environ.get('AFCM_FTC_WAVES'):
+        _lib.lib().afcm_filtered_lrelu_tc_set_waves(int(os.environ['AFCM_FTC_WAVES']))
     if args.tile:
         tw, th = [int(v) for v in args.tile.split('x')]
         _lib.lib().afcm_filtered_lrelu_set_tile(tw, th)
