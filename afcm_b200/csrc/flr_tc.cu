@@ -70,6 +70,9 @@ template <int U, int D> struct FtcGeo {
     static constexpr int NPH = (U == 2) ? 1 : 2;          // distinct up-filter fragments (phases)
     static constexpr int NB5 = (D == 2) ? 2 : 4;          // 16-row chunks of R3 per block of 8 output rows
     static constexpr int IXS = 16 * D / U;                // input columns per strip step
+    // a last strip with at most 8 output columns left (every AFCM plane but the 256-pixel one ends with 4): output column K
+    // reads the up-sampled columns D K + sx .. D K + sx + FD - 1, sx < U, so columns 0..7 need this many 16-wide blocks
+    static constexpr int MBN = (D * 7 + (U - 1) + FD + 15) / 16;
 };
 
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi)
@@ -375,11 +378,13 @@ struct FtcWarp {
     }
 
     // (1) horizontal up-FIR of input row block yb (already converted) -> P[SLOT]
-    template <int SLOT>
+    // NARROW: the strip has at most 8 output columns, only the first MBN blocks of up-sampled columns and the first block of
+    // output columns are computed
+    template <int SLOT, bool NARROW>
     __device__ __forceinline__ void step1(const uint32_t (&in)[Geo::NC])
     {
 #pragma unroll
-        for (int b = 0; b < MB; b++) {
+        for (int b = 0; b < (NARROW ? Geo::MBN : MB); b++) {
             const int w = (U == 2) ? b : (b >> 1);          // first input chunk of the window
             const int ph = (U == 2) ? 0 : (b & 1);
             mma_h(P[SLOT][b], a1[ph], in[w], in[w + 1]);
@@ -391,11 +396,11 @@ struct FtcWarp {
     // ({ rows -8..-1, rows 0..7 } relative to the window's block of 8 output rows).
     // MODE 0 (D == 2, the chunk is the whole window): X[jb] = carry + upper half, carry = lower half.
     // MODE 1 (D == 4, first chunk): win = contribution.   MODE 2 (second chunk): win += contribution, then as MODE 0.
-    template <int CUR, int NB0, int MODE>
+    template <int CUR, int NB0, int MODE, bool NARROW>
     __device__ __forceinline__ void chunk(int al, uint32_t (&win)[JB][2], uint32_t (&X)[JB])
     {
 #pragma unroll
-        for (int mb = 0; mb < MB; mb++) {
+        for (int mb = 0; mb < (NARROW ? Geo::MBN : MB); mb++) {
             const uint32_t quad[4] = {P[0][mb][0], P[0][mb][1], P[1][mb][0], P[1][mb][1]};
             uint32_t e[2][2];
 #pragma unroll
@@ -430,7 +435,7 @@ struct FtcWarp {
     // out_scale is folded into the Td_x taps; a skip tensor is added as skip * out_scale.
     // `rows`: 3 = both blocks, 2 = only the second (X1), 1 = only the first.  The block pair is the one yq points
     // at; ADV = number of 8-row blocks yq advances afterwards.
-    template <bool EDGE, int ADV>
+    template <bool EDGE, int ADV, bool NARROW>
     __device__ __forceinline__ void emit(const uint32_t (&X0)[JB], const uint32_t (&X1)[JB], int rows)
     {
         TOUT* q0 = yq;                                              // (row w0 + 8 eb + g, col k0 + 2t)
@@ -441,7 +446,7 @@ struct FtcWarp {
             r1 = r1 && eb + 1 >= 0 && eb + 1 < nwb && w0 + 8 * eb + 8 + g < p.yh;
         }
 #pragma unroll
-        for (int nb = 0; nb < 2; nb++) {
+        for (int nb = 0; nb < (NARROW ? 1 : 2); nb++) {
             float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int rel = 0; rel < NREL; rel++) {
@@ -482,7 +487,7 @@ struct FtcWarp {
 
     // ---- U == 2, D == 2: super-iteration s = input row blocks 2s, 2s+1 -> up-sampled chunks 2s-1, 2s (= windows)
     // -> output row blocks 2s-2, 2s-1, emitted together.
-    template <bool EDGE>
+    template <bool EDGE, bool NARROW>
     __device__ __forceinline__ void super22(int s, uint32_t (&X0)[JB], uint32_t (&X1)[JB])
     {
         uint32_t in[Geo::NC], win[JB][2];
@@ -490,15 +495,16 @@ struct FtcWarp {
         //  * s == 0 produces blocks -2 and -1, which do not exist.  The first chunk only reaches block -1 (through the
         //    carry), so it is skipped together with the emit; the second chunk stays (its carry is part of block 0).
         //  * a last super whose second block lies beyond the segment (odd number of row blocks) stops after the first.
-        convert<EDGE>(2 * s, in); step1<0>(in); fetch<EDGE>();
-        if (!EDGE || s > 0) chunk<0, 0, 0>(0, win, X0);                 // block 2s-2
+        convert<EDGE>(2 * s, in); step1<0, NARROW>(in); fetch<EDGE>();
+        if (!EDGE || s > 0) chunk<0, 0, 0, NARROW>(0, win, X0);                 // block 2s-2
         if (!EDGE || eb + 1 < nwb) {
-            convert<EDGE>(2 * s + 1, in); step1<1>(in); fetch<EDGE>();
-            chunk<1, 0, 0>(0, win, X1);                                 // block 2s-1
+            convert<EDGE>(2 * s + 1, in); step1<1, NARROW>(in); fetch<EDGE>();
+            chunk<1, 0, 0, NARROW>(0, win, X1);                                 // block 2s-1
         }
-        if (!EDGE || s > 0) emit<EDGE, 2>(X0, X1, 3);                   // EDGE: rows outside the segment are masked
+        if (!EDGE || s > 0) emit<EDGE, 2, NARROW>(X0, X1, 3);                   // EDGE: rows outside the segment are masked
         else skip_emit<2>();
     }
+    template <bool NARROW>
     __device__ void run22()
     {
         uint32_t X0[JB], X1[JB];
@@ -506,39 +512,40 @@ struct FtcWarp {
         for (int jb = 0; jb < JB; jb++) X0[jb] = X1[jb] = 0u;
         const int S = ((nwb - 1) >> 1) + 2;
         int lo = 0, hi = 0;
-        if (interior) {
+        if (!NARROW && interior) {
             lo = max(1, (-iy + 15) >> 4);
             hi = min(min((fdiv8(p.xh - 8 - iy) - FTC_PD - 1) >> 1, min((p.yh - w0) >> 4, nwb >> 1)) + 1, S);
         }
         if (hi < lo) hi = lo = 0;
         eb = -2; yq -= 16 * p.ys_h;
         int s = 0;
-        for (; s < (hi > lo ? lo : S); s++) super22<true>(s, X0, X1);
-        if (hi > lo) {
-            for (; s < hi; s++) super22<false>(s, X0, X1);
-            for (; s < S; s++) super22<true>(s, X0, X1);
+        for (; s < (hi > lo ? lo : S); s++) super22<true, NARROW>(s, X0, X1);
+        if (!NARROW && hi > lo) {
+            for (; s < hi; s++) super22<false, false>(s, X0, X1);
+            for (; s < S; s++) super22<true, false>(s, X0, X1);
         }
     }
 
     // ---- U == 4, D == 2: iteration it = input row block it -> chunks (= windows) 2it-2, 2it-1 -> output row blocks
     // 2it-3 (odd, completes the pair started by the previous iteration) and 2it-2 (even, kept in X0).
-    template <bool EDGE, int CUR>
+    template <bool EDGE, int CUR, bool NARROW>
     __device__ __forceinline__ void iter42(int it, uint32_t (&X0)[JB])
     {
         uint32_t in[Geo::NC], win[JB][2], X1[JB];
         // eb == 2it-4.  Pipeline fill / drain (EDGE iterations only): a chunk is needed if its block or the block its
         // carry reaches exists, the emit if one block of its pair exists; an iteration past the segment does nothing.
         if (EDGE && eb >= nwb) { skip_emit<2>(); return; }
-        convert<EDGE>(it, in); step1<CUR>(in); fetch<EDGE>();
+        convert<EDGE>(it, in); step1<CUR, NARROW>(in); fetch<EDGE>();
         if (EDGE) {
 #pragma unroll
             for (int jb = 0; jb < JB; jb++) X1[jb] = 0u;
         }
-        if (!EDGE || (it >= 1 && eb + 1 < nwb)) chunk<CUR, 0, 0>(0, win, X1);   // block 2it-3 (carry: 2it-2)
-        if (!EDGE || it >= 2) emit<EDGE, 2>(X0, X1, 3);                         // pair (2it-4, 2it-3)
+        if (!EDGE || (it >= 1 && eb + 1 < nwb)) chunk<CUR, 0, 0, NARROW>(0, win, X1);   // block 2it-3 (carry: 2it-2)
+        if (!EDGE || it >= 2) emit<EDGE, 2, NARROW>(X0, X1, 3);                         // pair (2it-4, 2it-3)
         else skip_emit<2>();
-        if (!EDGE || (it >= 1 && eb < nwb)) chunk<CUR, 2, 0>(0, win, X0);       // block 2it-2 (== eb after the emit)
+        if (!EDGE || (it >= 1 && eb < nwb)) chunk<CUR, 2, 0, NARROW>(0, win, X0);       // block 2it-2 (== eb after the emit)
     }
+    template <bool NARROW>
     __device__ void run42()
     {
         uint32_t X0[JB];
@@ -547,7 +554,7 @@ struct FtcWarp {
         const int iters = ((nwb - 1) >> 1) + 3;
         const int S = (iters + 1) >> 1;
         int lo = 0, hi = 0;
-        if (interior) {
+        if (!NARROW && interior) {
             // iterations 2s, 2s+1: input blocks up to 2s+1 (+PD), output pairs s-2.. : blocks 4s-4 .. 4s-1
             lo = max(1, (-iy + 15) >> 4);
             hi = min(min((fdiv8(p.xh - 8 - iy) - FTC_PD - 1) >> 1, min((p.yh - w0) >> 5, nwb >> 2)) + 1, S);
@@ -555,38 +562,39 @@ struct FtcWarp {
         if (hi < lo) hi = lo = 0;
         eb = -4; yq -= 32 * p.ys_h;
         int s = 0;
-        for (; s < (hi > lo ? lo : S); s++) { iter42<true, 0>(2 * s, X0); iter42<true, 1>(2 * s + 1, X0); }
-        if (hi > lo) {
-            for (; s < hi; s++) { iter42<false, 0>(2 * s, X0); iter42<false, 1>(2 * s + 1, X0); }
-            for (; s < S; s++) { iter42<true, 0>(2 * s, X0); iter42<true, 1>(2 * s + 1, X0); }
+        for (; s < (hi > lo ? lo : S); s++) { iter42<true, 0, NARROW>(2 * s, X0); iter42<true, 1, NARROW>(2 * s + 1, X0); }
+        if (!NARROW && hi > lo) {
+            for (; s < hi; s++) { iter42<false, 0, false>(2 * s, X0); iter42<false, 1, false>(2 * s + 1, X0); }
+            for (; s < S; s++) { iter42<true, 0, false>(2 * s, X0); iter42<true, 1, false>(2 * s + 1, X0); }
         }
     }
 
     // ---- U == 2, D == 4: iteration it = input row blocks 2it, 2it+1 -> chunks 2it-1 (second half of window it-1)
     // and 2it (first half of window it) -> output row block it-2; blocks are emitted one at a time as the second
     // half of the pair (it-3, it-2).
-    template <bool EDGE>
+    template <bool EDGE, bool NARROW>
     __device__ __forceinline__ void iter24(int it, uint32_t (&win)[JB][2], uint32_t (&Xp)[JB])
     {
         uint32_t in[Geo::NC], X[JB];
         // eb == it-3.  Pipeline fill / drain (EDGE iterations only): iteration 0 has no block of its own (its first chunk
         // only reaches block -1), iteration 1 emits block -1; the last iteration's second chunk opens a window past the
         // segment.
-        convert<EDGE>(2 * it, in); step1<0>(in); fetch<EDGE>();
+        convert<EDGE>(2 * it, in); step1<0, NARROW>(in); fetch<EDGE>();
         if (EDGE) {
 #pragma unroll
             for (int jb = 0; jb < JB; jb++) X[jb] = 0u;
         }
-        if (!EDGE || it >= 1) chunk<0, 0, 2>(1, win, X);                // block it-2 (carry: it-1)
-        if (!EDGE || it >= 2) emit<EDGE, 1>(Xp, X, 2);                  // pair (it-3, it-2), second half only
+        if (!EDGE || it >= 1) chunk<0, 0, 2, NARROW>(1, win, X);                // block it-2 (carry: it-1)
+        if (!EDGE || it >= 2) emit<EDGE, 1, NARROW>(Xp, X, 2);                  // pair (it-3, it-2), second half only
         else skip_emit<1>();
 #pragma unroll
         for (int jb = 0; jb < JB; jb++) Xp[jb] = X[jb];
         if (!EDGE || it - 1 < nwb) {
-            convert<EDGE>(2 * it + 1, in); step1<1>(in); fetch<EDGE>();
-            chunk<1, 0, 1>(0, win, X);
+            convert<EDGE>(2 * it + 1, in); step1<1, NARROW>(in); fetch<EDGE>();
+            chunk<1, 0, 1, NARROW>(0, win, X);
         }
     }
+    template <bool NARROW>
     __device__ void run24()
     {
         uint32_t win[JB][2], Xp[JB];
@@ -594,26 +602,27 @@ struct FtcWarp {
         for (int jb = 0; jb < JB; jb++) { win[jb][0] = win[jb][1] = 0u; Xp[jb] = 0u; }
         const int iters = nwb + 2;
         int lo = 0, hi = 0;
-        if (interior) {
+        if (!NARROW && interior) {
             lo = max(3, (-iy + 15) >> 4);
             hi = min(min((fdiv8(p.xh - 8 - iy) - FTC_PD - 1) >> 1, fdiv8(p.yh - w0) + 1) + 1, iters);
         }
         if (hi < lo) hi = lo = 0;
         eb = -3; yq -= 24 * p.ys_h;
         int it = 0;
-        for (; it < (hi > lo ? lo : iters); it++) iter24<true>(it, win, Xp);
-        if (hi > lo) {
-            for (; it < hi; it++) iter24<false>(it, win, Xp);
-            for (; it < iters; it++) iter24<true>(it, win, Xp);
+        for (; it < (hi > lo ? lo : iters); it++) iter24<true, NARROW>(it, win, Xp);
+        if (!NARROW && hi > lo) {
+            for (; it < hi; it++) iter24<false, false>(it, win, Xp);
+            for (; it < iters; it++) iter24<true, false>(it, win, Xp);
         }
     }
 
     __device__ void run()
     {
         prime();
-        if (U == 2 && D == 2) run22();
-        else if (U == 4 && D == 2) run42();
-        else run24();
+        const bool narrow = p.yw - k0 <= 8;             // warp-uniform
+        if (U == 2 && D == 2) { if (narrow) run22<true>(); else run22<false>(); }
+        else if (U == 4 && D == 2) { if (narrow) run42<true>(); else run42<false>(); }
+        else { if (narrow) run24<true>(); else run24<false>(); }
         cp_async_wait<0>();
     }
 };
