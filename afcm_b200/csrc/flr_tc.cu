@@ -630,8 +630,11 @@ struct FtcWarp {
 #ifndef AFCM_FTC_MINB22
 #define AFCM_FTC_MINB22 4
 #endif
+#ifndef AFCM_FTC_MINB24
+#define AFCM_FTC_MINB24 2
+#endif
 template <int U, int D, typename TIN, typename TOUT, int ACT, bool FAST>
-__global__ void __launch_bounds__(FTC_WARPS * 32, (U == 2 && D == 4) ? 2 : (U == 4 ? 4 : AFCM_FTC_MINB22))
+__global__ void __launch_bounds__(FTC_WARPS * 32, (U == 2 && D == 4) ? AFCM_FTC_MINB24 : (U == 4 ? 4 : AFCM_FTC_MINB22))
 flr_tc_kernel(const __grid_constant__ FlrTcParams p)
 {
     // zero-padded tap tables (index e + FTC_TAB_OFS): the fragments below index them with per-lane offsets
