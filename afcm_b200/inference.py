@@ -86,6 +86,54 @@ class GraphedGenerator:
         return self.y
 
 
+class PipelinedGenerator:
+    """Host-to-host inference with the copies hidden behind the forward: batches arrive in pinned HOST buffers and results
+    leave into pinned HOST buffers, like the reference's per-slice loop (evaluate.py:43-104), but the upload of batch k+1
+    (copy stream) and the download of batch k-1 (second copy stream) run while the graph of batch k replays.  Two device
+    staging sets per direction; events order upload -> forward -> download per set, so a set is reused only after its
+    consumer has finished.  `submit()` returns immediately; `finish()` makes the current stream wait for every download."""
+
+    def __init__(self, runner, depth=2):
+        assert isinstance(runner, GraphedGenerator) and depth >= 2
+        self.runner, self.depth, self.k = runner, depth, 0
+        dev = runner.device
+        self.up, self.down = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        mk = lambda t: [torch.empty_like(t) for _ in range(depth)]
+        self.sz, self.sc, self.sx = mk(runner.z), mk(runner.c), mk(runner.x)
+        if runner.graph is None:
+            runner.capture()
+        self.sy = mk(runner.y)
+        ev = lambda: [torch.cuda.Event() for _ in range(depth)]
+        self.uploaded, self.consumed, self.computed, self.downloaded = ev(), ev(), ev(), ev()
+
+    def submit(self, hz, hc, hx, hy):
+        """hz, hc, hx: pinned host inputs of one batch; hy: pinned host buffer that receives the result."""
+        r, i = self.runner, self.k % self.depth
+        cur = torch.cuda.current_stream(r.device)
+        with torch.cuda.stream(self.up):
+            self.up.wait_event(self.consumed[i])                 # the forward that read this staging set is done
+            self.sz[i].copy_(hz, non_blocking=True)
+            self.sc[i].copy_(hc.reshape(r.batch, -1), non_blocking=True)
+            self.sx[i].copy_(hx, non_blocking=True)
+            self.uploaded[i].record(self.up)
+        cur.wait_event(self.uploaded[i])
+        y = r(self.sz[i], self.sc[i], self.sx[i])                # device-to-device into the graph's buffers + replay
+        self.consumed[i].record(cur)
+        cur.wait_event(self.downloaded[i])                       # the previous result of this set has left the device
+        self.sy[i].copy_(y, non_blocking=True)
+        self.computed[i].record(cur)
+        with torch.cuda.stream(self.down):
+            self.down.wait_event(self.computed[i])
+            hy.copy_(self.sy[i], non_blocking=True)
+            self.downloaded[i].record(self.down)
+        self.k += 1
+
+    def finish(self):
+        cur = torch.cuda.current_stream(self.runner.device)
+        cur.wait_stream(self.down)
+        cur.wait_stream(self.up)
+
+
 def slice_partition(num_slices, world_size, rank):
     """Contiguous block [lo, hi) of slice indices owned by `rank` (ceil(D / world) per rank)."""
     assert 0 <= rank < world_size and num_slices >= 0

@@ -156,3 +156,28 @@ def test_volume_predictor_matches_direct_call(golden_tiny):
         ref = G(z.to(dev), torch.from_numpy(c).to(dev), xf, noise_mode='const').cpu()
     assert rel_err(y.numpy(), ref.numpy()) < 1e-5
     assert np.allclose(c[:, 0], [0, .2, .4, .6, .8, 0])
+
+
+def test_pipelined_generator_matches_direct_call(golden_tiny):
+    """Host-to-host pipelined inference (upload / forward / download on three streams, two staging sets): every batch of a
+    sequence of DIFFERENT batches comes back equal to the direct call on that batch."""
+    from afcm_b200 import inference
+    dev = torch.device('cuda:0')
+    G = _load_tiny(golden_tiny, dev)
+    B, steps = 3, 5
+    g = torch.Generator().manual_seed(7)
+    S = G.synthesis
+    batches = [(torch.randn(B, G.z_dim, generator=g).pin_memory(), torch.rand(B, 1, generator=g).pin_memory(),
+                (torch.rand(B, S.img_channels_in, S.img_resolution, S.img_resolution, generator=g) * 2 - 1).pin_memory())
+               for _ in range(steps)]
+    outs = [torch.empty(B, 1, S.img_resolution, S.img_resolution).pin_memory() for _ in range(steps)]
+    runner = inference.GraphedGenerator(G, batch=B).capture()
+    pipe = inference.PipelinedGenerator(runner)
+    for (z, c, x), y in zip(batches, outs):
+        pipe.submit(z, c, x, y)
+    pipe.finish()
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        for (z, c, x), y in zip(batches, outs):
+            ref = G(z.to(dev), c.to(dev), x.to(dev), noise_mode='const').cpu()
+            assert rel_err(y.numpy(), ref.numpy()) < 1e-6
