@@ -88,6 +88,8 @@ class VolumePredictor:
     def __call__(self, volume, thickness=1, seed=0):
         D = int(np.asarray(volume).shape[0])
         lo, hi = slice_partition(D, self.world_size, self.rank)
+        if self.device.type == 'cuda' and hi > lo:
+            return self._run_pipelined(np.asarray(volume), lo, hi, thickness, seed), (lo, hi)
         x, c = build_stacks(volume, lo, hi, thickness)
         z = self.latents(lo, hi, seed)
         outs = []
@@ -101,6 +103,56 @@ class VolumePredictor:
         H, W = np.asarray(volume).shape[1:]
         y = torch.cat(outs) if outs else torch.empty([0, 1, H, W])
         return y, (lo, hi)
+
+    def _pinned(self, name, shape, dtype):
+        """Pinned host staging buffers, kept between calls (pinning is a driver call of milliseconds)."""
+        cache = self.__dict__.setdefault('_pin', {})
+        key = (name, tuple(shape), dtype)
+        if key not in cache:
+            cache[key] = torch.empty(shape, dtype=dtype).pin_memory()
+        return cache[key]
+
+    def _run_pipelined(self, vol, lo, hi, thickness, seed):
+        """GPU path: the host gathers the stacks of batch k+1 into pinned memory while the device runs batch k; uploads
+        go through one copy stream, results come back through another into one pinned output block.  Nothing is
+        synchronised between batches; the call returns after the last download.  The result lives in a pinned buffer that
+        the next call with the same block shape reuses (clone it to keep it)."""
+        n, B = hi - lo, self.batch
+        H, W = vol.shape[1:]
+        dev = self.device
+        np_dt = torch.uint8 if vol.dtype == np.uint8 else torch.float32
+        hx = self._pinned('x', [n, 4, H, W], np_dt)
+        hc = self._pinned('c', [n, 1], torch.float32)
+        hz = self._pinned('z', [n, self.z_dim], torch.float32)
+        hy = self._pinned('y', [n, 1, H, W], torch.float32)
+        cur = torch.cuda.current_stream(dev)
+        if '_streams' not in self.__dict__:
+            self._streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        up, down = self._streams
+        up.wait_stream(cur)
+        down.wait_stream(cur)
+        keep = []                                            # device tensors stay alive until the final synchronisation
+        with torch.no_grad():
+            for b0 in range(0, n, B):
+                b1 = min(b0 + B, n)
+                x, c = build_stacks(vol, lo + b0, lo + b1, thickness)
+                hx[b0:b1].copy_(torch.from_numpy(x)); hc[b0:b1].copy_(torch.from_numpy(c))
+                hz[b0:b1].copy_(self.latents(lo + b0, lo + b1, seed))
+                with torch.cuda.stream(up):
+                    xb = hx[b0:b1].to(dev, non_blocking=True)
+                    cb = hc[b0:b1].to(dev, non_blocking=True)
+                    zb = hz[b0:b1].to(dev, non_blocking=True)
+                    ev_up = torch.cuda.Event(); ev_up.record(up)
+                cur.wait_event(ev_up)
+                yb = self.run(zb, cb, xb).float()
+                ev_y = torch.cuda.Event(); ev_y.record(cur)
+                with torch.cuda.stream(down):
+                    down.wait_event(ev_y)
+                    hy[b0:b1].copy_(yb, non_blocking=True)
+                keep.append((xb, cb, zb, yb))
+        cur.wait_stream(down)
+        down.synchronize()
+        return hy                    # pinned; valid until the next call with a block of the same shape
 
     def collect(self, y_local, block, num_slices):
         """Gathers the per-rank blocks on rank 0 (plain scatter into the volume: every voxel is produced once)."""
