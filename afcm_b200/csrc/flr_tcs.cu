@@ -118,16 +118,26 @@ flr_tcs_kernel(const __grid_constant__ FlrParams p)
         const int sh = (int)p.xs_h, sw = (int)p.xs_w;
         const float* x0 = xp + iby * sh + ibx * sw;                 // sample (0,0) of the tile (may lie outside the plane)
         constexpr int NIT = (G::IHP * 32 + TS_THREADS - 1) / TS_THREADS;
+        // All global loads of the thread are issued before the first shared-memory store: interleaved, every store is a
+        // possible alias of the next load for the compiler, and the pass ran as NIT dependent load -> store round trips
+        // (57 % of the kernel's stall samples, profiles/r01_ncu_flr_tcs.txt).
+        float v0[NIT], v1[NIT];
 #pragma unroll
         for (int it = 0; it < NIT; it++) {
             const int i = tid + it * TS_THREADS;
             const int iy = i >> 5, ix = (i & 31) * 2;
             const bool rok = iy < G::IH && (unsigned)(iby + iy) < (unsigned)p.xh;
             const float* src = x0 + iy * sh + ix * sw;
-            float v0 = 0.f, v1 = 0.f;
-            if (rok && ix < G::IW && (unsigned)(ibx + ix) < (unsigned)p.xw) v0 = src[0] + bias;
-            if (rok && ix + 1 < G::IW && (unsigned)(ibx + ix + 1) < (unsigned)p.xw) v1 = src[sw] + bias;
-            if (iy < G::IHP && ix < G::P_X) *reinterpret_cast<uint32_t*>(bufA + iy * G::P_X + ix) = Op::pack(v0, v1);
+            const bool ok0 = rok && ix < G::IW && (unsigned)(ibx + ix) < (unsigned)p.xw;
+            const bool ok1 = rok && ix + 1 < G::IW && (unsigned)(ibx + ix + 1) < (unsigned)p.xw;
+            v0[it] = ok0 ? __ldg(src) + bias : 0.f;
+            v1[it] = ok1 ? __ldg(src + sw) + bias : 0.f;
+        }
+#pragma unroll
+        for (int it = 0; it < NIT; it++) {
+            const int i = tid + it * TS_THREADS;
+            const int iy = i >> 5, ix = (i & 31) * 2;
+            if (iy < G::IHP && ix < G::P_X) *reinterpret_cast<uint32_t*>(bufA + iy * G::P_X + ix) = Op::pack(v0[it], v1[it]);
         }
         if (SIGN == 2) {
             // the tile's part of the packed sign tensor as aligned 32-bit words: staged row = 8 words = 32 bytes starting at
