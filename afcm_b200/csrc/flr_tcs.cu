@@ -122,16 +122,29 @@ flr_tcs_kernel(const __grid_constant__ FlrParams p)
         // possible alias of the next load for the compiler, and the pass ran as NIT dependent load -> store round trips
         // (57 % of the kernel's stall samples, profiles/r01_ncu_flr_tcs.txt).
         float v0[NIT], v1[NIT];
+        // tiles whose input window lies inside the plane (most of them on the large planes) need only the tile-shape tests
+        const bool inner = iby >= 0 && iby + G::IH <= p.xh && ibx >= 0 && ibx + G::IW <= p.xw;
+        if (inner) {
+            const float* xt = x0 + (tid >> 5) * sh + (tid & 31) * 2 * sw;
 #pragma unroll
-        for (int it = 0; it < NIT; it++) {
-            const int i = tid + it * TS_THREADS;
-            const int iy = i >> 5, ix = (i & 31) * 2;
-            const bool rok = iy < G::IH && (unsigned)(iby + iy) < (unsigned)p.xh;
-            const float* src = x0 + iy * sh + ix * sw;
-            const bool ok0 = rok && ix < G::IW && (unsigned)(ibx + ix) < (unsigned)p.xw;
-            const bool ok1 = rok && ix + 1 < G::IW && (unsigned)(ibx + ix + 1) < (unsigned)p.xw;
-            v0[it] = ok0 ? __ldg(src) + bias : 0.f;
-            v1[it] = ok1 ? __ldg(src + sw) + bias : 0.f;
+            for (int it = 0; it < NIT; it++) {
+                const int iy = (tid >> 5) + it * (TS_THREADS / 32), ix = (tid & 31) * 2;
+                const float* src = xt + it * (TS_THREADS / 32) * sh;
+                v0[it] = (iy < G::IH && ix < G::IW) ? __ldg(src) + bias : 0.f;
+                v1[it] = (iy < G::IH && ix + 1 < G::IW) ? __ldg(src + sw) + bias : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int it = 0; it < NIT; it++) {
+                const int i = tid + it * TS_THREADS;
+                const int iy = i >> 5, ix = (i & 31) * 2;
+                const bool rok = iy < G::IH && (unsigned)(iby + iy) < (unsigned)p.xh;
+                const float* src = x0 + iy * sh + ix * sw;
+                const bool ok0 = rok && ix < G::IW && (unsigned)(ibx + ix) < (unsigned)p.xw;
+                const bool ok1 = rok && ix + 1 < G::IW && (unsigned)(ibx + ix + 1) < (unsigned)p.xw;
+                v0[it] = ok0 ? __ldg(src) + bias : 0.f;
+                v1[it] = ok1 ? __ldg(src + sw) + bias : 0.f;
+            }
         }
 #pragma unroll
         for (int it = 0; it < NIT; it++) {
