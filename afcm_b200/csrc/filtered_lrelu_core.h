@@ -152,21 +152,33 @@ AFCM_HD void flr_pass_load(int tid, int nthr, const FlrParams& p, const FlrTile&
     FlrRowCol rc(tid, nthr, p.p_in);
     const T* x0 = xp + t.iby * p.xs_h + t.ibx * p.xs_w;          // element (0,0) of the tile (may lie outside the plane)
     const int sh = (int)p.xs_h, sw = (int)p.xs_w;                // offsets inside a plane fit 32 bits (checked by the host)
+    // Four items per round, all loads before the first store: a shared-memory store between two global loads is a
+    // possible alias for the compiler and serialises the pass into dependent load -> store round trips.
+    constexpr int B = 4;
     if (t.iby >= 0 && t.iby + p.inh <= p.xh && t.ibx >= 0 && t.ibx + p.inw <= p.xw) {
         // interior tile: every input sample exists, only the pitch padding columns are zero
-        for (int i = tid; i < n; i += nthr, rc.next()) {
-            float v = 0.f;
-            if (rc.col < p.inw) v = (float)x0[rc.row * sh + rc.col * sw] + bias;
-            s_in[i] = v;
+        for (int i = tid; i < n; i += B * nthr) {
+            float v[B];
+            FlrRowCol r2 = rc;
+            for (int k = 0; k < B; k++, r2.next())
+                v[k] = (i + k * nthr < n && r2.col < p.inw) ? (float)x0[r2.row * sh + r2.col * sw] + bias : 0.f;
+            for (int k = 0; k < B; k++)
+                if (i + k * nthr < n) s_in[i + k * nthr] = v[k];
+            rc = r2;
         }
     } else {
-        for (int i = tid; i < n; i += nthr, rc.next()) {
-            const int iy = rc.row, ix = rc.col;
-            const int gy = t.iby + iy, gx = t.ibx + ix;
-            float v = 0.f;
-            if (ix < p.inw && gy >= 0 && gy < p.xh && gx >= 0 && gx < p.xw)
-                v = (float)x0[iy * sh + ix * sw] + bias;
-            s_in[i] = v;
+        for (int i = tid; i < n; i += B * nthr) {
+            float v[B];
+            FlrRowCol r2 = rc;
+            for (int k = 0; k < B; k++, r2.next()) {
+                const int iy = r2.row, ix = r2.col;
+                const int gy = t.iby + iy, gx = t.ibx + ix;
+                v[k] = (i + k * nthr < n && ix < p.inw && gy >= 0 && gy < p.xh && gx >= 0 && gx < p.xw)
+                           ? (float)x0[iy * sh + ix * sw] + bias : 0.f;
+            }
+            for (int k = 0; k < B; k++)
+                if (i + k * nthr < n) s_in[i + k * nthr] = v[k];
+            rc = r2;
         }
     }
 }
