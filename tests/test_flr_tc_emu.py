@@ -42,3 +42,24 @@ def test_emulation_matches_oracle(up, down, pad, H, W, seg):
     assert np.abs(y - ref).max() <= 1e-5 * np.abs(ref).max()
     y16 = filtered_lrelu_tc_emu(x, fu, fd, b, up, down, pad, np.sqrt(2), 0.2, 2.0, fp16=True, seg_wblocks=seg)
     assert np.abs(y16 - ref).max() <= 2e-3 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize('up,down,pad,H,W,seg', [(2, 2, [9, 8, 9, 8], 38, 38, None), (2, 2, [8, 9, 10, 7], 38, 52, 4),
+                                                 (2, 4, [34, 33, 34, 33], 54, 54, None), (4, 2, [-6, -9, -6, -9], 22, 26, None)])
+def test_fragment_coordinates_of_the_sign_tensor(up, down, pad, H, W, seg):
+    """Groundwork for a sign mode of the kernel: the pre-activation value a warp holds in fragment element (column block mb,
+    row m; row block nb, column n) is the up-sampled sample the reference sign tensor indexes at (uy, ux) as stated in
+    Warp.record -- every sample of the sign tensor's extent is produced by some warp and equals the oracle's value."""
+    rng = np.random.RandomState(H + W)
+    fu = scipy.signal.firwin(6 * up, 0.4, width=0.3, fs=2).astype(np.float32)
+    fd = scipy.signal.firwin(6 * down, 0.25, width=0.2, fs=2).astype(np.float32)
+    x = (rng.randn(1, 1, H, W) * 2).astype(np.float32)
+    _, so, pre = orc.filtered_lrelu(x, fu, fd, None, up=up, down=down, padding=pad, gain=np.sqrt(2), slope=0.2, clamp=2.0,
+                                    write_signs=True, return_preact=True)
+    sz = orc.filtered_lrelu_sizes(H, W, up, down, len(fu), len(fd), pad)
+    sh = sz['SH']
+    sw = sz['OW'] * down - (down - 1) + len(fd) - 1                      # written width of the sign tensor (its pitch is padded)
+    _, got = filtered_lrelu_tc_emu(x, fu, fd, None, up, down, pad, np.sqrt(2), 0.2, 2.0, seg_wblocks=seg, preact_shape=(sh, sw))
+    assert not np.isnan(got).any()
+    ref = pre[:, :, :sh, :sw]
+    assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()

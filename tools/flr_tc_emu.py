@@ -40,6 +40,7 @@ class Warp:
 
     def __init__(self, geo, x, y, prm, fp16):
         self.g, self.x, self.y, self.p, self.fp16 = geo, x, y, prm, fp16
+        self.pre_map = None                                   # optional [SH][SW] map of pre-activation values (see record)
         G, p = geo, prm
         U, D = G.U, G.D
         # constant blocks (load_consts): A1[ph][J 16][X 16], B2[nb][Y 16][V 8], A3[al][W 16][V 16], B4[rel][J 16][K 8]
@@ -93,6 +94,21 @@ class Warp:
             # D[J 16][Y 8] = A1[ph][J][X 16] * in[Y][8 w + X]^T
             self.P[slot][b] = r16(self.A1[ph] @ blk[:, 8 * w:8 * w + 16].T, self.fp16)
 
+    def record(self, mb, nb0, pre):
+        """Where the sign tensor would get its codes from: fragment element (J = 16 mb + m, V = 8 (nb0 + q) + n of the window
+        whose current input row block is blk) is up-sampled sample (row, column) of the plane in sign-tensor coordinates
+            uy = D w0 + 8 U (blk - 1) + 8 (nb0 + q) + n - sy,      ux = D k0 + 16 mb + m - sx."""
+        G, p = self.g, self.p
+        blk = self.next_block - 1
+        H, W = self.pre_map.shape
+        for q in range(2):
+            for m in range(16):
+                ux = G.D * self.k0 + 16 * mb + m - p['sx']
+                for n in range(8):
+                    uy = G.D * self.w0 + 8 * G.U * (blk - 1) + 8 * (nb0 + q) + n - p['sy']
+                    if 0 <= uy < H and 0 <= ux < W:
+                        self.pre_map[uy, ux] = pre[q][m, n]
+
     def act(self, v):
         p = self.p
         v = np.where(v < 0, v * p['slope'], v)
@@ -104,7 +120,10 @@ class Warp:
         for mb in range(self.mb_n):
             prev, curb = self.P[1 - cur][mb], self.P[cur][mb]
             quad = np.concatenate([prev, curb], axis=1)                     # [J 16][Y 16], natural row order
-            e = [r16(self.act(quad @ self.B2[nb0 + q]), self.fp16) for q in range(2)]      # [J 16][V 8] each
+            pre = [quad @ self.B2[nb0 + q] for q in range(2)]               # [J 16][V 8] each, in units of u_scale
+            if self.pre_map is not None:
+                self.record(mb, nb0, pre)
+            e = [r16(self.act(v), self.fp16) for v in pre]
             for h in range(2):
                 jb = 2 * mb + h
                 Bv = np.concatenate([e[0][8 * h:8 * h + 8, :].T, e[1][8 * h:8 * h + 8, :].T], axis=0)    # [V 16][J 8]
@@ -210,8 +229,11 @@ class Warp:
         {(2, 2): self.run22, (4, 2): self.run42, (2, 4): self.run24}[(self.g.U, self.g.D)]()
 
 
-def filtered_lrelu_tc_emu(x, fu, fd, b, up, down, padding, gain, slope, clamp, flip_filter=False, fp16=False, seg_wblocks=None):
-    """x: [N, C, H, W] -> y like afcm_filtered_lrelu_tc (host parameter set-up of the C entry point + launch_tc)."""
+def filtered_lrelu_tc_emu(x, fu, fd, b, up, down, padding, gain, slope, clamp, flip_filter=False, fp16=False, seg_wblocks=None,
+                          preact_shape=None):
+    """x: [N, C, H, W] -> y like afcm_filtered_lrelu_tc (host parameter set-up of the C entry point + launch_tc).
+    preact_shape = (SH, SW): also return the pre-activation values (after the gain, before slope / clamp) the warps hold,
+    placed at their sign-tensor coordinates -> (y, pre [N, C, SH, SW]); NaN where no warp computed the sample."""
     x = np.asarray(x, np.float64)
     N, C, xh, xw = x.shape
     px0, px1, py0, py1 = padding
@@ -238,11 +260,14 @@ def filtered_lrelu_tc_emu(x, fu, fd, b, up, down, padding, gain, slope, clamp, f
     segs = -(-wblocks // p['seg_wblocks'])
     p['iy_step'] = p['seg_wblocks'] * 8 * down // up
     y = np.zeros((N, C, yh, yw))
+    pre = np.full((N, C) + tuple(preact_shape), np.nan) if preact_shape else None
     for n in range(N):
         for c in range(C):
             p['bias'] = 0.0 if b is None else float(b[c])
             w = Warp(G, x[n, c], y[n, c], p, fp16)
+            if pre is not None:
+                w.pre_map = pre[n, c]
             for unit in range(p['strips'] * segs):
                 w.begin_strip(unit)
                 w.run()
-    return y
+    return y if pre is None else (y, pre / u_scale)
