@@ -63,3 +63,23 @@ def test_fragment_coordinates_of_the_sign_tensor(up, down, pad, H, W, seg):
     assert not np.isnan(got).any()
     ref = pre[:, :, :sh, :sw]
     assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize('up,down,pad,H,W,seg', [(2, 2, [9, 8, 9, 8], 38, 38, None), (2, 2, [8, 9, 10, 7], 38, 52, 4),
+                                                 (2, 2, [9, 8, 9, 8], 22, 26, None), (2, 4, [34, 33, 34, 33], 54, 54, None),
+                                                 (4, 2, [-6, -9, -6, -9], 22, 26, None), (4, 2, [-5, -10, -7, -8], 54, 38, 4)])
+def test_sign_write_mode_design(up, down, pad, H, W, seg):
+    """The planned sign-write mode, emulated: codes taken from the fragments each warp holds, packed with the warp recipe,
+    stored under the ownership rule of Warp.flush_signs, give the oracle's sign tensor bit for bit (columns the reference
+    never reads -- beyond the written width -- excluded)."""
+    rng = np.random.RandomState(H * 3 + W)
+    fu = scipy.signal.firwin(6 * up, 0.4, width=0.3, fs=2).astype(np.float32)
+    fd = scipy.signal.firwin(6 * down, 0.25, width=0.2, fs=2).astype(np.float32)
+    x = (rng.randn(1, 2, H, W) * 2).astype(np.float32)
+    b = rng.randn(2).astype(np.float32)
+    _, so = orc.filtered_lrelu(x, fu, fd, b, up=up, down=down, padding=pad, gain=np.sqrt(2), slope=0.2, clamp=1.0, write_signs=True)
+    sz = orc.filtered_lrelu_sizes(H, W, up, down, len(fu), len(fd), pad)
+    sw = sz['OW'] * down - (down - 1) + len(fd) - 1
+    _, got = filtered_lrelu_tc_emu(x, fu, fd, b, up, down, pad, np.sqrt(2), 0.2, 1.0, seg_wblocks=seg, sign_shape=so.shape[2:])
+    unpack = lambda s: np.stack([(s >> (2 * j)) & 3 for j in range(4)], -1).reshape(*s.shape[:3], -1)[..., :sw]
+    assert np.array_equal(unpack(got), unpack(so))

@@ -41,6 +41,8 @@ class Warp:
     def __init__(self, geo, x, y, prm, fp16):
         self.g, self.x, self.y, self.p, self.fp16 = geo, x, y, prm, fp16
         self.pre_map = None                                   # optional [SH][SW] map of pre-activation values (see record)
+        self.sign_words = None                                # optional [SH][SWB / 4] uint32 sign tensor of the plane
+        self.codes = {}
         G, p = geo, prm
         U, D = G.U, G.D
         # constant blocks (load_consts): A1[ph][J 16][X 16], B2[nb][Y 16][V 8], A3[al][W 16][V 16], B4[rel][J 16][K 8]
@@ -114,6 +116,34 @@ class Warp:
         v = np.where(v < 0, v * p['slope'], v)
         return np.clip(v, -p['act_clamp'], p['act_clamp'])
 
+    def code_of(self, pre):
+        """2-bit code of a pre-activation value (in units of u_scale): 1 = negative, 2 = clamped (overrides)."""
+        p = self.p
+        a = np.where(pre < 0, pre * p['slope'], pre)
+        return np.where(np.abs(a) > p['act_clamp'], 2, (pre < 0).astype(np.int64)).astype(np.uint64)
+
+    def flush_signs(self, nb0):
+        """Sign write of one chunk (16 up-sampled rows x 16 mb_n columns): the warp recipe of tools/flr_sign_pack_model.py,
+        then the ownership rule -- a strip stores the D aligned words of its own 16 D up-sampled columns (the last strip
+        every word up to the end of the row), a segment the rows of its own output rows (the last one the rest)."""
+        from tools.flr_sign_pack_model import pack_chunk
+        G, p = self.g, self.p
+        SH, NW = self.sign_words.shape
+        blk = self.next_block - 1
+        strip = self.k0 // 16
+        last_strip = strip == p['strips'] - 1
+        n_own = (NW - G.D * strip) if last_strip else G.D
+        code = np.concatenate([self.codes[mb] for mb in range(self.mb_n)] + [np.zeros((16, 16), np.uint64)] * 2, axis=0)
+        words = pack_chunk(code, p['sx'])                                   # [16 rows][mb_n + 1]
+        assert n_own <= words.shape[1]
+        row_lo = G.D * self.w0
+        row_hi = SH if self.w0 + 8 * p['seg_wblocks'] >= p['yh'] else G.D * (self.w0 + 8 * p['seg_wblocks'])
+        for n in range(16):
+            uy = G.D * self.w0 + 8 * G.U * (blk - 1) + 8 * nb0 + n - p['sy']
+            if row_lo <= uy < row_hi and uy >= 0:
+                for wl in range(n_own):
+                    self.sign_words[uy, G.D * strip + wl] = words[n, wl]
+
     def chunk(self, cur, nb0, mode, al, win, X):
         """Vertical up-FIR of the window (previous | current) for row blocks nb0, nb0 + 1, activation, and that chunk's
         contribution to the window of R3.  win / X: lists over jb of [16 W][8 J] / [8 W][8 J]."""
@@ -123,6 +153,8 @@ class Warp:
             pre = [quad @ self.B2[nb0 + q] for q in range(2)]               # [J 16][V 8] each, in units of u_scale
             if self.pre_map is not None:
                 self.record(mb, nb0, pre)
+            if self.sign_words is not None:
+                self.codes[mb] = np.concatenate([self.code_of(pre[0]), self.code_of(pre[1])], axis=1)     # [J 16][V 16]
             e = [r16(self.act(v), self.fp16) for v in pre]
             for h in range(2):
                 jb = 2 * mb + h
@@ -138,6 +170,8 @@ class Warp:
                     win[jb] = r16(win[jb] + contrib, self.fp16)
                     X[jb] = r16(self.carry[jb] + win[jb][:8], self.fp16)
                     self.carry[jb] = win[jb][8:]
+        if self.sign_words is not None:
+            self.flush_signs(nb0)
 
     def emit(self, X0, X1, rows, adv):
         """Horizontal down-FIR of two blocks of 8 output rows and the masked store; advances the output cursor."""
@@ -230,10 +264,11 @@ class Warp:
 
 
 def filtered_lrelu_tc_emu(x, fu, fd, b, up, down, padding, gain, slope, clamp, flip_filter=False, fp16=False, seg_wblocks=None,
-                          preact_shape=None):
+                          preact_shape=None, sign_shape=None):
     """x: [N, C, H, W] -> y like afcm_filtered_lrelu_tc (host parameter set-up of the C entry point + launch_tc).
     preact_shape = (SH, SW): also return the pre-activation values (after the gain, before slope / clamp) the warps hold,
-    placed at their sign-tensor coordinates -> (y, pre [N, C, SH, SW]); NaN where no warp computed the sample."""
+    placed at their sign-tensor coordinates -> (y, pre [N, C, SH, SW]); NaN where no warp computed the sample.
+    sign_shape = (SH, SWB): also emulate the planned sign-write mode -> (y, signs uint8 [N, C, SH, SWB])."""
     x = np.asarray(x, np.float64)
     N, C, xh, xw = x.shape
     px0, px1, py0, py1 = padding
@@ -261,13 +296,18 @@ def filtered_lrelu_tc_emu(x, fu, fd, b, up, down, padding, gain, slope, clamp, f
     p['iy_step'] = p['seg_wblocks'] * 8 * down // up
     y = np.zeros((N, C, yh, yw))
     pre = np.full((N, C) + tuple(preact_shape), np.nan) if preact_shape else None
+    sgn = np.zeros((N, C, sign_shape[0], sign_shape[1] // 4), np.uint32) if sign_shape else None
     for n in range(N):
         for c in range(C):
             p['bias'] = 0.0 if b is None else float(b[c])
             w = Warp(G, x[n, c], y[n, c], p, fp16)
             if pre is not None:
                 w.pre_map = pre[n, c]
+            if sgn is not None:
+                w.sign_words = sgn[n, c]
             for unit in range(p['strips'] * segs):
                 w.begin_strip(unit)
                 w.run()
+    if sgn is not None:
+        return y, sgn.astype('<u4').view(np.uint8).reshape(N, C, sign_shape[0], sign_shape[1])
     return y if pre is None else (y, pre / u_scale)
