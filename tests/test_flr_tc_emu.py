@@ -83,3 +83,27 @@ def test_sign_write_mode_design(up, down, pad, H, W, seg):
     _, got = filtered_lrelu_tc_emu(x, fu, fd, b, up, down, pad, np.sqrt(2), 0.2, 1.0, seg_wblocks=seg, sign_shape=so.shape[2:])
     unpack = lambda s: np.stack([(s >> (2 * j)) & 3 for j in range(4)], -1).reshape(*s.shape[:3], -1)[..., :sw]
     assert np.array_equal(unpack(got), unpack(so))
+
+
+@pytest.mark.parametrize('up,down,pad,H,W', [(2, 2, [9, 8, 9, 8], 38, 38), (2, 2, [8, 9, 10, 7], 38, 52), (2, 4, [34, 33, 34, 33], 54, 54),
+                                             (4, 2, [-6, -9, -6, -9], 22, 26)])
+def test_sign_read_mode_design(up, down, pad, H, W):
+    """The backward pass as the planned sign-read mode: the op with up / down and the filters exchanged, the padding, gain
+    and sign offsets of OPS/filtered_lrelu.py:252-263, reading the forward's sign tensor at the fragment coordinates."""
+    rng = np.random.RandomState(H * 5 + W)
+    fu = scipy.signal.firwin(6 * up, 0.4, width=0.3, fs=2).astype(np.float32)
+    fd = scipy.signal.firwin(6 * down, 0.25, width=0.2, fs=2).astype(np.float32)
+    x = (rng.randn(1, 2, H, W) * 2).astype(np.float32)
+    y, so = orc.filtered_lrelu(x, fu, fd, None, up=up, down=down, padding=pad, gain=np.sqrt(2), slope=0.2, clamp=1.0, write_signs=True)
+    dy = rng.randn(*y.shape).astype(np.float32)
+    px0, px1, py0, py1 = pad
+    yh, yw = y.shape[2:]
+    pp = [(len(fu) - 1) + (len(fd) - 1) - px0, W * up - yw * down + px0 - (up - 1),
+          (len(fu) - 1) + (len(fd) - 1) - py0, H * up - yh * down + py0 - (up - 1)]
+    gg = np.sqrt(2) * up ** 2 / down ** 2
+    sxo, syo = -(len(fu) - 1) + px0, -(len(fu) - 1) + py0
+    ref = orc.filtered_lrelu(dy, fd, fu, None, up=down, down=up, padding=pp, gain=gg, slope=0.2, clamp=None, flip_filter=True,
+                             si=so, sx=sxo, sy=syo)
+    assert ref.shape == x.shape
+    got = filtered_lrelu_tc_emu(dy, fd, fu, None, down, up, pp, gg, 0.2, None, flip_filter=True, si=so, s_ofs=(sxo, syo))
+    assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()

@@ -43,6 +43,7 @@ class Warp:
         self.pre_map = None                                   # optional [SH][SW] map of pre-activation values (see record)
         self.sign_words = None                                # optional [SH][SWB / 4] uint32 sign tensor of the plane
         self.codes = {}
+        self.sign_in, self.sign_ofs = None, (0, 0)            # sign-read mode: uint8 [SH][SWB] of the plane, (s_ox, s_oy)
         G, p = geo, prm
         U, D = G.U, G.D
         # constant blocks (load_consts): A1[ph][J 16][X 16], B2[nb][Y 16][V 8], A3[al][W 16][V 16], B4[rel][J 16][K 8]
@@ -116,6 +117,22 @@ class Warp:
         v = np.where(v < 0, v * p['slope'], v)
         return np.clip(v, -p['act_clamp'], p['act_clamp'])
 
+    def sign_mult(self, mb, nb0, q):
+        """Sign-read mode (backward): multiplier of every fragment element of column block mb, row block nb0 + q -- slope where
+        the stored code is 1, 0 where it is 2, 1 elsewhere and outside the tensor (OPS/filtered_lrelu.cu:562-572)."""
+        G, p = self.g, self.p
+        si, (s_ox, s_oy) = self.sign_in, self.sign_ofs
+        blk = self.next_block - 1
+        m = np.ones((16, 8))
+        for j in range(16):
+            ex = G.D * self.k0 + 16 * mb + j - p['sx'] + s_ox
+            for n in range(8):
+                ey = G.D * self.w0 + 8 * G.U * (blk - 1) + 8 * (nb0 + q) + n - p['sy'] + s_oy
+                if 0 <= ey < si.shape[0] and 0 <= ex < 4 * si.shape[1]:
+                    code = (int(si[ey, ex >> 2]) >> (2 * (ex & 3))) & 3
+                    m[j, n] = p['slope'] if code == 1 else (0.0 if code >= 2 else 1.0)
+        return m
+
     def code_of(self, pre):
         """2-bit code of a pre-activation value (in units of u_scale): 1 = negative, 2 = clamped (overrides)."""
         p = self.p
@@ -155,7 +172,10 @@ class Warp:
                 self.record(mb, nb0, pre)
             if self.sign_words is not None:
                 self.codes[mb] = np.concatenate([self.code_of(pre[0]), self.code_of(pre[1])], axis=1)     # [J 16][V 16]
-            e = [r16(self.act(v), self.fp16) for v in pre]
+            if self.sign_in is not None:
+                e = [r16(v * self.sign_mult(mb, nb0, q), self.fp16) for q, v in enumerate(pre)]
+            else:
+                e = [r16(self.act(v), self.fp16) for v in pre]
             for h in range(2):
                 jb = 2 * mb + h
                 Bv = np.concatenate([e[0][8 * h:8 * h + 8, :].T, e[1][8 * h:8 * h + 8, :].T], axis=0)    # [V 16][J 8]
@@ -264,11 +284,12 @@ class Warp:
 
 
 def filtered_lrelu_tc_emu(x, fu, fd, b, up, down, padding, gain, slope, clamp, flip_filter=False, fp16=False, seg_wblocks=None,
-                          preact_shape=None, sign_shape=None):
+                          preact_shape=None, sign_shape=None, si=None, s_ofs=(0, 0)):
     """x: [N, C, H, W] -> y like afcm_filtered_lrelu_tc (host parameter set-up of the C entry point + launch_tc).
     preact_shape = (SH, SW): also return the pre-activation values (after the gain, before slope / clamp) the warps hold,
     placed at their sign-tensor coordinates -> (y, pre [N, C, SH, SW]); NaN where no warp computed the sample.
-    sign_shape = (SH, SWB): also emulate the planned sign-write mode -> (y, signs uint8 [N, C, SH, SWB])."""
+    sign_shape = (SH, SWB): also emulate the planned sign-write mode -> (y, signs uint8 [N, C, SH, SWB]).
+    si [N, C, SH, SWB], s_ofs = (sx, sy): the planned sign-read mode (the backward pass of the op)."""
     x = np.asarray(x, np.float64)
     N, C, xh, xw = x.shape
     px0, px1, py0, py1 = padding
@@ -305,6 +326,8 @@ def filtered_lrelu_tc_emu(x, fu, fd, b, up, down, padding, gain, slope, clamp, f
                 w.pre_map = pre[n, c]
             if sgn is not None:
                 w.sign_words = sgn[n, c]
+            if si is not None:
+                w.sign_in, w.sign_ofs = si[n, c], s_ofs
             for unit in range(p['strips'] * segs):
                 w.begin_strip(unit)
                 w.run()
