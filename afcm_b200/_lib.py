@@ -40,6 +40,10 @@ SIGNATURES = {
     'afcm_filtered_lrelu_tc': (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp,           # x xs xdt y ys ydt b skip
                                     _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i,        # N C xh xw yh yw fu n fd n
                                     _i, _i, _i, _i, _i, _i, _f, _f, _f, _f, _i, _vp]),  # up down pads gain slope clamp scale flip stream
+    'afcm_filtered_lrelu_t5': (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp,           # same arguments as afcm_filtered_lrelu_tc
+                                    _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i,
+                                    _i, _i, _i, _i, _i, _i, _f, _f, _f, _f, _i, _vp]),
+    'afcm_filtered_lrelu_t5_plan': (_i, [_i] * 9 + [_pi, _i]),
     'afcm_filtered_lrelu_out_size': (_i, [_i] * 10 + [_pi, _pi]),
     'afcm_filtered_lrelu_sign_size': (_i, [_i] * 4 + [_pi, _pi]),
     'afcm_filtered_lrelu_set_tile': (_i, [_i, _i]),

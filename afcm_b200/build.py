@@ -18,7 +18,7 @@ ROOT = os.path.dirname(HERE)
 OUT = os.path.join(HERE, 'libafcm_b200.so')
 OBJ = os.path.join(HERE, 'csrc', '_obj')
 
-SOURCES = ['common.cu', 'filtered_lrelu.cu', 'flr_tc.cu', 'flr_tcs.cu', 'upfirdn2d.cu', 'bias_act.cu', 'small_ops.cu', 'conv2d_simt.cu',
+SOURCES = ['common.cu', 'filtered_lrelu.cu', 'flr_tc.cu', 'flr_tcs.cu', 'flr_t5.cu', 'upfirdn2d.cu', 'bias_act.cu', 'small_ops.cu', 'conv2d_simt.cu',
            'conv2d_tc.cu', 'conv2d_bwd.cu', 'conv2d_wgrad_tc5.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC'] + os.environ.get('AFCM_NVCC_EXTRA', '').split()     # e.g. -DAFCM_FTC_MINB22=4 (tuning)

@@ -123,8 +123,29 @@ def _run_fused(x, fu, fd, b, si, up, down, px0, px1, py0, py1, sx, sy, gain, slo
     return y, so, 0
 
 
+# The tcgen05 / TMEM kernel (csrc/flr_t5.cu) is tried first by filtered_lrelu_tc() when the call qualifies (fp16 input with
+# 16-byte aligned strides, no bias); False pins the mma.sync kernel (A/B timing, tests).
+t5_enabled = True
+
+
+def padded_pitch_empty(shape, dtype, device, align_bytes=16):
+    """An [N,C,H,W] tensor whose row pitch is padded to `align_bytes` (the TMA input requirement of the tcgen05
+    filtered_lrelu: every stride a multiple of 16 bytes).  Returns the [N,C,H,W] view of the padded allocation."""
+    N, C, H, W = [int(v) for v in shape]
+    q = max(1, align_bytes // torch.empty([], dtype=dtype).element_size())
+    Wp = (W + q - 1) // q * q
+    return torch.empty([N, C, H, Wp], dtype=dtype, device=device)[..., :W]
+
+
+def t5_eligible(x, b):
+    """Whether afcm_filtered_lrelu_t5 accepts this input (the library re-checks and answers AFCM_ERR_UNSUPPORTED)."""
+    if not t5_enabled or b is not None or x.dtype != torch.float16 or x.stride(3) != 1:
+        return False
+    return x.data_ptr() % 16 == 0 and all((int(st) * 2) % 16 == 0 for st in x.stride()[:3])
+
+
 def filtered_lrelu_tc(x, fu, fd, b=None, up=1, down=1, padding=0, gain=np.sqrt(2), slope=0.2, clamp=None,
-                      flip_filter=False, skip=None, out_scale=1.0, out_dtype=None, out=None):
+                      flip_filter=False, skip=None, out_scale=1.0, out_dtype=None, out=None, impl=None):
     """Tensor-core forward of filtered_lrelu (afcm_filtered_lrelu_tc, csrc/flr_tc.cu): same arguments and
     result as filtered_lrelu() up to fp16 operand rounding (max |err| <= 2e-3 * max|y|).  Inference only (no
     autograd, no sign tensor).  `skip` is added to the result and `out_scale` multiplies it (NET:376-377,
@@ -154,6 +175,18 @@ def filtered_lrelu_tc(x, fu, fd, b=None, up=1, down=1, padding=0, gain=np.sqrt(2
         assert skip.shape == y.shape and skip.dtype == y.dtype and skip.stride() == y.stride()
     clamp = float(clamp) if clamp is not None else float('inf')
     nbytes = x.element_size() * x.numel() + y.element_size() * y.numel() * (2 if skip is not None else 1)
+    if impl == 't5' or (impl is None and t5_eligible(x, b)):
+        # tcgen05 / TMEM kernel; AFCM_ERR_UNSUPPORTED (geometry, clamp range, strides) falls through to the mma.sync kernel
+        rc = _lib.timed('filtered_lrelu', nbytes, lambda: L.afcm_filtered_lrelu_t5(
+            _lib.ptr(x), _lib.i64x4(x.stride()), _lib.dtype_code(x.dtype), _lib.ptr(y), _lib.i64x4(y.stride()),
+            _lib.dtype_code(y.dtype), _lib.ptr(b), _lib.ptr(skip), N, C, xh, xw, yh, yw,
+            _lib.np_ptr(fu_h), fu_n, _lib.np_ptr(fd_h), fd_n, up, down, px0, px1, py0, py1,
+            float(gain), float(slope), clamp, float(out_scale), int(bool(flip_filter)), _lib.stream_ptr(x.device)))
+        _lib.check(rc, allow_unsupported=True)
+        if rc == 0:
+            return y
+        if impl == 't5':
+            return None
     rc = _lib.timed('filtered_lrelu', nbytes, lambda: L.afcm_filtered_lrelu_tc(
         _lib.ptr(x), _lib.i64x4(x.stride()), _lib.dtype_code(x.dtype), _lib.ptr(y), _lib.i64x4(y.stride()),
         _lib.dtype_code(y.dtype), _lib.ptr(b), _lib.ptr(skip), N, C, xh, xw, yh, yw,

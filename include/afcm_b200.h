@@ -101,6 +101,26 @@ int afcm_filtered_lrelu_tc(const void* x, const int64_t* xs, int x_dtype, void* 
  * at most n resident waves of CTAs (default 16, the measured optimum); 0 = one warp per 16-column strip. */
 int afcm_filtered_lrelu_tc_set_waves(int waves);
 
+/* filtered_lrelu on tcgen05 / tensor memory (afcm_b200/csrc/flr_t5.cu): the Blackwell-native inference kernel.  Replaces
+ * the same reference entry point as afcm_filtered_lrelu (filtered_lrelu_plugin.filtered_lrelu, OPS/filtered_lrelu.cpp:16-209,
+ * kernel OPS/filtered_lrelu.cu:139-1099) for the fast path: same arguments as afcm_filtered_lrelu_tc.  Input rows arrive by
+ * TMA, every FIR pass is a banded-Toeplitz tcgen05.mma with the image tile resident in tensor memory.  Requirements (else
+ * AFCM_ERR_UNSUPPORTED, and the caller falls back to afcm_filtered_lrelu_tc): x fp16 with a 16-byte aligned base and
+ * row / channel / sample strides that are multiples of 8 elements (pad the row pitch), no bias (b == NULL: the convolution
+ * epilogue adds it), (up,down) in {(2,2),(4,2),(2,4)} with 6*up / 6*down taps, clamp in [2^-10, 2^10]; y fp16 or fp32, any
+ * strides with ys[3] == 1; skip (same dtype / strides as y) is added as skip * out_scale.  Tolerance: 2e-3 of max|y|. */
+int afcm_filtered_lrelu_t5(const void* x, const int64_t* xs, int x_dtype, void* y, const int64_t* ys, int y_dtype,
+                           const float* b, const void* skip,
+                           int N, int C, int xh, int xw, int yh, int yw,
+                           const float* fu_host, int fu_taps, const float* fd_host, int fd_taps,
+                           int up, int down, int px0, int px1, int py0, int py1,
+                           float gain, float slope, float clamp, float out_scale, int flip_filter,
+                           void* stream);
+/* The plan afcm_filtered_lrelu_t5 would use (host only, no device access; not part of the stable ABI): fills `out` with
+ * the fields of afcm::T5Plan (afcm_b200/csrc/flr_t5_plan.h), kw = 0 selects the strip width automatically.  Used by the
+ * CPU-tier emulation test of the kernel's index algebra. */
+int afcm_filtered_lrelu_t5_plan(int xh, int xw, int up, int down, int px0, int px1, int py0, int py1, int kw, int* out, int n_out);
+
 /* Tensor-core filtered_lrelu WITH the sign tensor (afcm_b200/csrc/flr_tcs.cu): the training-step variant.  Same
  * arguments, sign-tensor format and sign_mode meaning as afcm_filtered_lrelu, so forward (SIGN_WRITE) and backward
  * (SIGN_READ, up/down exchanged by the caller as in OPS/filtered_lrelu.py:252-266) interoperate with the exact kernel.
