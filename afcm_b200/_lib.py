@@ -44,6 +44,7 @@ SIGNATURES = {
                                     _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i,
                                     _i, _i, _i, _i, _i, _i, _f, _f, _f, _f, _i, _vp]),
     'afcm_filtered_lrelu_t5_plan': (_i, [_i] * 9 + [_pi, _i]),
+    'afcm_filtered_lrelu_t5_trace': (_i, [_vp]),
     'afcm_filtered_lrelu_out_size': (_i, [_i] * 10 + [_pi, _pi]),
     'afcm_filtered_lrelu_sign_size': (_i, [_i] * 4 + [_pi, _pi]),
     'afcm_filtered_lrelu_set_tile': (_i, [_i, _i]),

@@ -42,6 +42,7 @@ constexpr int T5_STAGES = 3;
 constexpr int T5_RING_ROWS = 256;
 constexpr int T5_RING_HALF = T5_RING_ROWS * 128;        // bytes of one 64-column block of the ring
 constexpr int T5_TMEM_COLS = 512;
+constexpr int T5_OUT_BYTES = 64 * 128 * 2;              // staging tile of the output rows of one step
 constexpr int T5_C_TUY = 0, T5_C_D1 = 40, T5_C_D2 = 168, T5_C_D3 = 296, T5_C_D4 = 432;
 
 struct T5Params {
@@ -51,6 +52,7 @@ struct T5Params {
     int ys_h, y_f32;
     int C, total_units;
     float slope, out_scale;
+    long long* trace;                                   // development aid: per-role (code, clock) records of CTA 0, or null
     float kux[24], kuy[24], kdx[24], kdy[24];           // correlation-form taps (scales folded in, see the launcher)
 };
 
@@ -76,6 +78,18 @@ __device__ __forceinline__ uint32_t t5_act(uint32_t lo_bits, uint32_t hi_bits, u
     return o;
 }
 
+// Timeline records of CTA 0 (afcm_filtered_lrelu_t5_trace): role r (0 TMA, 1 MMA, 2 / 3 epilogue groups) appends one word per
+// event (code << 48 | clock64) to trace[r * 2048 ...]; the host zeroes the buffer beforehand.
+constexpr int T5_TRACE_SLOTS = 2048;
+struct T5Trace {
+    long long* base; int n;
+    __device__ T5Trace(long long* t, int role) : base(t && blockIdx.x == 0 ? t + role * T5_TRACE_SLOTS : nullptr), n(0) {}
+    __device__ __forceinline__ void mark(int code)
+    {
+        if (base && n < T5_TRACE_SLOTS) base[n++] = ((long long)code << 48) | (clock64() & 0xffffffffffffLL);
+    }
+};
+
 template <int U, int D>
 __global__ void __launch_bounds__(T5_THREADS, 1)
 flr_t5_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ T5Params p)
@@ -99,7 +113,8 @@ flr_t5_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     uint8_t* s_zero = s_t2 + T2_BYTES;
     uint8_t* s_t3 = s_zero + ZERO_BYTES;
     uint8_t* s_t4 = s_t3 + T3_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_t4 + (NL + 1) * T4_BYTES);
+    __half* s_out = reinterpret_cast<__half*>(s_t4 + (NL + 1) * T4_BYTES);     // [OS output rows][128 columns] staging of E3
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_out) + T5_OUT_BYTES);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + T5B_COUNT);
     float* s_taps = reinterpret_cast<float*>(tmem_slot + 2);          // [4][24]: kux, kuy, kdx, kdy
 
@@ -173,6 +188,7 @@ flr_t5_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     if (warp == 0) {
         // ================================================= TMA producer =================================================
         if (lane == 0) {
+            T5Trace tr(p.trace, 0);
             int stage = 0; uint32_t phase = 0;
             for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
                 const int plane = unit / pl.nstrips, strip = unit - plane * pl.nstrips;
@@ -180,10 +196,12 @@ flr_t5_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                 const int x0 = pl.iorg0 + pl.istep * strip;
                 for (int s = 0; s < nsteps; s++) {
                     mbar_wait(&bars[T5B_IN_EMPTY + stage], phase ^ 1);
+                    tr.mark(1);
                     mbar_expect_tx(&bars[T5B_IN_FULL + stage], (uint32_t)stage_bytes);
                     for (int h = 0; h < halves; h++)
                         tma_load_4d(s_in + stage * stage_bytes + h * K1 * 128, &map_x, &bars[T5B_IN_FULL + stage], x0 + 64 * h,
                                     pl.I0y + RS * s, c, n);
+                    tr.mark(2);
                     if (++stage == T5_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -203,12 +221,14 @@ flr_t5_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         const uint32_t tm_d3 = tmem_base + T5_C_D3, tm_d4 = tmem_base + T5_C_D4;
         uint32_t T = 0, nb[2] = {0u, 0u};
         int stage = 0; uint32_t in_phase = 0;
+        T5Trace tr(lane == 0 ? p.trace : nullptr, 1);
 
         // P4 of global step Tp (its rows sit in ring half Tp & 1; the lead rows at the end of the other half)
         auto issue_p4 = [&](uint32_t Tp, bool first_step_of_unit) {
             mbar_wait(&bars[T5B_E2_DONE], Tp & 1);
             if (Tp >= 1) mbar_wait(&bars[T5B_D4_EMPTY], (Tp - 1) & 1);
             tc_fence_after();
+            tr.mark(40);
             if (elect_one()) {
                 const uint32_t rows = ring_base + (uint32_t)((Tp & 1) * 128 * 128);
                 const uint32_t prev = ring_base + (uint32_t)(((Tp & 1) ^ 1) * 128 * 128);
@@ -230,6 +250,7 @@ flr_t5_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                 umma_commit(&bars[T5B_D4_FULL]);
             }
             __syncwarp();
+            tr.mark(41);
         };
         // P3 of group gg of the current step
         auto issue_p3 = [&](int gg, bool last) {
@@ -237,6 +258,7 @@ flr_t5_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
             mbar_wait(&bars[T5B_A3_FULL + bb], (nb[bb] - 1) & 1);
             if (gg == 0 && T > 0) mbar_wait(&bars[T5B_E2_DONE], (T - 1) & 1);          // D3 of the previous step has been read
             tc_fence_after();
+            tr.mark(30 + gg);
             if (elect_one()) {
                 const uint32_t a3 = tm_d2 + 64 * bb, d3 = tm_d3 + ADV * 4 * gg;
                 if (gg == 0) umma_f16_ts(tm_d3, a3, zero_lo, TC_DESC_HI, id_p3, false);
@@ -255,6 +277,7 @@ flr_t5_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                 if (last) umma_commit(&bars[T5B_D3_FULL]);
             }
             __syncwarp();
+            tr.mark(35 + gg);
         };
 
         bool prev_first = false;
@@ -264,6 +287,7 @@ flr_t5_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                 mbar_wait(&bars[T5B_IN_FULL + stage], in_phase);
                 if (T > 0) mbar_wait(&bars[T5B_P2_DONE], (T - 1) & 1);                 // D1 of the previous step has been read
                 tc_fence_after();
+                tr.mark(10);
                 if (elect_one()) {
                     const uint32_t sb = in_base + (uint32_t)(stage * stage_bytes);
 #pragma unroll
@@ -274,12 +298,15 @@ flr_t5_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                 }
                 __syncwarp();
                 if (++stage == T5_STAGES) { stage = 0; in_phase ^= 1; }
+                tr.mark(11);
                 mbar_wait(&bars[T5B_D1_FULL], T & 1);
                 tc_fence_after();
+                tr.mark(12);
                 // ---- groups of 64 up-sampled columns: P2 (g), P3 (g - 1); P4 of the previous step after the second P2
                 for (int g = 0; g < NG; g++) {
                     const int b = g & 1;
                     if (nb[b] > 0) { mbar_wait(&bars[T5B_P3_DONE + b], (nb[b] - 1) & 1); tc_fence_after(); }
+                    tr.mark(20 + g);
                     if (elect_one()) {
                         const uint32_t d2 = tm_d2 + 64 * b, a1 = tm_d1 + 8 * QPG * g;
                         // init set: lead (upper half of the previous chunk's window; group 0: zeros), odd full chunks, tail (lower half)
@@ -294,6 +321,7 @@ flr_t5_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                         if (g == NG - 1) umma_commit(&bars[T5B_P2_DONE]);
                     }
                     __syncwarp();
+                    tr.mark(25 + g);
                     nb[b]++;
                     if (T > 0 && g == (NG > 1 ? 1 : 0)) issue_p4(T - 1, prev_first);
                     if (g >= 1) issue_p3(g - 1, false);
@@ -315,10 +343,17 @@ flr_t5_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         { __half2 t = __floats2half2_rn(-p.slope, -p.slope); h_nslope = *reinterpret_cast<uint32_t*>(&t); }
         uint32_t T = 0, nuse = 0;
         int pv_plane = 0, pv_strip = 0, pv_s = 0;
+        T5Trace tr((quad == 0 && lane == 0) ? p.trace : nullptr, 2 + wg);
 
+        // E3: D4 (lanes = output columns, TMEM columns = output rows) -> transposed fp16 staging tile in shared memory -> rows
+        // written with 8-byte stores (a warp covers a whole row of the strip); the skip tensor is added on the way out.
+        const int ew = warp - 4;
+        const bool vec_ok = !p.y_f32 && ((p.ys_h | (int)(p.ys_c & 3) | (int)(p.ys_n & 3)) & 3) == 0 && (((uintptr_t)p.y | (uintptr_t)p.skip) & 7) == 0 &&
+                            (pl.KW & 3) == 0 && (pl.yw & 3) == 0;
         auto e3 = [&](uint32_t Tp, int plane, int strip, int s) {
             mbar_wait(&bars[T5B_D4_FULL], Tp & 1);
             tc_fence_after();
+            tr.mark(70);
             constexpr int NC = OS / 2;                            // D4 columns (output rows) per group: 32 or 16
             uint32_t r[NC];
             if constexpr (NC == 32) tmem_ld32(lane_base + T5_C_D4 + NC * wg, r);
@@ -326,24 +361,46 @@ flr_t5_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(&bars[T5B_D4_EMPTY]);
-            const int k = pl.korg0 + pl.KW * strip + m;
-            const bool mok = m >= pl.m0 && m < pl.m0 + pl.KW && k < pl.yw;
-            if (mok) {
-                const int n = plane / p.C, c = plane - n * p.C;
-                const long long pofs = n * p.ys_n + c * p.ys_c + k;
-                const int w0 = OS * s + pl.wlo0 + NC * wg;
+            asm volatile("bar.sync 1, 256;" ::: "memory");       // the staging tile of the previous step has been read
+            const int col = m - pl.m0;
+            if (col >= 0 && col < pl.KW) {
+                __half* so = s_out + (NC * wg) * 128 + col;
 #pragma unroll
-                for (int j = 0; j < NC; j++) {
-                    const int w = w0 + j;
-                    if (w >= 0 && w < pl.yh) {
-                        const long long o = pofs + (long long)w * p.ys_h;
-                        float v = __uint_as_float(r[j]);
-                        if (p.y_f32) {
-                            if (p.skip) v += reinterpret_cast<const float*>(p.skip)[o] * p.out_scale;
-                            reinterpret_cast<float*>(p.y)[o] = v;
-                        } else {
-                            if (p.skip) v += __half2float(reinterpret_cast<const __half*>(p.skip)[o]) * p.out_scale;
-                            reinterpret_cast<__half*>(p.y)[o] = __float2half_rn(v);
+                for (int j = 0; j < NC; j++) so[j * 128] = __float2half_rn(__uint_as_float(r[j]));
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const int k0 = pl.KW * strip;
+            const int kwv = min(pl.KW, pl.yw - k0);
+            const int n = plane / p.C, c = plane - n * p.C;
+            const long long pofs = n * p.ys_n + c * p.ys_c + k0;
+            const int cc = 4 * lane;
+            if (cc < kwv) {
+                for (int rr = ew; rr < OS; rr += 8) {
+                    const int w = OS * s + pl.wlo0 + rr;
+                    if (w < 0 || w >= pl.yh) continue;
+                    const long long o = pofs + (long long)w * p.ys_h + cc;
+                    const uint2 v = *reinterpret_cast<const uint2*>(s_out + rr * 128 + cc);
+                    if (vec_ok) {
+                        uint2 outv = v;
+                        if (p.skip) {
+                            const uint2 sk = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(p.skip) + o);
+                            const __half2 sc = __floats2half2_rn(p.out_scale, p.out_scale);
+                            __half2 a0 = __hfma2(*reinterpret_cast<const __half2*>(&sk.x), sc, *reinterpret_cast<const __half2*>(&v.x));
+                            __half2 a1 = __hfma2(*reinterpret_cast<const __half2*>(&sk.y), sc, *reinterpret_cast<const __half2*>(&v.y));
+                            outv.x = *reinterpret_cast<uint32_t*>(&a0); outv.y = *reinterpret_cast<uint32_t*>(&a1);
+                        }
+                        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.y) + o) = outv;
+                    } else {
+                        const __half* hv = reinterpret_cast<const __half*>(&v);
+                        for (int e = 0; e < 4 && cc + e < kwv; e++) {
+                            float f = __half2float(hv[e]);
+                            if (p.y_f32) {
+                                if (p.skip) f += reinterpret_cast<const float*>(p.skip)[o + e] * p.out_scale;
+                                reinterpret_cast<float*>(p.y)[o + e] = f;
+                            } else {
+                                if (p.skip) f += __half2float(reinterpret_cast<const __half*>(p.skip)[o + e]) * p.out_scale;
+                                reinterpret_cast<__half*>(p.y)[o + e] = __float2half_rn(f);
+                            }
                         }
                     }
                 }
@@ -353,10 +410,13 @@ flr_t5_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
             const int plane = unit / pl.nstrips, strip = unit - plane * pl.nstrips;
             for (int s = 0; s < nsteps; s++) {
-                // ---- E1: activation of this group's D2 buffers (in place: 64 fp32 columns -> 32 packed half2 columns)
+                // ---- E1: activation of this group's D2 buffers (in place: 64 fp32 columns -> 32 packed half2 columns); the output
+                // rows of the previous step (E3, its P4 is issued right after the second P2 of this step) go out after the first one
+                bool e3_done = T == 0;
                 for (int g = wg; g < NG; g += 2) {
                     mbar_wait(&bars[T5B_D2_FULL + wg], nuse & 1);
                     tc_fence_after();
+                    tr.mark(50 + g);
                     const uint32_t d2 = lane_base + T5_C_D2 + 64 * wg;
                     uint32_t ra[32], rb[32], o[16];
                     tmem_ld32(d2, ra);
@@ -371,11 +431,15 @@ flr_t5_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                     tmem_st_wait();
                     tc_fence_before();
                     mbar_arrive(&bars[T5B_A3_FULL + wg]);
+                    tr.mark(55 + g);
                     nuse++;
+                    if (!e3_done) { e3(T - 1, pv_plane, pv_strip, pv_s); tr.mark(71); e3_done = true; }
                 }
+                if (!e3_done) { e3(T - 1, pv_plane, pv_strip, pv_s); tr.mark(71); }
                 // ---- E2: D3 columns [64 wg, 64 wg + 64) of this step -> ring rows (fp16, SWIZZLE_128B rows of 64 columns)
                 mbar_wait(&bars[T5B_D3_FULL], T & 1);
                 tc_fence_after();
+                tr.mark(60);
                 {
                     const int row = (int)((T & 1) * 128) + m;
                     uint8_t* rbase = s_ring + wg * T5_RING_HALF;
@@ -398,8 +462,7 @@ flr_t5_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                 fence_proxy_async();
                 tc_fence_before();
                 mbar_arrive(&bars[T5B_E2_DONE]);
-                // ---- E3 of the previous step (its P4 was issued during this step)
-                if (T > 0) e3(T - 1, pv_plane, pv_strip, pv_s);
+                tr.mark(61);
                 pv_plane = plane; pv_strip = strip; pv_s = s;
                 T++;
             }
@@ -416,12 +479,14 @@ flr_t5_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     }
 }
 
+static long long* g_t5_trace = nullptr;
+
 template <int U, int D>
 static int launch_t5(const CUtensorMap& map, const T5Params& p, cudaStream_t st)
 {
     constexpr int K1 = 128 / U + 16, NL = (6 * D - 1 + 15) / 16;
     const int smem = 1024 + T5_STAGES * p.pl.halves * K1 * 128 + 2 * T5_RING_HALF + 16 * U * 128 + 4096 + 2048 + (NL + 1) * 2048 +
-                     T5B_COUNT * 8 + 16 + 96 * 4;
+                     T5_OUT_BYTES + T5B_COUNT * 8 + 16 + 96 * 4;
     if (smem > max_smem_optin()) { set_error("filtered_lrelu_t5: %d bytes of shared memory needed", smem); return AFCM_ERR_UNSUPPORTED; }
     static int configured = 0;
     if (configured < smem) {
@@ -438,6 +503,10 @@ static int launch_t5(const CUtensorMap& map, const T5Params& p, cudaStream_t st)
 }  // namespace afcm
 
 using namespace afcm;
+
+// Development aid (not part of the stable ABI): device buffer of 4 * 2 * 1024 int64 that CTA 0 of the following launches
+// fills with (code, clock64) records per role (0 TMA, 1 MMA issuer, 2 / 3 epilogue groups; [0] = count); NULL switches it off.
+extern "C" int afcm_filtered_lrelu_t5_trace(void* dev_buffer) { g_t5_trace = (long long*)dev_buffer; return AFCM_OK; }
 
 extern "C" int afcm_filtered_lrelu_t5_plan(int xh, int xw, int up, int down, int px0, int px1, int py0, int py1, int kw, int* out, int n_out)
 {
@@ -485,6 +554,7 @@ extern "C" int afcm_filtered_lrelu_t5(const void* x, const int64_t* xs, int x_dt
     AFCM_CHECK_ARG(units < 0x7fffffffLL, "too many strips");
     p.total_units = (int)units;
     p.slope = slope; p.out_scale = out_scale;
+    p.trace = g_t5_trace;
     // the activation runs in units of `clamp`:  clamp(lrelu(u gain)) / clamp = sat(u') - sat(-slope u'),  u' = u gain / clamp
     const float u_scale = 1.f / clamp;
     for (int t = 0; t < fu_taps; t++) {

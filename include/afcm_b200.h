@@ -120,6 +120,9 @@ int afcm_filtered_lrelu_t5(const void* x, const int64_t* xs, int x_dtype, void* 
  * the fields of afcm::T5Plan (afcm_b200/csrc/flr_t5_plan.h), kw = 0 selects the strip width automatically.  Used by the
  * CPU-tier emulation test of the kernel's index algebra. */
 int afcm_filtered_lrelu_t5_plan(int xh, int xw, int up, int down, int px0, int px1, int py0, int py1, int kw, int* out, int n_out);
+/* Development aid (not part of the stable ABI): a device buffer of 4 x 2048 int64 that CTA 0 of the following
+ * afcm_filtered_lrelu_t5 launches fills with (event code, clock64) records per warp role; NULL switches tracing off. */
+int afcm_filtered_lrelu_t5_trace(void* dev_buffer);
 
 /* Tensor-core filtered_lrelu WITH the sign tensor (afcm_b200/csrc/flr_tcs.cu): the training-step variant.  Same
  * arguments, sign-tensor format and sign_mode meaning as afcm_filtered_lrelu, so forward (SIGN_WRITE) and backward

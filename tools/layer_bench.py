@@ -97,8 +97,15 @@ def main():
                 x = x.half()
             if 'nobias' in ops:
                 b = None
+            impl = 'tc'
+            if 't5' in ops:                       # the tcgen05 / TMEM kernel: fp16 planes with a 16-byte aligned row pitch, no bias
+                from afcm_b200.torch_utils.ops.filtered_lrelu import padded_pitch_empty
+                xv = padded_pitch_empty(x.shape, torch.float16, dev)
+                xv.copy_(x)
+                x, b, impl = xv, None, 't5'
             fn = lambda: filtered_lrelu_tc(x, L.up_filter, L.down_filter, b, up=L.up_factor, down=L.down_factor,
-                                           padding=L.padding, gain=float(np.sqrt(2)), slope=0.2, clamp=256.0, out_dtype=out_dt)
+                                           padding=L.padding, gain=float(np.sqrt(2)), slope=0.2, clamp=256.0, out_dtype=out_dt, impl=impl)
+            assert fn() is not None
             ms = time_cuda(fn, flush=flush)
             nbytes = float(B * cout * (x.element_size() * Hc * Hc + (2 if out_dt == torch.float16 else 4) * out * out))
             row.update(flrelu_tc_ms=ms, flrelu_tc_gbs=nbytes / ms / 1e6, flrelu_tc_frac=nbytes / ms / 1e6 / hbm)
