@@ -59,6 +59,7 @@ SIGNATURES = {
     'afcm_conv_tc_plane_elems': (_i64, [_i, _i, _i]),
     'afcm_conv_tc_pack': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'afcm_conv2d_tc': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    'afcm_conv2d_tc_nchw': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     'afcm_plane_dot_scale': (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
     'afcm_plane_sum': (_i, [_vp, _vp, _i64, _i64, _vp]),
     'afcm_conv2d_wgrad_f32': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
@@ -78,6 +79,36 @@ SIGNATURES = {
 }
 
 _lib = None
+_call_device = None          # device index of the tensors of the native call being assembled (set by stream_ptr())
+
+
+class _DeviceGuarded:
+    """The loaded library with a device guard around every entry point.  The C entry points launch on the calling thread's
+    CURRENT device (cudaFuncSetAttribute, occupancy queries and the launch itself), while the stream handed to them belongs
+    to the tensors' device: when the two differ the call is wrapped in `torch.cuda.device(...)` -- what OptionalCUDAGuard
+    does in the reference plugins (OPS/filtered_lrelu.cpp:22).  The tensors' device is the one stream_ptr() was last asked
+    for, which every wrapper evaluates while it assembles the arguments of its call."""
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+        self._fns = {}
+
+    def __getattr__(self, name):
+        fn = self._fns.get(name)
+        if fn is None:
+            raw = getattr(self._cdll, name)
+
+            def fn(*args, _raw=raw):
+                global _call_device
+                dev, _call_device = _call_device, None
+                if dev is not None:
+                    import torch
+                    if dev != torch.cuda.current_device():
+                        with torch.cuda.device(dev):
+                            return _raw(*args)
+                return _raw(*args)
+            self._fns[name] = fn
+        return fn
 
 
 def lib():
@@ -94,7 +125,7 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        _lib = L
+        _lib = _DeviceGuarded(L)
     return _lib
 
 
@@ -127,7 +158,12 @@ def ptr(t):
 
 
 def stream_ptr(device=None):
+    """Raw handle of torch's current stream on `device`; also notes the device for the guard around the native call."""
     import torch
+    global _call_device
+    if device is not None:
+        device = torch.device(device)
+        _call_device = device.index if device.index is not None else torch.cuda.current_device()
     return torch.cuda.current_stream(device).cuda_stream
 
 

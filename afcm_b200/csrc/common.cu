@@ -26,18 +26,27 @@ static int device_attr(cudaDeviceAttr attr)
     return v;
 }
 
+// attribute caches are per device: a process may drive several GPUs (DataParallel-style callers, `device=` arguments)
+static int cached_attr(int (&cache)[64], cudaDeviceAttr attr)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return device_attr(attr);
+    if (!cache[dev]) cache[dev] = device_attr(attr);
+    return cache[dev];
+}
+
 int sm_count()
 {
-    static int v = 0;
-    if (!v) v = device_attr(cudaDevAttrMultiProcessorCount);
-    return v > 0 ? v : 148;
+    static int v[64] = {0};
+    const int r = cached_attr(v, cudaDevAttrMultiProcessorCount);
+    return r > 0 ? r : 148;
 }
 
 int max_smem_optin()
 {
-    static int v = 0;
-    if (!v) v = device_attr(cudaDevAttrMaxSharedMemoryPerBlockOptin);
-    return v > 0 ? v : 232448;
+    static int v[64] = {0};
+    const int r = cached_attr(v, cudaDevAttrMaxSharedMemoryPerBlockOptin);
+    return r > 0 ? r : 232448;
 }
 
 }  // namespace afcm

@@ -23,6 +23,13 @@
 //     warps 4-7 epilogue (tcgen05.ld -> demodulation scale -> coalesced NCHW fp32 stores)
 //   * persistent CTAs (one per SM), static tile striding, output-channel tiles innermost so CTAs that
 //     run concurrently share their activation tiles in L2.
+//   * ASW variant (afcm_conv2d_tc_nchw): the A operand is built IN the kernel from the fp16 NCHW planes the preceding
+//     filtered_lrelu wrote -- no packed copy of the activations exists.  Eight producer warps (12-19) read aligned pixel
+//     pairs of 8 channels x 8 pixels per warp instruction, transpose them in registers (movmatrix.m8n8.trans.b16), apply the
+//     modulation coefficient in fp32 and store the words straight into the K-major SWIZZLE_128B tile the tensor core reads
+//     (the swizzle makes the 32 stores of a warp hit 32 different banks), then fence.proxy.async + mbarrier arrive.  The
+//     row pitch W+2 of the flat-plane formulation is virtual: flat pixel p = y (W+2) + x lives at element p - 2y of the
+//     plane, x >= W and rows outside the plane are zeros.
 #include <cuda.h>
 #include "afcm_common.cuh"
 #include "tc_ptx.cuh"
@@ -33,6 +40,9 @@ constexpr int TC_BM = 128;            // pixels per tile (UMMA M)
 constexpr int TC_BK = 64;             // channels per pipeline stage
 constexpr int TC_MAX_STAGES = 8;      // pipeline depth is chosen per launch: small channel tiles need more stages in flight
 constexpr int TC_THREADS = 384;         // warps 0-3: TMA producer, MMA issuer, TMEM allocator, idle; warps 4-11: two epilogue groups
+constexpr int TC_ASW_WARPS = 8;         // ASW variant: warps 12-19 build the A tiles from NCHW planes (one 8-channel block each)
+constexpr int TC_ASW_THREADS = TC_THREADS + 32 * TC_ASW_WARPS;
+constexpr int TC_AROW_BLKS = 17;        // 8-pixel blocks of a row-reuse A tile (TC_AROW_PX / 8)
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;          // 16 KB
 constexpr int TC_AROW_PX = TC_BM + 8;                  // row-reuse mode: 128 pixels + the two pixels to the right, rounded to 8
 constexpr int TC_AROW_BYTES = TC_AROW_PX * TC_BK * 2;  // 17 KB
@@ -51,12 +61,18 @@ struct TcParams {
     int a_stages;                          // mode 2: depth of the A ring (`stages` is the depth of the B ring)
     int bres;                              // 1 (row-reuse mode, single channel tile): all weight tiles stay resident in shared memory
     unsigned idesc;
+    const __half* xn;       // ASW: [N, Ci, H, W] fp16 activations (NCHW, contiguous)
+    const float* icoef;     // ASW: [N, Ci] modulation coefficients or null
     unsigned* dbg;          // mapped host memory for progress markers (AFCM_TC_DEBUG), or null
     int dbg_mode;           // debug bisection switches (see afcm_conv_tc_debug_buffer)
 };
 
+__device__ __forceinline__ uint32_t pack_tc(float lo, float hi, __half*);
+__device__ __forceinline__ uint32_t pack_tc(float lo, float hi, __nv_bfloat16*);
+
 // ---- the kernel --------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <bool ASW>
+__global__ void __launch_bounds__(ASW ? TC_ASW_THREADS : TC_THREADS, 1)
 conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ TcParams p)
 {
@@ -87,10 +103,13 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&map_b) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        // ASW: an A tile is complete when every producer warp has arrived (+ the TMA thread's expect_tx arrive where the stage
+        // also carries weight tiles)
+        const uint32_t full_count = !ASW ? 1u : (p.rowreuse == 2 ? 1u : (p.bres ? (uint32_t)TC_ASW_WARPS : (uint32_t)TC_ASW_WARPS + 1u));
+        for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], full_count); mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
         mbar_init(bfull, 1);
-        for (int a = 0; a < 4; a++) { mbar_init(&afull[a], 1); mbar_init(&aempty[a], 1); }
+        for (int a = 0; a < 4; a++) { mbar_init(&afull[a], ASW ? (uint32_t)TC_ASW_WARPS : 1u); mbar_init(&aempty[a], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -125,10 +144,12 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     const int p0 = mt * TC_BM, o0 = nt * p.BN;
                     for (int ky = 0; ky < 3; ky++) {
                         for (int cb = 0; cb < p.cblocks; cb++) {
-                            mbar_wait(&aempty[as], aph ^ 1, p.dbg, 0x600u | (unsigned)as);
-                            mbar_expect_tx(&afull[as], (uint32_t)TC_AROW_BYTES);
-                            tma_load_3d(smem + as * TC_AROW_BYTES, &map_a2, &afull[as], cb * TC_BK, p0 + (ky - p.pad) * p.Wp - p.pad, n);
-                            if (++as == p.a_stages) { as = 0; aph ^= 1; }
+                            if (!ASW) {
+                                mbar_wait(&aempty[as], aph ^ 1, p.dbg, 0x600u | (unsigned)as);
+                                mbar_expect_tx(&afull[as], (uint32_t)TC_AROW_BYTES);
+                                tma_load_3d(smem + as * TC_AROW_BYTES, &map_a2, &afull[as], cb * TC_BK, p0 + (ky - p.pad) * p.Wp - p.pad, n);
+                                if (++as == p.a_stages) { as = 0; aph ^= 1; }
+                            }
                             for (int kx = 0; kx < 3; kx++) {
                                 mbar_wait(&empty[stage], phase ^ 1, p.dbg, 0x100u | (unsigned)stage);
                                 mbar_expect_tx(&full[stage], (uint32_t)b_bytes);
@@ -146,6 +167,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 const int p0 = mt * TC_BM, o0 = nt * p.BN;
                 for (int kb = 0; kb < ((p.dbg_mode & 8) ? min(kblocks, p.stages) : kblocks); kb++) {
                     if (p.bres) {
+                        if (ASW) break;                                  // the stage holds the A tile only: nothing for TMA to do
                         const int ky = kb / p.cblocks, cb = kb - ky * p.cblocks;
                         mbar_wait(&empty[stage], phase ^ 1, p.dbg, 0x100u | (unsigned)stage);
                         mbar_expect_tx(&full[stage], (uint32_t)TC_AROW_BYTES);
@@ -159,8 +181,8 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         const int ky = kb / p.cblocks, cb = kb - ky * p.cblocks;
                         mbar_wait(&empty[stage], phase ^ 1, p.dbg, 0x100u | (unsigned)stage);
                         uint8_t* sa = ring + stage * stage_bytes;
-                        mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
-                        tma_load_3d(sa, &map_a2, &full[stage], cb * TC_BK, p0 + (ky - p.pad) * p.Wp - p.pad, n);
+                        mbar_expect_tx(&full[stage], (uint32_t)(ASW ? stage_bytes - TC_AROW_BYTES : stage_bytes));
+                        if (!ASW) tma_load_3d(sa, &map_a2, &full[stage], cb * TC_BK, p0 + (ky - p.pad) * p.Wp - p.pad, n);
 #pragma unroll
                         for (int kx = 0; kx < 3; kx++)
                             tma_load_3d(sa + TC_AROW_BYTES + kx * b_bytes, &map_b, &full[stage], cb * TC_BK, o0, ky * 3 + kx);
@@ -285,7 +307,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
-    } else if (warp >= 4 && !(p.dbg_mode & 8)) {
+    } else if (warp >= 4 && warp < 12 && !(p.dbg_mode & 8)) {
         // ================= epilogue =================
         // Two groups of four warps (one warp per TMEM lane quadrant each) take alternate 32-channel column chunks of
         // the accumulator: with small channel tiles the store loop, not the MMA, bounds the tile time.
@@ -358,6 +380,71 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             if (lane == 0) mbar_arrive(&tempty[acc]);
             if (blockIdx.x == 0 && et == 0) dbg_mark(p.dbg, 4, (unsigned)tile + 1);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    if (ASW && warp >= 12) {
+        // ================= A-tile producers (ASW): NCHW fp16 planes -> K-major SWIZZLE_128B tile =================
+        // Warp pw owns the 8-channel block pw of the 64-channel stage (= 16-byte chunk pw of every tile row).  Per block of
+        // 8 pixels: lane (r8, q) loads the pixel pair 2q of channel r8 (4 bytes), the warp transposes the 8 x 8 block of
+        // 16-bit words, after which the lane holds the channel pair 2q of pixel r8 -- one 32-bit word of tile row r8.
+        const int pw = warp - 12, q = lane & 3, r8 = lane >> 2;
+        const uint32_t off_lane = (uint32_t)(r8 * 128 + ((pw ^ r8) << 4) + 4 * q);      // the tile row index is 8 blk + r8: (row & 7) == r8
+        const bool two_rings = p.rowreuse == 2;
+        const int nst = two_rings ? p.a_stages : p.stages;
+        const int sbytes = two_rings ? TC_AROW_BYTES : stage_bytes;
+        uint8_t* abase = two_rings ? smem : ring;
+        uint64_t* fullb = two_rings ? afull : full;
+        uint64_t* emptyb = two_rings ? aempty : empty;
+        const long long plane = (long long)p.H * p.W;
+        const unsigned HWp = (unsigned)(p.H * p.Wp);
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const int r = tile / p.n_tiles;
+            const int mt = r % p.m_tiles, n = r / p.m_tiles;
+            const int p0 = mt * TC_BM;
+            for (int ky = 0; ky < 3; ky++) {
+                for (int cb = 0; cb < p.cblocks; cb++) {
+                    const int cl = cb * TC_BK + 8 * pw + r8;                       // channel this lane LOADS
+                    const bool c_ok = cl < p.Ci;
+                    const __half* src = p.xn + ((long long)n * p.Ci + (c_ok ? cl : 0)) * plane;
+                    int pp = p0 + (ky - p.pad) * p.Wp - p.pad + 2 * q;            // flat pixel of this lane's pair in block 0 (even)
+                    int y = (pp + 4 * p.Wp) / p.Wp - 4;                            // floor(pp / Wp): pp >= -2 Wp - 2
+                    int x = pp - y * p.Wp;
+                    uint32_t v[TC_AROW_BLKS];
+#pragma unroll
+                    for (int blk = 0; blk < TC_AROW_BLKS; blk++) {
+                        const bool ok = c_ok && (unsigned)pp < HWp && x < p.W;
+                        v[blk] = 0u;
+                        if (ok) v[blk] = __ldg(reinterpret_cast<const unsigned int*>(src + (pp - 2 * y)));   // element y W + x
+                        pp += 8; x += 8;
+                        if (x >= p.Wp) { x -= p.Wp; y++; }
+                    }
+                    // modulation coefficients of the channel pair this lane holds after the transpose
+                    float s0 = 1.f, s1 = 1.f;
+                    if (p.icoef) {
+                        const int cs = cb * TC_BK + 8 * pw + 2 * q;
+                        s0 = cs < p.Ci ? p.icoef[(long long)n * p.Ci + cs] : 0.f;
+                        s1 = cs + 1 < p.Ci ? p.icoef[(long long)n * p.Ci + cs + 1] : 0.f;
+                    }
+                    mbar_wait(&emptyb[stage], phase ^ 1, p.dbg, 0x800u | (unsigned)stage);
+                    const uint32_t dst = smem_u32(abase + stage * sbytes) + off_lane;
+#pragma unroll
+                    for (int blk = 0; blk < TC_AROW_BLKS; blk++) {
+                        uint32_t t;
+                        asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(t) : "r"(v[blk]));
+                        if (p.icoef) {
+                            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&t));
+                            t = pack_tc(f.x * s0, f.y * s1, (__half*)nullptr);     // fp32 product, one rounding: as the pack kernel
+                        }
+                        asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + (uint32_t)(blk * 1024)), "r"(t) : "memory");
+                    }
+                    fence_proxy_async();                                           // generic-proxy stores -> visible to tcgen05.mma
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&fullb[stage]);
+                    if (++stage == nst) { stage = 0; phase ^= 1; }
+                }
+            }
         }
     }
 
@@ -594,10 +681,32 @@ extern "C" int afcm_conv_tc_pack(const void* x, int x_dtype, const float* icoef,
     return AFCM_OK;
 }
 
+static int conv2d_tc_launch(const void* xp, const void* xn, const float* icoef, const void* w_tc, const float* ocoef, const float* bias, void* y,
+                            int y_dtype, int tc_dtype, int N, int Ci, int H, int W, int Co, int pad, void* stream);
+
 extern "C" int afcm_conv2d_tc(const void* xp, const void* w_tc, const float* ocoef, const float* bias, void* y, int y_dtype, int tc_dtype,
                               int N, int Ci, int H, int W, int Co, int pad, void* stream)
 {
-    AFCM_CHECK_ARG(xp && w_tc && y, "xp, w_tc and y must be given");
+    AFCM_CHECK_ARG(xp, "xp must be given");
+    return conv2d_tc_launch(xp, nullptr, nullptr, w_tc, ocoef, bias, y, y_dtype, tc_dtype, N, Ci, H, W, Co, pad, stream);
+}
+
+// The same convolution reading the fp16 NCHW activations directly (no packed copy): y[n,o] = ocoef[n,o] * conv(icoef[n,i] * x[n,i], w) + bias[o].
+// Full padding (2) only; W even and x 4-byte aligned (the planes are read as aligned pixel pairs); fp16 operands.
+extern "C" int afcm_conv2d_tc_nchw(const void* x, const float* icoef, const void* w_tc, const float* ocoef, const float* bias, void* y,
+                                   int y_dtype, int N, int Ci, int H, int W, int Co, void* stream)
+{
+    AFCM_CHECK_ARG(x, "x must be given");
+    if ((W & 1) || ((uintptr_t)x & 3)) { set_error("conv2d_tc_nchw: W must be even and x 4-byte aligned"); return AFCM_ERR_UNSUPPORTED; }
+    if ((long long)H * (W + 2) + 4LL * (W + 2) >= (1LL << 30)) { set_error("conv2d_tc_nchw: plane too large"); return AFCM_ERR_UNSUPPORTED; }
+    return conv2d_tc_launch(nullptr, x, icoef, w_tc, ocoef, bias, y, y_dtype, AFCM_F16, N, Ci, H, W, Co, 2, stream);
+}
+
+static int conv2d_tc_launch(const void* xp, const void* xn, const float* icoef, const void* w_tc, const float* ocoef, const float* bias, void* y,
+                            int y_dtype, int tc_dtype, int N, int Ci, int H, int W, int Co, int pad, void* stream)
+{
+    AFCM_CHECK_ARG(w_tc && y, "w_tc and y must be given");
+    const bool asw = xn != nullptr;
     AFCM_CHECK_ARG(y_dtype == AFCM_F32 || y_dtype == AFCM_F16, "y must be float32 or float16");
     AFCM_CHECK_ARG(N > 0 && Ci > 0 && Co > 0 && H > 0 && W > 0, "empty problem");
     AFCM_CHECK_ARG(tc_dtype == AFCM_F16 || tc_dtype == AFCM_BF16, "tc dtype must be F16 or BF16");
@@ -605,7 +714,8 @@ extern "C" int afcm_conv2d_tc(const void* xp, const void* w_tc, const float* oco
     if (H + 2 * pad - 2 <= 0 || W + 2 * pad - 2 <= 0) { set_error("conv2d_tc: empty output"); return AFCM_ERR_INVALID; }
     TcParams p;
     memset(&p, 0, sizeof(p));
-    p.ocoef = ocoef; p.bias = bias; p.y = y; p.y_half = y_dtype == AFCM_F16; p.dbg = g_dbg_dev; p.dbg_mode = g_dbg_mode;
+    p.ocoef = ocoef; p.bias = bias; p.y = y; p.y_half = y_dtype == AFCM_F16; p.dbg = g_dbg_dev; p.dbg_mode = asw ? 0 : g_dbg_mode;
+    p.xn = (const __half*)xn; p.icoef = icoef;
     p.N = N; p.Ci = Ci; p.Co = Co; p.H = H; p.W = W; p.Wp = W + 2; p.pad = pad;
     p.OH = H + 2 * pad - 2; p.OW = W + 2 * pad - 2;
     p.n_tiles = ceil_div(Co, 256);
@@ -622,8 +732,11 @@ extern "C" int afcm_conv2d_tc(const void* xp, const void* w_tc, const float* oco
     const int co_pad = (Co + 15) & ~15, ci_pad = (Ci + 63) & ~63;
     const uint64_t c_pad = (uint64_t)((Ci + 7) & ~7), rows = (uint64_t)H * p.Wp;
     CUtensorMap map_a, map_b;
-    int rc = encode_3d(&map_a, tc_dtype, xp, c_pad, rows, (uint64_t)N, c_pad * 2, rows * c_pad * 2, TC_BK, TC_BM);
-    if (rc) return rc;
+    int rc = 0;
+    if (!asw) {
+        rc = encode_3d(&map_a, tc_dtype, xp, c_pad, rows, (uint64_t)N, c_pad * 2, rows * c_pad * 2, TC_BK, TC_BM);
+        if (rc) return rc;
+    }
     rc = encode_3d(&map_b, tc_dtype, w_tc, (uint64_t)ci_pad, (uint64_t)co_pad, 9, (uint64_t)ci_pad * 2, (uint64_t)ci_pad * 2 * co_pad,
                    TC_BK, (uint32_t)p.BN);
     if (rc) return rc;
@@ -631,11 +744,12 @@ extern "C" int afcm_conv2d_tc(const void* xp, const void* w_tc, const float* oco
     // small channel tiles are bound by re-reading the activation tile once per tap from L2 (9 x 16 KB per 128 pixels):
     // there one tile per kernel ROW serves its three taps.  Large tiles keep the per-tap stages (B dominates).
     // BN <= 192: combined stages (A row + its three weight tiles); larger tiles: separate A / B rings (mode 2)
-    p.rowreuse = g_rowreuse >= 0 ? g_rowreuse : (p.BN <= 192 ? 1 : 2);
+    p.rowreuse = (g_rowreuse >= 0 && !asw) ? g_rowreuse : (p.BN <= 192 ? 1 : 2);
     if (p.rowreuse == 1 && p.BN > 192) p.rowreuse = 2;
     p.a_stages = 3;
+    if (asw) map_a = map_b;                      // unused by the ASW kernel; keeps the parameter initialised
     CUtensorMap map_a2 = map_a;
-    if (p.rowreuse) {
+    if (p.rowreuse && !asw) {
         rc = encode_3d(&map_a2, tc_dtype, xp, c_pad, rows, (uint64_t)N, c_pad * 2, rows * c_pad * 2, TC_BK, TC_AROW_PX);
         if (rc) return rc;
     }
@@ -653,10 +767,15 @@ extern "C" int afcm_conv2d_tc(const void* xp, const void* w_tc, const float* oco
     if (stages < 2) { set_error("conv2d_tc: not enough shared memory for the pipeline"); return AFCM_ERR_UNSUPPORTED; }
     p.stages = stages;
     const int smem = stages * stage_bytes + fixed + front;
-    AFCM_CUDA(cudaFuncSetAttribute(conv2d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int grid = sm_count();
     if (grid > p.total_tiles) grid = p.total_tiles;
-    conv2d_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, map_a2, p);
+    if (asw) {
+        AFCM_CUDA(cudaFuncSetAttribute(conv2d_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        conv2d_tc_kernel<true><<<grid, TC_ASW_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, map_a2, p);
+    } else {
+        AFCM_CUDA(cudaFuncSetAttribute(conv2d_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        conv2d_tc_kernel<false><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, map_a2, p);
+    }
     AFCM_LAUNCH_CHECK();
     count_launch();
     return AFCM_OK;

@@ -488,11 +488,7 @@ static int launch_t5(const CUtensorMap& map, const T5Params& p, cudaStream_t st)
     const int smem = 1024 + T5_STAGES * p.pl.halves * K1 * 128 + 2 * T5_RING_HALF + 16 * U * 128 + 4096 + 2048 + (NL + 1) * 2048 +
                      T5_OUT_BYTES + T5B_COUNT * 8 + 16 + 96 * 4;
     if (smem > max_smem_optin()) { set_error("filtered_lrelu_t5: %d bytes of shared memory needed", smem); return AFCM_ERR_UNSUPPORTED; }
-    static int configured = 0;
-    if (configured < smem) {
-        AFCM_CUDA(cudaFuncSetAttribute(flr_t5_kernel<U, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = smem;
-    }
+    AFCM_CUDA(cudaFuncSetAttribute(flr_t5_kernel<U, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));     // per device: not cached
     int blocks = p.total_units < sm_count() ? p.total_units : sm_count();
     flr_t5_kernel<U, D><<<blocks, T5_THREADS, smem, st>>>(map, p);
     AFCM_LAUNCH_CHECK();

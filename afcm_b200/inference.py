@@ -38,8 +38,10 @@ class GraphedGenerator:
     """Replays the generator forward for a fixed batch size as ONE CUDA graph launch (~250 kernel launches
     per forward otherwise; at small batches the forward is launch-bound).  Inputs are copied into static
     device buffers on the current stream, the graph is replayed, the static output is returned (valid until
-    the next call).  Host-side filter taps and tensor maps are baked into the captured kernel parameters, so
-    the graph must be rebuilt (`capture()`) after the weights change."""
+    the next call).  Host-side filter taps, tensor maps and the addresses of the prepared weights are baked into the
+    captured kernel parameters: the runner re-captures by itself when the precision changes, when a parameter has been
+    updated in place (optimizer step, load_state_dict) or when the prepared-weight cache has released anything
+    (conv2d_gradfix.prep_generation()), so a replay never reads freed or stale weights."""
 
     def __init__(self, G, batch, device=None, noise_mode='const', warmup=2, input_dtype=torch.float32):
         self.G = G
@@ -58,6 +60,11 @@ class GraphedGenerator:
         self.graph = None
         self.precision = None
         self.kernels_per_replay = 0
+        self._weights_tag = None
+
+    def _tag(self):
+        # parameter versions move on every in-place update; the generation moves on cache clears / evictions / re-preparation
+        return (conv2d_gradfix.prep_generation(), tuple(p._version for p in self.G.parameters()))
 
     def capture(self):
         self.precision = get_precision()
@@ -73,10 +80,11 @@ class GraphedGenerator:
         with torch.no_grad(), torch.cuda.graph(self.graph):
             self.y = self.G(self.z, self.c, self.x, noise_mode=self.noise_mode)
         self.kernels_per_replay = _lib.launch_count() - n0        # library kernels recorded in the graph
+        self._weights_tag = self._tag()
         return self
 
     def __call__(self, z, c, x):
-        if self.graph is None or self.precision != get_precision():
+        if self.graph is None or self.precision != get_precision() or self._weights_tag != self._tag():
             self.capture()
         assert z.shape[0] == self.batch, f'graph captured for batch {self.batch}, got {z.shape[0]}'
         self.z.copy_(z, non_blocking=True)

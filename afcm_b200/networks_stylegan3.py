@@ -638,7 +638,9 @@ class SynthesisNetwork(torch.nn.Module):
         ws = ws.to(torch.float32).unbind(dim=1)
         x = self.pad_input(img_in)                                                    # NET:669
         E_features = {}
-        enc_kwargs = {k: v for k, v in layer_kwargs.items() if k in ('force_fp32', 'update_emas')}
+        # the reference calls the encoder layers without keyword arguments (NET:673-680): their magnitude_ema buffers are
+        # never updated (they stay at 1.0 in reference checkpoints) -- only force_fp32 is forwarded here
+        enc_kwargs = {k: v for k, v in layer_kwargs.items() if k in ('force_fp32',)}
         for idx in range(self.num_layers):                                            # NET:673-680
             rev_idx = self.num_layers - idx - 1
             rev_prev = self.num_layers - max(idx - 1, 0) - 1

@@ -18,11 +18,27 @@ from ... import _lib
 conv_impl = 'f32'
 tc_dtype = torch.float16
 act_dtype = torch.float32
+direct_nchw = True                   # tensor-core path, fp16 activations, full padding: the GEMM reads the NCHW planes itself (no pack pass)
 wgrad_impl = 'tcgen05'               # tensor-core weight gradient: 'tcgen05' (TMEM accumulators) | 'mma' (mma.sync + atomics)
 enabled = False                      # kept for API compatibility with the reference module
 weight_gradients_disabled = False
 
 _prep_cache = {}
+_prep_generation = 0                 # bumped whenever a prepared tensor may have been released or replaced (see prep_generation())
+
+
+def prep_generation():
+    """Counter of events that invalidate device addresses handed out by prepare_weight(): cache clears / evictions and
+    re-preparation after a weight update.  A captured CUDA graph has those addresses baked in; inference.GraphedGenerator
+    records the value at capture time and re-captures when it has moved, so a replay never reads freed or stale weights."""
+    return _prep_generation
+
+
+def clear_prepared_weights():
+    """Drops every prepared weight (after an optimizer step: the fp32 parameters have changed)."""
+    global _prep_generation
+    _prep_cache.clear()
+    _prep_generation += 1
 
 
 def set_conv_impl(impl, dtype=None, act=None):
@@ -52,10 +68,13 @@ def prepare_weight(w, pre_scale=1.0, normalize=False, want_tc=False, want_wsq=Fa
     dtype = dtype or tc_dtype
     key = (id(w), float(pre_scale), bool(normalize))
     ent = _prep_cache.get(key)
+    global _prep_generation
     if ent is not None and (ent['_ref']() is not w or ent['_version'] != w._version):
         ent = None                      # address / id reuse or in-place update (optimizer step): re-prepare
+        _prep_generation += 1
     if ent is None:
         if len(_prep_cache) > 512:
+            _prep_generation += 1
             for k in [k for k, v in _prep_cache.items() if v['_ref']() is None]:
                 del _prep_cache[k]
             if len(_prep_cache) > 512:
@@ -109,11 +128,19 @@ def conv2d_native(x, w, padding, icoef=None, ocoef=None, pre_scale=1.0, normaliz
     assert y.dtype == out_dtype and y.is_contiguous()
     st = _lib.stream_ptr(x.device)
     ent = prepare_weight(w, pre_scale, normalize, want_tc=use_tc)
+    flops = 2.0 * N * Co * Ci * kh * kw * OH * OW
+    if use_tc and direct_nchw and padding == 2 and x.dtype == torch.float16 and tc_dtype == torch.float16 and W % 2 == 0:
+        # no packed copy of the activations -- the kernel's producer warps build the A tiles from the planes
+        rc = _lib.timed('conv2d_tc', flops, lambda: L.afcm_conv2d_tc_nchw(
+            _lib.ptr(x), _lib.ptr(icoef), _lib.ptr(ent[('w_tc', tc_dtype)]), _lib.ptr(ocoef), _lib.ptr(bias), _lib.ptr(y),
+            _lib.dtype_code(out_dtype), N, Ci, H, W, Co, st))
+        _lib.check(rc, allow_unsupported=True)
+        if rc == 0:
+            return y
     if use_tc:
         plane = int(L.afcm_conv_tc_plane_elems(H, W, Ci))
         xp = torch.empty([N, plane], dtype=tc_dtype, device=x.device)
         code = _lib.dtype_code(tc_dtype)
-        flops = 2.0 * N * Co * Ci * kh * kw * OH * OW
         _lib.timed('conv_tc_pack', float(x.element_size() * x.numel() + 2 * xp.numel()), lambda: _lib.check(
             L.afcm_conv_tc_pack(_lib.ptr(x), _lib.dtype_code(x.dtype), _lib.ptr(icoef), _lib.ptr(xp), code, N, Ci, H, W, st)))
         _lib.timed('conv2d_tc', flops, lambda: _lib.check(

@@ -22,7 +22,11 @@ from . import _lib
 
 
 def slice_batch_partition(global_batch, world_size, rank):
-    """Contiguous block of a global batch owned by `rank` (same rule as inference.slice_partition)."""
+    """Contiguous block of a global batch owned by `rank`: blocks differ by at most one sample (the first
+    `global_batch % world_size` ranks hold one more).  NB this is NOT inference.slice_partition, which hands out
+    ceil(D / world) slices per rank.  With unequal blocks the plain 1/world average of per-rank MEAN losses that
+    GeneratorTrainer applies is a mean of means; pass `loss_weight = local_n * world / global_n` to
+    GeneratorTrainer.step() to obtain the global-batch mean gradient (bench.py and the tests use equal blocks)."""
     base, rem = divmod(int(global_batch), int(world_size))
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
@@ -146,7 +150,7 @@ class FusedAdam:
         # the kernel updated the weights behind autograd's version counters: drop the prepared-weight cache of the
         # inference path (conv2d_gradfix.prepare_weight keys on the version)
         from .torch_utils.ops import conv2d_gradfix
-        conv2d_gradfix._prep_cache.clear()
+        conv2d_gradfix.clear_prepared_weights()
 
 
 class GeneratorTrainer:
@@ -162,16 +166,17 @@ class GeneratorTrainer:
         self.opt = FusedAdam(self.flat, lr=lr, betas=betas)
         self.world = self.reducer.world
 
-    def forward_backward(self, z, c, x, target):
+    def forward_backward(self, z, c, x, target, loss_weight=1.0):
         self.flat.zero_grad()
         self.reducer.begin()
         y = self.G(z, c, x, noise_mode='const')
         loss = (y - target).abs().mean()
-        loss.backward()
+        (loss * loss_weight if loss_weight != 1.0 else loss).backward()
         self.reducer.finish()
         return loss.detach()
 
-    def step(self, z, c, x, target):
-        loss = self.forward_backward(z, c, x, target)
+    def step(self, z, c, x, target, loss_weight=1.0):
+        """`loss_weight`: local_n * world / global_n when the ranks hold unequal blocks (see slice_batch_partition)."""
+        loss = self.forward_backward(z, c, x, target, loss_weight)
         self.opt.step(grad_scale=1.0 / self.world)
         return loss

@@ -212,6 +212,13 @@ int afcm_conv_tc_pack(const void* x, int x_dtype, const float* icoef, void* xp, 
                       int N, int Ci, int H, int W, void* stream);
 int afcm_conv2d_tc(const void* xp, const void* w_tc, const float* ocoef, const float* bias, void* y, int y_dtype, int tc_dtype,
                    int N, int Ci, int H, int W, int Co, int pad, void* stream);
+/* The same GEMM WITHOUT the pack step (NET:365-377 / NET:503-511: the convolution consumes what the preceding
+ * filtered_lrelu wrote): x [N,Ci,H,W] fp16 NCHW contiguous is read directly, eight producer warps of the kernel transpose
+ * 8-channel x 8-pixel blocks in registers and store them into the K-major swizzled tile the tensor core reads; icoef
+ * [N,Ci] or NULL is applied on the way (fp32 product, one rounding -- bit-identical to afcm_conv_tc_pack + afcm_conv2d_tc).
+ * Full padding (2), fp16 operands; returns AFCM_ERR_UNSUPPORTED for an odd W or a base address that is not 4-byte aligned. */
+int afcm_conv2d_tc_nchw(const void* x, const float* icoef, const void* w_tc, const float* ocoef, const float* bias, void* y,
+                        int y_dtype, int N, int Ci, int H, int W, int Co, void* stream);
 
 /* Debug / tuning aids, not part of the stable ABI: progress markers of the tcgen05 kernel in mapped host memory;
  * forced TMA->MMA ring depth (0 = automatic: as many stages as fit, at most 8). */

@@ -143,3 +143,34 @@ def test_tc_fast_variant_matches_oracle(up, down, pad, N, C, H, W):
     assert y.shape == ref.shape
     err = np.abs(y - ref).max() / np.abs(ref).max()
     assert err <= 2 * TOL, err
+
+
+FULL_CASES = [  # the plane sizes that carry most bytes of the BASELINE forward: up, down, padding, H
+    (2, 2, [9, 8, 9, 8], 278),            # 278 -> 276
+    (2, 4, [34, 33, 34, 33], 278),        # 278 -> 148
+    (4, 2, [-6, -9, -6, -9], 150),        # 150 -> 276
+    (2, 2, [-11, -12, -11, -12], 278),    # 278 -> 256 (last synthesis layer)
+    (2, 4, [34, 33, 34, 33], 150),        # 150 -> 84
+    (4, 2, [-6, -9, -6, -9], 86),         # 86 -> 148
+]
+
+
+@pytest.mark.parametrize('up,down,pad,H', FULL_CASES)
+def test_tc_fast_variant_full_size_vs_oracle(up, down, pad, H):
+    """Per-operator parity of the benchmarked variant (fp16 planes in and out, no bias, sat() activation, clamp 256) at the
+    full-size geometries, against the CPU oracle: max|err| <= 2e-3 max|y| (fp16 operands + fp16 result rounding)."""
+    import torch
+    from afcm_b200.torch_utils.ops.filtered_lrelu import filtered_lrelu_tc
+    from oracle import afcm_oracle as orc
+    rng = np.random.RandomState(H + 17 * up + down)
+    fu, fd = _filters(up, down)
+    x = (rng.randn(1, 3, H, H) * 3).astype(np.float16)
+    ref = orc.filtered_lrelu(x.astype(np.float32), fu, fd, None, up=up, down=down, padding=pad, gain=np.sqrt(2), slope=0.2, clamp=256.0)
+    ref = ref[0] if isinstance(ref, tuple) else ref
+    dev = torch.device('cuda')
+    y = filtered_lrelu_tc(torch.from_numpy(x).to(dev), torch.from_numpy(fu).to(dev), torch.from_numpy(fd).to(dev), None,
+                          up=up, down=down, padding=pad, gain=np.sqrt(2), slope=0.2, clamp=256.0, out_dtype=torch.float16)
+    assert y is not None and y.dtype == torch.float16 and tuple(y.shape) == ref.shape
+    err = np.abs(y.float().cpu().numpy() - ref).max() / np.abs(ref).max()
+    print(f'flr_tc fast variant {H}px up{up} down{down}: rel err {err:.3e}')
+    assert err <= TOL, err

@@ -79,8 +79,9 @@ def test_full_generator_fp32(golden_full):
     assert rel_err(y0.cpu().numpy(), g['y'][:1]) < 1e-4
 
 
-FAST_TOL = 2e-2          # max|y - y_ref| / max|y_ref| of the fast path (fp16 operands AND fp16 activation storage)
-FAST_PSNR = 45.0         # dB, peak = max|y_ref|
+FAST_TOL = 6e-3          # max|y - y_ref| / max|y_ref| of the fast path (fp16 operands AND fp16 activation storage); measured 2.8e-3
+FAST_PSNR = 58.0         # dB, peak = max|y_ref|; measured 62.5
+FAST_LAYER_TOL = 4e-3    # bound on EVERY layer output (crop of the golden file, relative to that layer's max|.|); measured 1e-4 .. 1.7e-3
 
 
 def _psnr(a, b):
@@ -108,6 +109,18 @@ def test_full_generator_fast_path(golden_full):
         assert y.dtype == torch.float32
         inter = [k for k, v in taps.items() if v.ndim == 4 and v.dtype == torch.float16]
         assert len(inter) >= 26, inter                    # activations really are stored as fp16
+        # every layer output of the 16-bit path against the reference's fp32 value (per-layer validation)
+        last = G.synthesis.layer_names[-1]
+        worst = ('', 0.0)
+        for k, v in taps.items():
+            crop = (v[:, :4, 5:13, 5:13] if v.ndim == 4 else v[:, :64]).float().cpu().numpy()
+            if k == last:
+                crop = crop / 0.25
+            e = float(np.abs(crop - g['crop.' + k]).max() / float(g['stat.' + k][2]))
+            print(f'fast path layer {k}: rel err {e:.3e}')
+            worst = max(worst, (k, e), key=lambda t: t[1])
+            assert e < FAST_LAYER_TOL, (k, e)
+        print(f'fast path: worst layer {worst[0]} {worst[1]:.3e}')
         err, psnr = rel_err(y.cpu().numpy(), g['y']), _psnr(y.cpu().numpy(), g['y'])
         print(f'fast path: rel err {err:.3e}, PSNR {psnr:.1f} dB')
         assert err < FAST_TOL and psnr > FAST_PSNR

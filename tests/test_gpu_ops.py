@@ -77,7 +77,13 @@ def test_filtered_lrelu_signs_match_oracle(dev, golden_ops):
         a, bb = unpack(so.cpu().numpy()), unpack(so_o)
         pre = pre[:, :, :sz['SH'], :sw]
         act = np.where(pre < 0, pre * slope, pre)
+        # A sign bit is a threshold test on a float: samples whose pre-activation value lies within rounding distance of the
+        # threshold (0, or +-clamp) may legitimately differ between two summation orders and are left out of the comparison.
+        # The masked share is counted and bounded so the mask cannot hide a real defect.
         safe = ((np.abs(pre) > 1e-5) | (pre == 0)) & ((np.abs(np.abs(act) - cl) > 1e-4 * max(cl, 1)) if np.isfinite(cl) else True)
+        masked = 1.0 - float(np.mean(safe))
+        print(f'sign tensor {name}: {masked:.2e} of the samples masked (within rounding of a threshold)')
+        assert masked < 2e-3, (name, masked)
         assert (a[safe] == bb[safe]).all(), name
 
 
