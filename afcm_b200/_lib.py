@@ -39,7 +39,10 @@ SIGNATURES = {
                                      _i, _i, _i, _i, _i, _i, _f, _f, _f, _f, _i, _i, _vp, _i, _i, _i, _i, _vp]),
     'afcm_filtered_lrelu_tc': (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp,           # x xs xdt y ys ydt b skip
                                     _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i,        # N C xh xw yh yw fu n fd n
-                                    _i, _i, _i, _i, _i, _i, _f, _f, _f, _f, _i, _vp]),  # up down pads gain slope clamp scale flip stream
+                                    _i, _i, _i, _i, _i, _i, _f, _f, _f, _f, _i, _vp]),
+    'afcm_filtered_lrelu_tc_padded': (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp,           # x xs xdt y ys ydt b skip
+                                    _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i,        # N C xh xw yh yw fu n fd n
+                                    _i, _i, _i, _i, _i, _i, _f, _f, _f, _f, _i, _i, _vp]),  # up down pads gain slope clamp scale flip stream
     'afcm_filtered_lrelu_t5': (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp,           # same arguments as afcm_filtered_lrelu_tc
                                     _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i,
                                     _i, _i, _i, _i, _i, _i, _f, _f, _f, _f, _i, _vp]),
@@ -59,7 +62,7 @@ SIGNATURES = {
     'afcm_conv_tc_plane_elems': (_i64, [_i, _i, _i]),
     'afcm_conv_tc_pack': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'afcm_conv2d_tc': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    'afcm_conv2d_tc_nchw': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    'afcm_conv2d_tc_nchw': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     'afcm_plane_dot_scale': (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
     'afcm_plane_sum': (_i, [_vp, _vp, _i64, _i64, _vp]),
     'afcm_conv2d_wgrad_f32': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),

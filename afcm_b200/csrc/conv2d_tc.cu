@@ -24,12 +24,14 @@
 //   * persistent CTAs (one per SM), static tile striding, output-channel tiles innermost so CTAs that
 //     run concurrently share their activation tiles in L2.
 //   * ASW variant (afcm_conv2d_tc_nchw): the A operand is built IN the kernel from the fp16 NCHW planes the preceding
-//     filtered_lrelu wrote -- no packed copy of the activations exists.  Eight producer warps (12-19) read aligned pixel
-//     pairs of 8 channels x 8 pixels per warp instruction, transpose them in registers (movmatrix.m8n8.trans.b16), apply the
-//     modulation coefficient in fp32 and store the words straight into the K-major SWIZZLE_128B tile the tensor core reads
-//     (the swizzle makes the 32 stores of a warp hit 32 different banks), then fence.proxy.async + mbarrier arrive.  The
-//     row pitch W+2 of the flat-plane formulation is virtual: flat pixel p = y (W+2) + x lives at element p - 2y of the
-//     plane, x >= W and rows outside the plane are zeros.
+//     filtered_lrelu wrote -- no packed copy of the activations exists.  Warp 3 streams RAW tiles [64 channels][152 plane
+//     elements] through a TMA ring (box on the flat [N][Ci][H pitch] view of the tensor, 16-byte aligned start, zero fill
+//     outside the plane and beyond Ci); eight producer warps (12-19), one per 8-channel block, read aligned pixel pairs of two
+//     channel rows per lane from it, byte-permute them into {channel pair, pixel} words, apply the modulation coefficient in
+//     fp32 and store the words straight into the K-major SWIZZLE_128B tile the tensor core reads (the swizzle makes the 32
+//     stores of a warp hit 32 different banks; the 304-byte raw rows do the same for the loads), then fence.proxy.async +
+//     mbarrier arrive.  The row pitch W+2 of the flat-plane formulation is virtual: flat pixel p = y (W+2) + x lives at element
+//     p - 2y of the plane; x >= W and rows outside the plane are zeros.
 #include <cuda.h>
 #include "afcm_common.cuh"
 #include "tc_ptx.cuh"
@@ -43,6 +45,9 @@ constexpr int TC_THREADS = 384;         // warps 0-3: TMA producer, MMA issuer, 
 constexpr int TC_ASW_WARPS = 8;         // ASW variant: warps 12-19 build the A tiles from NCHW planes (one 8-channel block each)
 constexpr int TC_ASW_THREADS = TC_THREADS + 32 * TC_ASW_WARPS;
 constexpr int TC_AROW_BLKS = 17;        // 8-pixel blocks of a row-reuse A tile (TC_AROW_PX / 8)
+constexpr int TC_RAW_PX = 152;          // ASW raw tile: plane elements per channel row (136 + alignment slack; 304-byte rows: conflict-free)
+constexpr int TC_RAW_BYTES = TC_RAW_PX * TC_BK * 2;    // 19 KB
+constexpr int TC_RAW_MAX_STAGES = 8;    // depth of the raw ring is chosen per launch (p.raw_stages): it carries the global-memory latency
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;          // 16 KB
 constexpr int TC_AROW_PX = TC_BM + 8;                  // row-reuse mode: 128 pixels + the two pixels to the right, rounded to 8
 constexpr int TC_AROW_BYTES = TC_AROW_PX * TC_BK * 2;  // 17 KB
@@ -59,10 +64,12 @@ struct TcParams {
     int rowreuse;                          // 1: one A tile of 136 pixels per (ky, channel block) serves the three kx taps;
                                            // 2: the same with separate rings for the A rows and the per-tap weight tiles
     int a_stages;                          // mode 2: depth of the A ring (`stages` is the depth of the B ring)
+    int raw_stages;                        // ASW: depth of the raw-tile ring
     int bres;                              // 1 (row-reuse mode, single channel tile): all weight tiles stay resident in shared memory
     unsigned idesc;
     const __half* xn;       // ASW: [N, Ci, H, W] fp16 activations (NCHW, contiguous)
     const float* icoef;     // ASW: [N, Ci] modulation coefficients or null
+    int pitched;            // ASW: the planes are stored at the row pitch W + 2 with zero pad pixels: the flat plane exists in memory
     unsigned* dbg;          // mapped host memory for progress markers (AFCM_TC_DEBUG), or null
     int dbg_mode;           // debug bisection switches (see afcm_conv_tc_debug_buffer)
 };
@@ -76,6 +83,7 @@ __global__ void __launch_bounds__(ASW ? TC_ASW_THREADS : TC_THREADS, 1)
 conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ TcParams p)
 {
+    // ASW: map_a is the RAW map (flat [H pitch] x Ci x N view of the NCHW tensor, no swizzle); map_a2 is unused
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int b_bytes = p.BN * TC_BK * 2;
@@ -83,6 +91,8 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                           : (p.bres ? TC_AROW_BYTES : (p.rowreuse ? TC_AROW_BYTES + 3 * b_bytes : TC_A_BYTES + b_bytes));
     // in front of the ring: the resident weights (tile (tap, cb) at (tap * cblocks + cb) * b_bytes), or the A ring of mode 2
     const int res_bytes = p.rowreuse == 2 ? p.a_stages * TC_AROW_BYTES : (p.bres ? 9 * p.cblocks * b_bytes : 0);
+    uint8_t* raw = smem;                                                // ASW: TC_RAW_STAGES raw tiles in front of everything
+    if (ASW) smem += p.raw_stages * TC_RAW_BYTES;                       // 19 x 1024 bytes each: the operand tiles stay 1024-byte aligned
     uint8_t* ring = smem + res_bytes;
     uint8_t* tail = ring + p.stages * stage_bytes;
     uint64_t* full = reinterpret_cast<uint64_t*>(tail);                 // [TC_MAX_STAGES]
@@ -90,10 +100,12 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint64_t* tfull = empty + TC_MAX_STAGES;                            // [2]
     uint64_t* tempty = tfull + 2;                                       // [2]
     uint64_t* bfull = tempty + 2;                                       // [1]
-    uint64_t* afull = bfull + 1;                                        // [4] mode 2: A ring
-    uint64_t* aempty = afull + 4;                                       // [4]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 4);
-    float* s_ocoef = reinterpret_cast<float*>(tail + 256);              // [2][256]
+    uint64_t* afull = bfull + 1;                                        // [8] mode 2: A ring
+    uint64_t* aempty = afull + 8;                                       // [8]
+    uint64_t* rfull = aempty + 8;                                       // [8] ASW: raw ring
+    uint64_t* rempty = rfull + TC_RAW_MAX_STAGES;                       // [8]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty + TC_RAW_MAX_STAGES);
+    float* s_ocoef = reinterpret_cast<float*>(tail + 512);              // [2][256]  (53 barriers + the TMEM slot take 428 bytes)
     float* s_bias = s_ocoef + 512;                                      // [2][256]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -105,11 +117,13 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (warp == 1 && lane == 0) {
         // ASW: an A tile is complete when every producer warp has arrived (+ the TMA thread's expect_tx arrive where the stage
         // also carries weight tiles)
-        const uint32_t full_count = !ASW ? 1u : (p.rowreuse == 2 ? 1u : (p.bres ? (uint32_t)TC_ASW_WARPS : (uint32_t)TC_ASW_WARPS + 1u));
+        const uint32_t npw = (uint32_t)TC_ASW_WARPS;
+        const uint32_t full_count = !ASW ? 1u : (p.rowreuse == 2 ? 1u : (p.bres ? npw : npw + 1u));
         for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], full_count); mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
         mbar_init(bfull, 1);
-        for (int a = 0; a < 4; a++) { mbar_init(&afull[a], ASW ? (uint32_t)TC_ASW_WARPS : 1u); mbar_init(&aempty[a], 1); }
+        for (int a = 0; a < 8; a++) { mbar_init(&afull[a], ASW ? npw : 1u); mbar_init(&aempty[a], 1); }
+        for (int a = 0; a < TC_RAW_MAX_STAGES; a++) { mbar_init(&rfull[a], 1); mbar_init(&rempty[a], npw); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -383,61 +397,124 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
     }
 
+    if (ASW && warp == 3 && lane == 0) {
+        // ================= raw-tile TMA producer (ASW) =================
+        // One box [64 channels][TC_RAW_PX plane elements] per (tile, ky, channel block), starting at the 8-element boundary at or
+        // below the first element the A tile needs: element index of flat pixel p = p - 2 floor(p / Wp) (dense planes) or p (planes
+        // stored at the pitch W + 2).
+        int rs = 0; uint32_t rph = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const int r = tile / p.n_tiles;
+            const int mt = r % p.m_tiles, n = r / p.m_tiles;
+            for (int ky = 0; ky < 3; ky++) {
+                const int pp0 = mt * TC_BM + (ky - p.pad) * p.Wp - p.pad;
+                const int y0 = (pp0 + 4 * p.Wp) / p.Wp - 4;
+                const int a0 = ((p.pitched ? pp0 : pp0 - 2 * y0) >> 3) << 3;   // floor to a multiple of 8 (also for negatives)
+                for (int cb = 0; cb < p.cblocks; cb++) {
+                    mbar_wait(&rempty[rs], rph ^ 1, p.dbg, 0x900u | (unsigned)rs);
+                    mbar_expect_tx(&rfull[rs], (uint32_t)TC_RAW_BYTES);
+                    tma_load_3d(raw + rs * TC_RAW_BYTES, &map_a, &rfull[rs], a0, cb * TC_BK, n);
+                    if (++rs == p.raw_stages) { rs = 0; rph ^= 1; }
+                }
+            }
+        }
+    }
     if (ASW && warp >= 12) {
-        // ================= A-tile producers (ASW): NCHW fp16 planes -> K-major SWIZZLE_128B tile =================
-        // Warp pw owns the 8-channel block pw of the 64-channel stage (= 16-byte chunk pw of every tile row).  Per block of
-        // 8 pixels: lane (r8, q) loads the pixel pair 2q of channel r8 (4 bytes), the warp transposes the 8 x 8 block of
-        // 16-bit words, after which the lane holds the channel pair 2q of pixel r8 -- one 32-bit word of tile row r8.
-        const int pw = warp - 12, q = lane & 3, r8 = lane >> 2;
-        const uint32_t off_lane = (uint32_t)(r8 * 128 + ((pw ^ r8) << 4) + 4 * q);      // the tile row index is 8 blk + r8: (row & 7) == r8
+        // ================= A-tile producers (ASW): raw [channel][element] tile -> K-major SWIZZLE_128B tile =================
+        // Warp pw owns the 8-channel block pw of the 64-channel stage (= 16-byte chunk pw of every tile row).  Per iteration
+        // the warp moves 16 pixels x 8 channels: lane (b2, m, q) reads pixel pair m of 8-pixel block 2 it + b2 from the channel
+        // rows 2q and 2q + 1 of the raw tile (two 4-byte loads, conflict-free with the 304-byte raw rows), byte-permutes them
+        // into the words {channel pair q of the even pixel, of the odd pixel} and stores each into its tile row (32 different
+        // banks: the half-warps store even / odd pixels in opposite order).  Variants measured and rejected: an in-register
+        // 8 x 8 transpose with movmatrix (~16 clocks per warp instruction per SM: 2900 clocks per tile); the producer warps
+        // fetching the planes themselves with ld.global or cp.async rings (2-3 tiles of prefetch per warp do not cover the
+        // global-memory latency: 50 ms over the 28 layers instead of 36).
+        const int pw = warp - 12, q = lane & 3, m = (lane >> 2) & 3, b2 = lane >> 4;
+        const uint32_t raw_lane = smem_u32(raw) + (uint32_t)((8 * pw + 2 * q) * (TC_RAW_PX * 2));
+        const uint32_t off_even = (uint32_t)((8 * b2 + 2 * m) * 128 + ((pw ^ (2 * m)) << 4) + 4 * q);          // tile row & 7 == 2m
+        const uint32_t off_odd = (uint32_t)((8 * b2 + 2 * m + 1) * 128 + ((pw ^ (2 * m + 1)) << 4) + 4 * q);   // tile row & 7 == 2m + 1
+        const uint32_t off_first = b2 ? off_odd : off_even, off_second = b2 ? off_even : off_odd;
+        constexpr int NIT = (TC_AROW_BLKS + 1) / 2;                                // 9 iterations of 16 pixels (the last one: 8)
         const bool two_rings = p.rowreuse == 2;
         const int nst = two_rings ? p.a_stages : p.stages;
         const int sbytes = two_rings ? TC_AROW_BYTES : stage_bytes;
         uint8_t* abase = two_rings ? smem : ring;
         uint64_t* fullb = two_rings ? afull : full;
         uint64_t* emptyb = two_rings ? aempty : empty;
-        const long long plane = (long long)p.H * p.W;
         const unsigned HWp = (unsigned)(p.H * p.Wp);
-        int stage = 0; uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        auto tile_origin = [&](int tile, int ky, int& n, int& pp0, int& y0, int& a0) {
             const int r = tile / p.n_tiles;
-            const int mt = r % p.m_tiles, n = r / p.m_tiles;
-            const int p0 = mt * TC_BM;
+            const int mt = r % p.m_tiles;
+            n = r / p.m_tiles;
+            pp0 = mt * TC_BM + (ky - p.pad) * p.Wp - p.pad;
+            y0 = (pp0 + 4 * p.Wp) / p.Wp - 4;                                      // floor(pp0 / Wp): pp0 >= -2 Wp - 2
+            a0 = ((p.pitched ? pp0 : pp0 - 2 * y0) >> 3) << 3;                    // floor to a multiple of 8 (also for negatives)
+        };
+        int stage = 0; uint32_t phase = 0;
+        int rs = 0; uint32_t rph = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             for (int ky = 0; ky < 3; ky++) {
+                int n, pp0, y0, a0;
+                tile_origin(tile, ky, n, pp0, y0, a0);
                 for (int cb = 0; cb < p.cblocks; cb++) {
-                    const int cl = cb * TC_BK + 8 * pw + r8;                       // channel this lane LOADS
-                    const bool c_ok = cl < p.Ci;
-                    const __half* src = p.xn + ((long long)n * p.Ci + (c_ok ? cl : 0)) * plane;
-                    int pp = p0 + (ky - p.pad) * p.Wp - p.pad + 2 * q;            // flat pixel of this lane's pair in block 0 (even)
-                    int y = (pp + 4 * p.Wp) / p.Wp - 4;                            // floor(pp / Wp): pp >= -2 Wp - 2
-                    int x = pp - y * p.Wp;
-                    uint32_t v[TC_AROW_BLKS];
-#pragma unroll
-                    for (int blk = 0; blk < TC_AROW_BLKS; blk++) {
-                        const bool ok = c_ok && (unsigned)pp < HWp && x < p.W;
-                        v[blk] = 0u;
-                        if (ok) v[blk] = __ldg(reinterpret_cast<const unsigned int*>(src + (pp - 2 * y)));   // element y W + x
-                        pp += 8; x += 8;
-                        if (x >= p.Wp) { x -= p.Wp; y++; }
-                    }
-                    // modulation coefficients of the channel pair this lane holds after the transpose
+                    // modulation coefficients of the channel pair this lane assembles
                     float s0 = 1.f, s1 = 1.f;
                     if (p.icoef) {
                         const int cs = cb * TC_BK + 8 * pw + 2 * q;
                         s0 = cs < p.Ci ? p.icoef[(long long)n * p.Ci + cs] : 0.f;
                         s1 = cs + 1 < p.Ci ? p.icoef[(long long)n * p.Ci + cs + 1] : 0.f;
                     }
-                    mbar_wait(&emptyb[stage], phase ^ 1, p.dbg, 0x800u | (unsigned)stage);
-                    const uint32_t dst = smem_u32(abase + stage * sbytes) + off_lane;
+                    mbar_wait(&rfull[rs], rph, p.dbg, 0xa00u | (unsigned)rs);
+                    int pp = pp0 + 8 * b2 + 2 * m;                                 // flat pixel of this lane's pair in iteration 0 (even)
+                    const uint32_t src = raw_lane + (uint32_t)(rs * TC_RAW_BYTES) - (uint32_t)(2 * a0);
+                    uint32_t v0[NIT], v1[NIT];
+                    if (p.pitched) {
+                        // the flat plane exists in memory (pad pixels are stored zeros, outside the plane: zero fill): a straight copy
+                        const uint32_t a = src + (uint32_t)(2 * pp);
 #pragma unroll
-                    for (int blk = 0; blk < TC_AROW_BLKS; blk++) {
-                        uint32_t t;
-                        asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(t) : "r"(v[blk]));
-                        if (p.icoef) {
-                            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&t));
-                            t = pack_tc(f.x * s0, f.y * s1, (__half*)nullptr);     // fp32 product, one rounding: as the pack kernel
+                        for (int it = 0; it < NIT; it++) {
+                            v0[it] = 0u; v1[it] = 0u;
+                            if (it < NIT - 1 || b2 == 0) {
+                                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v0[it]) : "r"(a + (uint32_t)(32 * it)) : "memory");
+                                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v1[it]) : "r"(a + (uint32_t)(32 * it + TC_RAW_PX * 2)) : "memory");
+                            }
                         }
-                        asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + (uint32_t)(blk * 1024)), "r"(t) : "memory");
+                    } else {
+                        int y = y0, x = pp - y0 * p.Wp;
+                        if (x >= p.Wp) { x -= p.Wp; y++; }
+#pragma unroll
+                        for (int it = 0; it < NIT; it++) {
+                            // rows outside the plane / channels >= Ci were zero-filled; pad pixels x >= W are zeros by definition
+                            const bool ok = (unsigned)pp < HWp && x < p.W && (it < NIT - 1 || b2 == 0);
+                            v0[it] = 0u; v1[it] = 0u;
+                            if (ok) {
+                                const uint32_t a = src + (uint32_t)(2 * (pp - 2 * y));  // element y W + x = pp - 2y of the plane
+                                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v0[it]) : "r"(a) : "memory");
+                                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v1[it]) : "r"(a + (uint32_t)(TC_RAW_PX * 2)) : "memory");
+                            }
+                            pp += 16; x += 16;
+                            if (x >= p.Wp) { x -= p.Wp; y++; }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&rempty[rs]);                       // the raw slot may be refilled
+                    if (++rs == p.raw_stages) { rs = 0; rph ^= 1; }
+                    mbar_wait(&emptyb[stage], phase ^ 1, p.dbg, 0x800u | (unsigned)stage);
+                    const uint32_t dst = smem_u32(abase + stage * sbytes);
+#pragma unroll
+                    for (int it = 0; it < NIT; it++) {
+                        uint32_t te = __byte_perm(v0[it], v1[it], 0x5410), to = __byte_perm(v0[it], v1[it], 0x7632);
+                        if (p.icoef) {                                             // fp32 product, one rounding: as the pack kernel
+                            const float2 fe = __half22float2(*reinterpret_cast<const __half2*>(&te));
+                            const float2 fo = __half22float2(*reinterpret_cast<const __half2*>(&to));
+                            te = pack_tc(fe.x * s0, fe.y * s1, (__half*)nullptr);
+                            to = pack_tc(fo.x * s0, fo.y * s1, (__half*)nullptr);
+                        }
+                        if (it < NIT - 1 || b2 == 0) {
+                            const uint32_t d = dst + (uint32_t)(it * 2048);
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(d + off_first), "r"(b2 ? to : te) : "memory");
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(d + off_second), "r"(b2 ? te : to) : "memory");
+                        }
                     }
                     fence_proxy_async();                                           // generic-proxy stores -> visible to tcgen05.mma
                     __syncwarp();
@@ -597,7 +674,7 @@ static EncodeTiledFn get_encode_fn()
 }
 
 int encode_tiled(CUtensorMap* map, int tc_dtype, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
-                 const uint32_t* box)
+                 const uint32_t* box, bool swizzle128)
 {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return AFCM_ERR_UNSUPPORTED; }
@@ -607,7 +684,8 @@ int encode_tiled(CUtensorMap* map, int tc_dtype, const void* base, int rank, con
     for (int i = 0; i + 1 < rank; i++) st[i] = strides[i];
     CUresult r = fn(map, tc_dtype == AFCM_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank,
                     const_cast<void*>(base), d, st, b, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return AFCM_ERR_INVALID; }
     return AFCM_OK;
 }
@@ -693,11 +771,19 @@ extern "C" int afcm_conv2d_tc(const void* xp, const void* w_tc, const float* oco
 
 // The same convolution reading the fp16 NCHW activations directly (no packed copy): y[n,o] = ocoef[n,o] * conv(icoef[n,i] * x[n,i], w) + bias[o].
 // Full padding (2) only; W even and x 4-byte aligned (the planes are read as aligned pixel pairs); fp16 operands.
-extern "C" int afcm_conv2d_tc_nchw(const void* x, const float* icoef, const void* w_tc, const float* ocoef, const float* bias, void* y,
+static int g_asw_pitch = 0;        // row pitch of the planes handed to conv2d_tc_launch by afcm_conv2d_tc_nchw (W or W + 2)
+
+extern "C" int afcm_conv2d_tc_nchw(const void* x, int x_pitch, const float* icoef, const void* w_tc, const float* ocoef, const float* bias, void* y,
                                    int y_dtype, int N, int Ci, int H, int W, int Co, void* stream)
 {
     AFCM_CHECK_ARG(x, "x must be given");
-    if ((W & 1) || ((uintptr_t)x & 3)) { set_error("conv2d_tc_nchw: W must be even and x 4-byte aligned"); return AFCM_ERR_UNSUPPORTED; }
+    AFCM_CHECK_ARG(x_pitch == W || x_pitch == W + 2, "x_pitch must be W (dense planes) or W + 2 (planes with two zero pad pixels per row)");
+    // planes are read as aligned pixel pairs; the raw tiles arrive by TMA from the flat [N][Ci][H W] view (16-byte aligned strides)
+    if ((W & 1) || (((long long)H * x_pitch) & 7) || ((uintptr_t)x & 15)) {
+        set_error("conv2d_tc_nchw: needs an even W, H * x_pitch a multiple of 8 and a 16-byte aligned x");
+        return AFCM_ERR_UNSUPPORTED;
+    }
+    g_asw_pitch = x_pitch;
     if ((long long)H * (W + 2) + 4LL * (W + 2) >= (1LL << 30)) { set_error("conv2d_tc_nchw: plane too large"); return AFCM_ERR_UNSUPPORTED; }
     return conv2d_tc_launch(nullptr, x, icoef, w_tc, ocoef, bias, y, y_dtype, AFCM_F16, N, Ci, H, W, Co, 2, stream);
 }
@@ -747,26 +833,67 @@ static int conv2d_tc_launch(const void* xp, const void* xn, const float* icoef, 
     p.rowreuse = (g_rowreuse >= 0 && !asw) ? g_rowreuse : (p.BN <= 192 ? 1 : 2);
     if (p.rowreuse == 1 && p.BN > 192) p.rowreuse = 2;
     p.a_stages = 3;
-    if (asw) map_a = map_b;                      // unused by the ASW kernel; keeps the parameter initialised
+    if (asw) {
+        // RAW map: dims {H pitch, Ci, N}, box {TC_RAW_PX, 64, 1}, no swizzle; out-of-range elements / channels are zero-filled
+        const uint64_t hw = (uint64_t)H * g_asw_pitch;
+        p.pitched = g_asw_pitch != W;
+        const uint64_t dims[3] = {hw, (uint64_t)Ci, (uint64_t)N}, strides[2] = {hw * 2, hw * 2 * (uint64_t)Ci};
+        const uint32_t box[3] = {(uint32_t)TC_RAW_PX, (uint32_t)TC_BK, 1};
+        rc = encode_tiled(&map_a, AFCM_F16, xn, 3, dims, strides, box, false);
+        if (rc) return rc;
+    }
     CUtensorMap map_a2 = map_a;
     if (p.rowreuse && !asw) {
         rc = encode_3d(&map_a2, tc_dtype, xp, c_pad, rows, (uint64_t)N, c_pad * 2, rows * c_pad * 2, TC_BK, TC_AROW_PX);
         if (rc) return rc;
     }
-    const int fixed = 256 + 4 * 256 * 4 + 1024;
+    const int fixed = 512 + 4 * 256 * 4 + 1024;
+    const int b_bytes = p.BN * TC_BK * 2;
     // a single channel tile whose 9 x cblocks weight tiles fit next to a 3-deep A ring: keep the weights resident
-    const int res_bytes = 9 * p.cblocks * p.BN * TC_BK * 2;
-    p.bres = p.rowreuse && g_bres != 0 && p.n_tiles == 1 && res_bytes + 3 * TC_AROW_BYTES + fixed <= max_smem_optin();
+    const int res_bytes = 9 * p.cblocks * b_bytes;
+    const int raw_min = asw ? 3 * TC_RAW_BYTES : 0;
+    p.bres = p.rowreuse && g_bres != 0 && p.n_tiles == 1 && res_bytes + 3 * TC_AROW_BYTES + fixed + raw_min <= max_smem_optin();
     p.bres = p.bres && p.rowreuse == 1;
-    const int front = p.rowreuse == 2 ? p.a_stages * TC_AROW_BYTES : (p.bres ? res_bytes : 0);
-    const int stage_bytes = p.rowreuse == 2 ? p.BN * TC_BK * 2
-                          : (p.bres ? TC_AROW_BYTES : (p.rowreuse ? TC_AROW_BYTES + 3 * p.BN * TC_BK * 2 : TC_A_BYTES + p.BN * TC_BK * 2));
-    int stages = (max_smem_optin() - fixed - front) / stage_bytes;
-    if (g_force_stages > 0) stages = g_force_stages;
-    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    int stages, smem;
+    if (!asw) {
+        const int front = p.rowreuse == 2 ? p.a_stages * TC_AROW_BYTES : (p.bres ? res_bytes : 0);
+        const int stage_bytes = p.rowreuse == 2 ? b_bytes : (p.bres ? TC_AROW_BYTES : (p.rowreuse ? TC_AROW_BYTES + 3 * b_bytes : TC_A_BYTES + b_bytes));
+        stages = (max_smem_optin() - fixed - front) / stage_bytes;
+        if (g_force_stages > 0) stages = g_force_stages;
+        if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+        smem = stages * stage_bytes + fixed + front;
+    } else {
+        // ASW: three raw tiles in flight carry the global-memory latency; the ring of transposed A tiles must be deep enough to
+        // hide the release -> refill -> arrive round trip between the tensor core and the producer warps (~700 clocks) behind
+        // the MMA time of the stages in between, which is short for small channel tiles (384 clocks per stage at BN = 64:
+        // measured 0.79 ms instead of 0.53 ms on the 64-channel layers with a 3-deep ring); the weight ring keeps >= 4 stages
+        const int avail = max_smem_optin() - fixed;
+        p.raw_stages = 3;
+        if (p.bres) {
+            stages = (avail - res_bytes - p.raw_stages * TC_RAW_BYTES) / TC_AROW_BYTES;               // A ring
+            if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+            smem = res_bytes + stages * TC_AROW_BYTES;
+        } else {
+            // without resident weights the A tiles and the weight tiles get rings of their own (a combined stage of a wide
+            // channel tile would not fit twice next to the raw ring)
+            p.rowreuse = 2;
+            stages = 4;                                                                               // weight ring
+            auto ast = [&]() { return (avail - stages * b_bytes - p.raw_stages * TC_RAW_BYTES) / TC_AROW_BYTES; };
+            if (ast() < 2) p.raw_stages = 2;
+            p.a_stages = ast() > 8 ? 8 : ast();
+            if (p.a_stages < 2) stages = 0;
+            else {
+                stages = (avail - p.a_stages * TC_AROW_BYTES - p.raw_stages * TC_RAW_BYTES) / b_bytes;   // leftover to the weights
+                if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+            }
+            smem = p.a_stages * TC_AROW_BYTES + stages * b_bytes;
+        }
+        if (p.raw_stages > TC_RAW_MAX_STAGES) p.raw_stages = TC_RAW_MAX_STAGES;
+        if (p.raw_stages < 2) stages = 0;
+        smem += fixed + p.raw_stages * TC_RAW_BYTES;
+    }
     if (stages < 2) { set_error("conv2d_tc: not enough shared memory for the pipeline"); return AFCM_ERR_UNSUPPORTED; }
     p.stages = stages;
-    const int smem = stages * stage_bytes + fixed + front;
     int grid = sm_count();
     if (grid > p.total_tiles) grid = p.total_tiles;
     if (asw) {

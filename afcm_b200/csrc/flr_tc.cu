@@ -52,6 +52,7 @@ struct FlrTcParams {
     long long xs_n, xs_c, ys_n, ys_c;                    // element strides, innermost stride 1
     int xs_h, ys_h;                                      // row strides (host-checked to fit 32 bits)
     int C, xh, xw, yh, yw;
+    int zero_cols;                                        // columns [yw, yw + zero_cols) of every output row are written as zeros (0 or 2)
     int strips, segs, seg_wblocks;                        // 16-column strips, row segments of 8*seg_wblocks rows
     int units;                                            // strips * segs: warps per plane
     unsigned total_warps;
@@ -275,7 +276,7 @@ struct FtcWarp {
             csz[c8] = ok ? (uint32_t)RAW_BYTES : 0u;
             ccol[c8] = (ok ? col : 0) - (ix + 2 * t);
         }
-        interior = __all_sync(0xffffffffu, cm == (1u << Geo::NC) - 1u) && k0 + 16 <= p.yw;
+        interior = __all_sync(0xffffffffu, cm == (1u << Geo::NC) - 1u) && k0 + 16 <= p.yw;       // (a strip holding the zero pair is not interior)
 #pragma unroll
         for (int mb = 0; mb < MB; mb++) { P[0][mb][0] = P[0][mb][1] = P[1][mb][0] = P[1][mb][1] = 0u; }
 #pragma unroll
@@ -465,7 +466,8 @@ struct FtcWarp {
                 if (r1) store_pair(q1 + 8 * nb, c[2], c[3]);
             } else {
                 // yw is even and the strip origin is even (host-checked): a column pair is inside or outside as a whole
-                const bool cok = k0 + 8 * nb + 2 * t < p.yw;
+                const int col = k0 + 8 * nb + 2 * t;
+                const bool cok = col < p.yw;
                 if (r0 && cok) {
                     if (has_skip) { c[0] += (float)q0[8 * nb + kofs] * p.out_scale; c[1] += (float)q0[8 * nb + kofs + 1] * p.out_scale; }
                     store_pair(q0 + 8 * nb, c[0], c[1]);
@@ -473,6 +475,12 @@ struct FtcWarp {
                 if (r1 && cok) {
                     if (has_skip) { c[2] += (float)q1[8 * nb + kofs] * p.out_scale; c[3] += (float)q1[8 * nb + kofs + 1] * p.out_scale; }
                     store_pair(q1 + 8 * nb, c[2], c[3]);
+                }
+                // planes stored at the row pitch yw + 2 for the convolution that follows (its flat-plane formulation wants two
+                // zero pixels behind every row, conv2d_tc.cu): the pair behind the last column is written as zeros
+                if (!cok && col < p.yw + p.zero_cols) {
+                    if (r0) store_pair(q0 + 8 * nb, 0.f, 0.f);
+                    if (r1) store_pair(q1 + 8 * nb, 0.f, 0.f);
                 }
             }
         }
@@ -619,7 +627,7 @@ struct FtcWarp {
     __device__ void run()
     {
         prime();
-        const bool narrow = p.yw - k0 <= 8;             // warp-uniform
+        const bool narrow = p.yw + p.zero_cols - k0 <= 8;             // warp-uniform (the zero pair behind the last column counts)
         if (U == 2 && D == 2) { if (narrow) run22<true>(); else run22<false>(); }
         else if (U == 4 && D == 2) { if (narrow) run42<true>(); else run42<false>(); }
         else { if (narrow) run24<true>(); else run24<false>(); }
@@ -673,7 +681,7 @@ static int g_ftc_waves = 16;          // 0: one warp per unit (no persistence); 
 template <int U, int D, typename TIN, typename TOUT, int ACT, bool FAST>
 static int launch_tc(FlrTcParams& p, int N, cudaStream_t st)
 {
-    p.strips = ceil_div(p.yw, 16);
+    p.strips = ceil_div(p.yw + p.zero_cols, 16);
     const long long planes = (long long)N * p.C;
     int wblocks = ceil_div(p.yh, 8);
     if (wblocks & 1) wblocks++;                         // segments are multiples of 16 output rows
@@ -736,6 +744,19 @@ extern "C" int afcm_filtered_lrelu_tc(const void* x, const int64_t* xs, int x_dt
                                       float gain, float slope, float clamp, float out_scale, int flip_filter,
                                       void* stream)
 {
+    return afcm_filtered_lrelu_tc_padded(x, xs, x_dtype, y, ys, y_dtype, b, skip, N, C, xh, xw, yh, yw, fu_host, fu_taps, fd_host, fd_taps,
+                                         up, down, px0, px1, py0, py1, gain, slope, clamp, out_scale, flip_filter, 0, stream);
+}
+
+extern "C" int afcm_filtered_lrelu_tc_padded(const void* x, const int64_t* xs, int x_dtype, void* y, const int64_t* ys, int y_dtype,
+                                             const float* b, const void* skip,
+                                             int N, int C, int xh, int xw, int yh, int yw,
+                                             const float* fu_host, int fu_taps, const float* fd_host, int fd_taps,
+                                             int up, int down, int px0, int px1, int py0, int py1,
+                                             float gain, float slope, float clamp, float out_scale, int flip_filter,
+                                             int zero_pad_cols, void* stream)
+{
+    AFCM_CHECK_ARG(zero_pad_cols == 0 || (zero_pad_cols == 2 && ys && ys[2] >= yw + 2), "zero_pad_cols must be 0, or 2 with a row pitch >= yw + 2");
     AFCM_CHECK_ARG(x && y && xs && ys, "x, y and their strides must be given");
     AFCM_CHECK_ARG((x_dtype == AFCM_F32 || x_dtype == AFCM_F16) && (y_dtype == AFCM_F32 || y_dtype == AFCM_F16),
                    "x and y must be float16 or float32");
@@ -764,7 +785,7 @@ extern "C" int afcm_filtered_lrelu_tc(const void* x, const int64_t* xs, int x_dt
     p.x = x; p.y = y; p.b = b; p.skip = skip;
     p.xs_n = xs[0]; p.xs_c = xs[1]; p.xs_h = (int)xs[2];
     p.ys_n = ys[0]; p.ys_c = ys[1]; p.ys_h = (int)ys[2];
-    p.C = C; p.xh = xh; p.xw = xw; p.yh = yh; p.yw = yw;
+    p.C = C; p.xh = xh; p.xw = xw; p.yh = yh; p.yw = yw; p.zero_cols = zero_pad_cols;
     // phase shift s: the strip's first up-sampled sample is a multiple of `up` away from the padding origin;
     // delta: one extra input column in front so that the column pairs are aligned.
     p.sx = floor_mod(-px0, up);

@@ -194,6 +194,6 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
 // Host: cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link dependency).  16-bit elements,
 // SWIZZLE_128B, rank 3..4; strides[] are the byte strides of dimensions 1..rank-1.
 int encode_tiled(CUtensorMap* map, int tc_dtype, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
-                 const uint32_t* box);
+                 const uint32_t* box, bool swizzle128 = true);
 
 }  // namespace afcm

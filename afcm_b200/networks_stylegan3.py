@@ -318,11 +318,13 @@ class _AliasFreeLayerBase(torch.nn.Module):
         pad_hi = pad_total - pad_lo
         self.padding = [int(pad_lo[0]), int(pad_hi[0]), int(pad_lo[1]), int(pad_hi[1])]
 
-    def _filtered_lrelu(self, x, gain, slope, skip=None, out_scale=1.0, out_dtype=None, bias_done=False):
+    def _filtered_lrelu(self, x, gain, slope, skip=None, out_scale=1.0, out_dtype=None, bias_done=False, conv_ready=False):
         """bias + filtered leaky ReLU + clamp (NET:371-372 / NET:510-511), with the skip addition
         (NET:376-377) and the output scale (NET:699-700) folded into the kernel epilogue when no autograd
         graph is needed.  On the fast inference path (conv2d_gradfix.fast_path()) the tensor-core kernel
-        runs it on fp16 planes; `out_dtype` then selects the storage type of the result."""
+        runs it on fp16 planes; `out_dtype` then selects the storage type of the result.  `conv_ready`: the result feeds a
+        3x3 convolution -- it is stored at the row pitch W + 2 with two zero columns behind every row, the flat plane the
+        tcgen05 GEMM reads directly (no pack pass between the two operators)."""
         b = None if bias_done else self.bias.to(torch.float32)    # bias_done: the conv epilogue already added it
         needs_graph = torch.is_grad_enabled() and (x.requires_grad or (b is not None and b.requires_grad))
         if not needs_graph:
@@ -332,7 +334,8 @@ class _AliasFreeLayerBase(torch.nn.Module):
                 y = filtered_lrelu.filtered_lrelu_tc(x, self.up_filter, self.down_filter, b, up=self.up_factor,
                                                      down=self.down_factor, padding=self.padding, gain=float(gain),
                                                      slope=float(slope), clamp=self.conv_clamp, skip=skip,
-                                                     out_scale=float(out_scale), out_dtype=out_dtype or x.dtype)
+                                                     out_scale=float(out_scale), out_dtype=out_dtype or x.dtype,
+                                                     conv_ready=conv_ready)
                 if y is not None:
                     return y
             if x.dtype == torch.float32:
@@ -398,7 +401,7 @@ class SynthesisLayer(_AliasFreeLayerBase):
         return y if rc == 0 else None
 
     def forward(self, x, w, global_w, E_features=None, include_skip=True, noise_mode='random', force_fp32=False,
-                update_emas=False, out_scale=1.0, out_dtype=None):
+                update_emas=False, out_scale=1.0, out_dtype=None, conv_ready=False):
         assert noise_mode in ['random', 'const', 'none']
         misc.assert_shape(x, [None, self.in_channels, int(self.in_size[1]), int(self.in_size[0])])
         misc.assert_shape(w, [x.shape[0], self.w_dim])
@@ -427,7 +430,7 @@ class SynthesisLayer(_AliasFreeLayerBase):
         gain = 1 if self.is_torgb else np.sqrt(2)
         slope = 1 if self.is_torgb else 0.2
         x = self._filtered_lrelu(x, gain, slope, skip=x_skip if include_skip else None, out_scale=out_scale,
-                                 out_dtype=out_dtype, bias_done=fast)
+                                 out_dtype=out_dtype, bias_done=fast, conv_ready=conv_ready and fast)
         misc.assert_shape(x, [None, self.out_channels, int(self.out_size[1]), int(self.out_size[0])])
         return x
 
@@ -453,7 +456,7 @@ class EncoderLayer(_AliasFreeLayerBase):
                             out_half_width, conv_kernel, filter_size, lrelu_upsampling, use_radial_filters, False,
                             is_critically_sampled)
 
-    def forward(self, x, force_fp32=False, update_emas=False):
+    def forward(self, x, force_fp32=False, update_emas=False, conv_ready=False):
         misc.assert_shape(x, [None, self.in_channels, int(self.in_size[1]), int(self.in_size[0])])
         if update_emas:
             magnitude_cur = x.detach().to(torch.float32).square().mean()
@@ -465,7 +468,7 @@ class EncoderLayer(_AliasFreeLayerBase):
             x = conv2d_gradfix.conv2d_native(x if fast else x.float(), self.weight, self.conv_kernel - 1, pre_scale=self.weight_gain,
                                              out_dtype=conv2d_gradfix.act_dtype if fast else None,
                                              bias=self.bias.detach().float() if fast else None)
-        x = self._filtered_lrelu(x, np.sqrt(2), 0.2, bias_done=fast)
+        x = self._filtered_lrelu(x, np.sqrt(2), 0.2, bias_done=fast, conv_ready=conv_ready and fast)
         misc.assert_shape(x, [None, self.out_channels, int(self.out_size[1]), int(self.out_size[0])])
         return x
 
@@ -644,7 +647,7 @@ class SynthesisNetwork(torch.nn.Module):
         for idx in range(self.num_layers):                                            # NET:673-680
             rev_idx = self.num_layers - idx - 1
             rev_prev = self.num_layers - max(idx - 1, 0) - 1
-            x = getattr(self, f'encoder_{idx}')(x, **enc_kwargs)
+            x = getattr(self, f'encoder_{idx}')(x, conv_ready=True, **enc_kwargs)     # every encoder output feeds a 3x3 convolution
             if (self.sizes[rev_idx] != self.sizes[rev_prev]) and self.sizes[rev_prev] != self.sizes[0]:
                 E_features[self.sizes[rev_idx]] = x
         g = self.e_16x16(x)                                                           # NET:682-686
@@ -663,8 +666,9 @@ class SynthesisNetwork(torch.nn.Module):
             scale = self.output_scale if idx == last else 1.0                         # NET:699-700 folded
             # fast path: activations stay fp16 up to and including the input of the fused ToRGB kernel
             od = None
+            feeds_conv = idx + 1 <= last and getattr(self, self.layer_names[idx + 1]).conv_kernel == 3
             x = getattr(self, name)(x, w, img_global, E_features, include_skip, out_scale=scale, out_dtype=od,
-                                    **layer_kwargs)
+                                    conv_ready=feeds_conv, **layer_kwargs)
         misc.assert_shape(x, [None, self.img_channels_out, self.img_resolution, self.img_resolution])
         return x.to(torch.float32)
 

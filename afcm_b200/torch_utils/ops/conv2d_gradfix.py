@@ -122,7 +122,6 @@ def conv2d_native(x, w, padding, icoef=None, ocoef=None, pre_scale=1.0, normaliz
         raise RuntimeError('afcm conv2d: activations must be float32 (or float16 on the tensor-core path)')
     if out_dtype != torch.float32 and not (use_tc and out_dtype == torch.float16):
         raise RuntimeError('afcm conv2d: the result is float32 (or float16 on the tensor-core path)')
-    x = x.contiguous()
     OH, OW = H + 2 * padding - kh + 1, W + 2 * padding - kw + 1
     y = out if out is not None else torch.empty([N, Co, OH, OW], dtype=out_dtype, device=x.device)
     assert y.dtype == out_dtype and y.is_contiguous()
@@ -130,13 +129,17 @@ def conv2d_native(x, w, padding, icoef=None, ocoef=None, pre_scale=1.0, normaliz
     ent = prepare_weight(w, pre_scale, normalize, want_tc=use_tc)
     flops = 2.0 * N * Co * Ci * kh * kw * OH * OW
     if use_tc and direct_nchw and padding == 2 and x.dtype == torch.float16 and tc_dtype == torch.float16 and W % 2 == 0:
-        # no packed copy of the activations -- the kernel's producer warps build the A tiles from the planes
-        rc = _lib.timed('conv2d_tc', flops, lambda: L.afcm_conv2d_tc_nchw(
-            _lib.ptr(x), _lib.ptr(icoef), _lib.ptr(ent[('w_tc', tc_dtype)]), _lib.ptr(ocoef), _lib.ptr(bias), _lib.ptr(y),
-            _lib.dtype_code(out_dtype), N, Ci, H, W, Co, st))
-        _lib.check(rc, allow_unsupported=True)
-        if rc == 0:
-            return y
+        # no packed copy of the activations -- the kernel's producer warps build the A tiles from the planes.
+        # Dense planes (pitch W) or planes stored at the pitch W + 2 with zero pad columns (filtered_lrelu.conv_ready_empty)
+        pitch = W + 2 if x.stride() == (Ci * H * (W + 2), H * (W + 2), W + 2, 1) else (W if x.is_contiguous() else 0)
+        if pitch and (H * pitch) % 8 == 0 and x.data_ptr() % 16 == 0:
+            rc = _lib.timed('conv2d_tc', flops, lambda: L.afcm_conv2d_tc_nchw(
+                _lib.ptr(x), pitch, _lib.ptr(icoef), _lib.ptr(ent[('w_tc', tc_dtype)]), _lib.ptr(ocoef), _lib.ptr(bias), _lib.ptr(y),
+                _lib.dtype_code(out_dtype), N, Ci, H, W, Co, st))
+            _lib.check(rc, allow_unsupported=True)
+            if rc == 0:
+                return y
+    x = x.contiguous()
     if use_tc:
         plane = int(L.afcm_conv_tc_plane_elems(H, W, Ci))
         xp = torch.empty([N, plane], dtype=tc_dtype, device=x.device)

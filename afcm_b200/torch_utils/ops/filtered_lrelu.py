@@ -145,8 +145,16 @@ def t5_eligible(x, b):
     return x.data_ptr() % 16 == 0 and all((int(st) * 2) % 16 == 0 for st in x.stride()[:3])
 
 
+def conv_ready_empty(shape, dtype, device):
+    """An [N,C,H,W] result tensor stored at the row pitch W + 2: with `zero_pad_cols=2` filtered_lrelu_tc() writes zeros into the
+    two extra columns, which makes the allocation the flat plane of row pitch W + 2 that the tcgen05 convolution reads directly
+    (conv2d_gradfix.conv2d_native, afcm_conv2d_tc_nchw with x_pitch = W + 2).  Returns the [N,C,H,W] view."""
+    N, C, H, W = [int(v) for v in shape]
+    return torch.empty([N, C, H, W + 2], dtype=dtype, device=device)[..., :W]
+
+
 def filtered_lrelu_tc(x, fu, fd, b=None, up=1, down=1, padding=0, gain=np.sqrt(2), slope=0.2, clamp=None,
-                      flip_filter=False, skip=None, out_scale=1.0, out_dtype=None, out=None, impl=None):
+                      flip_filter=False, skip=None, out_scale=1.0, out_dtype=None, out=None, impl=None, zero_pad_cols=0, conv_ready=False):
     """Tensor-core forward of filtered_lrelu (afcm_filtered_lrelu_tc, csrc/flr_tc.cu): same arguments and
     result as filtered_lrelu() up to fp16 operand rounding (max |err| <= 2e-3 * max|y|).  Inference only (no
     autograd, no sign tensor).  `skip` is added to the result and `out_scale` multiplies it (NET:376-377,
@@ -168,12 +176,18 @@ def filtered_lrelu_tc(x, fu, fd, b=None, up=1, down=1, padding=0, gain=np.sqrt(2
     yh, yw = _lib._c.c_int(), _lib._c.c_int()
     _lib.check(L.afcm_filtered_lrelu_out_size(xh, xw, up, down, fu_n, fd_n, px0, px1, py0, py1, yh, yw))
     yh, yw = yh.value, yw.value
-    y = out if out is not None else torch.empty([N, C, yh, yw], dtype=out_dtype, device=x.device)
+    if conv_ready and out is None and impl != 't5' and yw % 2 == 0:
+        y = conv_ready_empty([N, C, yh, yw], out_dtype, x.device)         # row pitch yw + 2, the kernel writes the zero columns
+        zero_pad_cols = 2
+    else:
+        y = out if out is not None else torch.empty([N, C, yh, yw], dtype=out_dtype, device=x.device)
     assert y.shape == (N, C, yh, yw) and y.dtype == out_dtype and y.stride(3) == 1
     if b is not None:
         b = b.detach().float().contiguous()
     if skip is not None:
-        assert skip.shape == y.shape and skip.dtype == y.dtype and skip.stride() == y.stride()
+        assert skip.shape == y.shape and skip.dtype == y.dtype
+        if skip.stride() != y.stride():
+            skip = skip.contiguous() if y.is_contiguous() else conv_ready_empty(y.shape, y.dtype, y.device).copy_(skip)
     clamp = float(clamp) if clamp is not None else float('inf')
     nbytes = x.element_size() * x.numel() + y.element_size() * y.numel() * (2 if skip is not None else 1)
     if impl == 't5' or (impl is None and t5_eligible(x, b)):
@@ -188,11 +202,11 @@ def filtered_lrelu_tc(x, fu, fd, b=None, up=1, down=1, padding=0, gain=np.sqrt(2
             return y
         if impl == 't5':
             return None
-    rc = _lib.timed('filtered_lrelu', nbytes, lambda: L.afcm_filtered_lrelu_tc(
+    rc = _lib.timed('filtered_lrelu', nbytes, lambda: L.afcm_filtered_lrelu_tc_padded(
         _lib.ptr(x), _lib.i64x4(x.stride()), _lib.dtype_code(x.dtype), _lib.ptr(y), _lib.i64x4(y.stride()),
         _lib.dtype_code(y.dtype), _lib.ptr(b), _lib.ptr(skip), N, C, xh, xw, yh, yw,
         _lib.np_ptr(fu_h), fu_n, _lib.np_ptr(fd_h), fd_n, up, down, px0, px1, py0, py1,
-        float(gain), float(slope), clamp, float(out_scale), int(bool(flip_filter)), _lib.stream_ptr(x.device)))
+        float(gain), float(slope), clamp, float(out_scale), int(bool(flip_filter)), int(zero_pad_cols), _lib.stream_ptr(x.device)))
     _lib.check(rc, allow_unsupported=True)
     return y if rc == 0 else None
 

@@ -97,6 +97,16 @@ int afcm_filtered_lrelu_tc(const void* x, const int64_t* xs, int x_dtype, void* 
                            int up, int down, int px0, int px1, int py0, int py1,
                            float gain, float slope, float clamp, float out_scale, int flip_filter,
                            void* stream);
+/* The same call writing, behind the last column of every output row, `zero_pad_cols` (0 or 2) zero samples: a result stored
+ * at the row pitch yw + 2 (ys[2] >= yw + 2) is then the flat plane of row pitch W + 2 that afcm_conv2d_tc_nchw reads without
+ * any row bookkeeping (x_pitch = W + 2). */
+int afcm_filtered_lrelu_tc_padded(const void* x, const int64_t* xs, int x_dtype, void* y, const int64_t* ys, int y_dtype,
+                           const float* b, const void* skip,
+                           int N, int C, int xh, int xw, int yh, int yw,
+                           const float* fu_host, int fu_taps, const float* fd_host, int fd_taps,
+                           int up, int down, int px0, int px1, int py0, int py1,
+                           float gain, float slope, float clamp, float out_scale, int flip_filter,
+                           int zero_pad_cols, void* stream);
 /* Scheduling of afcm_filtered_lrelu_tc for tuning (process-global, not part of the stable ABI): n >= 1 = persistent warps,
  * at most n resident waves of CTAs (default 16, the measured optimum); 0 = one warp per 16-column strip. */
 int afcm_filtered_lrelu_tc_set_waves(int waves);
@@ -213,11 +223,16 @@ int afcm_conv_tc_pack(const void* x, int x_dtype, const float* icoef, void* xp, 
 int afcm_conv2d_tc(const void* xp, const void* w_tc, const float* ocoef, const float* bias, void* y, int y_dtype, int tc_dtype,
                    int N, int Ci, int H, int W, int Co, int pad, void* stream);
 /* The same GEMM WITHOUT the pack step (NET:365-377 / NET:503-511: the convolution consumes what the preceding
- * filtered_lrelu wrote): x [N,Ci,H,W] fp16 NCHW contiguous is read directly, eight producer warps of the kernel transpose
- * 8-channel x 8-pixel blocks in registers and store them into the K-major swizzled tile the tensor core reads; icoef
+ * filtered_lrelu wrote): x [N,Ci,H,W] fp16 NCHW contiguous is read directly (TMA ring of raw [64 channels][152 elements]
+ * tiles), eight producer warps of the kernel transpose 8-channel x 8-pixel blocks in registers and store them into the
+ * K-major swizzled tile the tensor core reads; icoef
  * [N,Ci] or NULL is applied on the way (fp32 product, one rounding -- bit-identical to afcm_conv_tc_pack + afcm_conv2d_tc).
- * Full padding (2), fp16 operands; returns AFCM_ERR_UNSUPPORTED for an odd W or a base address that is not 4-byte aligned. */
-int afcm_conv2d_tc_nchw(const void* x, const float* icoef, const void* w_tc, const float* ocoef, const float* bias, void* y,
+ * x_pitch = W: dense planes.  x_pitch = W + 2: planes [N,Ci,H,W+2] whose last two columns are zeros (written by
+ * afcm_filtered_lrelu_tc_padded) -- the flat plane of the GEMM formulation then exists in memory and the producers copy
+ * without row bookkeeping (measured 15-20 % faster on the 64-channel layers).
+ * Full padding (2), fp16 operands; returns AFCM_ERR_UNSUPPORTED for an odd W, H * x_pitch not a multiple of 8 or a base
+ * address that is not 16-byte aligned (the raw tiles travel by TMA from the flat [N][Ci][H x_pitch] view of x). */
+int afcm_conv2d_tc_nchw(const void* x, int x_pitch, const float* icoef, const void* w_tc, const float* ocoef, const float* bias, void* y,
                         int y_dtype, int N, int Ci, int H, int W, int Co, void* stream);
 
 /* Debug / tuning aids, not part of the stable ABI: progress markers of the tcgen05 kernel in mapped host memory;

@@ -142,3 +142,47 @@ def test_conv2d_tc_rowreuse_modes_exact(mode):
             assert torch.equal(ref1, got1), (mode, 'pad1', N, Ci, Co, H, W)
     finally:
         _lib.lib().afcm_conv_tc_set_rowreuse(-1)
+
+
+@pytest.mark.parametrize('shape', [(2, 64, 64, 36, 36), (1, 4, 64, 52, 52), (2, 91, 181, 30, 22), (1, 181, 256, 38, 36), (2, 512, 512, 36, 36),
+                                   (1, 362, 512, 20, 84), (1, 128, 96, 276, 276), (1, 96, 300, 20, 20), (3, 8, 16, 8, 130)])
+@pytest.mark.parametrize('mod', [False, True])
+def test_conv2d_tc_direct_nchw_is_bit_identical_to_pack(shape, mod):
+    """afcm_conv2d_tc_nchw (producer warps build the A tiles from the fp16 NCHW planes, modulation applied on the
+    way) returns exactly what afcm_conv_tc_pack + afcm_conv2d_tc return -- every pipeline of the kernel (resident weights,
+    combined stages, separate A / B rings), ragged channel counts, planes from 8 to 276 pixels, several rows per tile."""
+    from afcm_b200.torch_utils.ops import conv2d_gradfix
+    N, Ci, Co, H, W = shape
+    dev = torch.device('cuda:0')
+    g = torch.Generator(device='cpu').manual_seed(31)
+    x = torch.randn(N, Ci, H, W, generator=g).to(dev).half()
+    w = torch.randn(Co, Ci, 3, 3, generator=g).to(dev)
+    icoef = (torch.rand(N, Ci, generator=g) + 0.5).to(dev) if mod else None
+    ocoef = (torch.rand(N, Co, generator=g) + 0.5).to(dev) if mod else None
+    bias = torch.randn(Co, generator=g).to(dev)
+    scale = 1.0 / np.sqrt(Ci * 9)
+    conv2d_gradfix.set_conv_impl('f32', torch.float16)
+    run = lambda: conv2d_gradfix.conv2d_native(x, w, 2, icoef=icoef, ocoef=ocoef, pre_scale=scale, impl='tc', out_dtype=torch.float16, bias=bias)
+    try:
+        conv2d_gradfix.direct_nchw = False
+        ref = run()
+        conv2d_gradfix.direct_nchw = True
+        n0 = _lib_launches()
+        got = run()
+        assert _lib_launches() - n0 == (1 if (H * W) % 8 == 0 else 2)          # one kernel: no pack launch (H W % 8: TMA stride rule)
+        # the same planes stored at the row pitch W + 2 with zero pad columns (what filtered_lrelu_tc writes for the convolution)
+        xq = torch.zeros(N, Ci, H, W + 2, device=dev, dtype=torch.float16)
+        xq[..., :W] = x
+        x = xq[..., :W]
+        n0 = _lib_launches()
+        got2 = run()
+        assert _lib_launches() - n0 == (1 if (H * (W + 2)) % 8 == 0 else 2)
+    finally:
+        conv2d_gradfix.direct_nchw = True
+    assert got.shape == ref.shape and torch.equal(got, ref)
+    assert torch.equal(got2, ref)
+
+
+def _lib_launches():
+    from afcm_b200 import _lib
+    return _lib.launch_count()

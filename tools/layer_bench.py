@@ -63,6 +63,10 @@ def main():
              [(n, getattr(S, n)) for n in S.layer_names]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     B = args.batch
+    if os.environ.get('AFCM_TC_ROWREUSE'):
+        _lib.lib().afcm_conv_tc_set_rowreuse(int(os.environ['AFCM_TC_ROWREUSE']))
+    if os.environ.get('AFCM_TC_DBG'):
+        _lib.lib().afcm_conv_tc_debug_buffer(int(os.environ['AFCM_TC_DBG']) << 8)
     if os.environ.get('AFCM_FTC_WAVES'):
         _lib.lib().afcm_filtered_lrelu_tc_set_waves(int(os.environ['AFCM_FTC_WAVES']))
     if args.tile:
@@ -132,6 +136,22 @@ def main():
                 pbytes = float(x.element_size() * x.numel() + 2 * xp.numel())
                 row.update(pack_ms=pms, pack_gbs=pbytes / pms / 1e6, conv_tc_ms=gms, conv_tc_tflops=flops / gms / 1e9, conv_tc_frac=flops / gms / 1e9 / tf)
                 tot['conv_tc_ms'] += gms; tot['pack_ms'] += pms
+                if 'conv_nchw' in ops and x.dtype == torch.float16:
+                    # the GEMM reading the fp16 NCHW planes itself (no pack pass)
+                    direct = lambda: _lib.check(Lb.afcm_conv2d_tc_nchw(_lib.ptr(x), H, None, _lib.ptr(ent[('w_tc', torch.float16)]), None, None,
+                                                                       _lib.ptr(y), _lib.dtype_code(y.dtype), B, cin, H, H, cout, st))
+                    dms = time_cuda(direct, flush=flush)
+                    row.update(conv_nchw_ms=dms, conv_nchw_tflops=flops / dms / 1e9, conv_nchw_frac=flops / dms / 1e9 / tf)
+                    tot['conv_nchw_ms'] = tot.get('conv_nchw_ms', 0.0) + dms
+                    # planes stored at the pitch W + 2 with zero pad columns (what filtered_lrelu_tc writes on the fast path)
+                    xq = torch.zeros(B, cin, H, H + 2, device=dev, dtype=torch.float16)
+                    xq[..., :H] = x
+                    pitched = lambda: _lib.check(Lb.afcm_conv2d_tc_nchw(_lib.ptr(xq), H + 2, None, _lib.ptr(ent[('w_tc', torch.float16)]), None, None,
+                                                                        _lib.ptr(y), _lib.dtype_code(y.dtype), B, cin, H, H, cout, st))
+                    qms = time_cuda(pitched, flush=flush)
+                    row.update(conv_pitched_ms=qms)
+                    tot['conv_pitched_ms'] = tot.get('conv_pitched_ms', 0.0) + qms
+                    del xq
                 del xp, y
             if 'conv_f32' in ops:
                 fms = time_cuda(lambda: conv2d_gradfix.conv2d_native(x.float(), w, 2, impl='f32'), iters=2, warmup=1)
@@ -149,6 +169,8 @@ def main():
         summ['flrelu_tc_gbs'] = tot['flrelu_tc_bytes'] / tot['flrelu_tc_ms'] / 1e6
         summ['flrelu_tc_frac_of_measured_hbm'] = summ['flrelu_tc_gbs'] / hbm
         summ['flrelu_tc_ms_per_slice'] = tot['flrelu_tc_ms'] / B
+    if tot.get('conv_nchw_ms'):
+        summ['conv_nchw_tflops'] = tot['flops'] / tot['conv_nchw_ms'] / 1e9
     if tot['conv_tc_ms']:
         summ['conv_tc_tflops'] = tot['flops'] / tot['conv_tc_ms'] / 1e9
         summ['conv_tc_frac_of_measured_bf16'] = summ['conv_tc_tflops'] / tf
