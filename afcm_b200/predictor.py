@@ -7,9 +7,13 @@ Reference behaviour restated here (paths relative to the reference repo):
     [0, D-1]; `slice_idx` c = (i - idx_A) / t.  t = 1 is plain cross-modality translation (c = 0), t > 1 is
     through-plane super-resolution, and t need not be an integer.
   * models/comodgan_model.py:101-108 -- z ~ N(0, I) per slice, c = slice_idx.
-  * models/predictor.py:144-202 -- slices are processed batch by batch and written into the output volume.  With the
-    2-D generator every output voxel is produced exactly once (patch_halo z = 0), so the overlap averaging of the
-    reference reduces to a plain scatter, which is what collect() does.
+  * models/predictor.py:144-202 with data/utils.py:85-124 -- the test loader cuts every slice into patches of
+    `patch_shape` (1 x 256 x 256) at `stride_shape` (1 x 32 x 32; the last patch of an axis is aligned to its end),
+    each prediction loses `patch_halo` (0, 8, 8) voxels on the sides that are not volume borders (remove_halo,
+    models/predictor.py:17-51), the remainders are ACCUMULATED into the prediction map while a normalisation mask counts
+    the visits, and the map is divided by the mask at the end.  A 256 x 256 volume has exactly one patch per slice and no
+    halo is removed, so there the procedure is a plain scatter (the fast path of VolumePredictor); larger in-plane
+    sizes take predict_patches() below, which restates the accumulate / normalise procedure.
 Slices are independent, so ranks own contiguous blocks of output slices (inference.slice_partition) and exchange
 nothing while computing; the only communication is the final gather of results (`collect`), which is not on the data
 path and works with any torch.distributed backend (gloo in the CPU tests, nccl on the GPUs).
@@ -56,6 +60,54 @@ def build_stacks(volume, lo, hi, thickness=1):
     return x, c
 
 
+def gen_indices(i, k, s):
+    """Patch origins along one axis (data/utils.py:119-124): 0, s, 2s, ... while the patch fits, then one patch aligned to
+    the end of the axis if the last regular one stops short of it."""
+    assert i >= k, 'Sample size has to be bigger than the patch size'
+    out = list(range(0, i - k + 1, s))
+    if out[-1] + k < i:
+        out.append(i - k)
+    return out
+
+
+def patch_grid(H, W, patch=(256, 256), stride=(32, 32)):
+    """(y, x) origins of the in-plane patches of one slice, in the reference's iteration order (data/utils.py:100-116)."""
+    return [(y, x) for y in gen_indices(H, patch[0], stride[0]) for x in gen_indices(W, patch[1], stride[1])]
+
+
+def halo_window(start, size, full, pad):
+    """One axis of remove_halo (models/predictor.py:22-36): the part of a patch [start, start + size) that is kept and where it
+    lands in the volume.  -> (patch slice, volume slice).  A side that touches the volume border keeps its voxels."""
+    stop = start + size
+    p0, i0 = (0, 0) if start == 0 else (pad, start + pad)
+    if stop == full:
+        p1, i1 = size, full
+    else:
+        p1, i1 = (size - pad, stop - pad) if pad != 0 else (1, stop)        # (pad == 0 away from the border keeps ONE voxel: the
+    return slice(p0, p1), slice(i0, i1)                                    #  reference's `-pad if pad != 0 else 1`)
+
+
+def latents_for(lo, hi, seed, z_dim):
+    """z ~ N(0, I) of output slices [lo, hi): a function of (seed, slice index, component) only -- a counter-based generator
+    (splitmix64 hash -> two uniforms -> Box-Muller), vectorised over the whole block, so the values do not depend on how the
+    volume is sharded or batched."""
+    n = max(hi - lo, 0)
+    if n == 0:
+        return torch.empty([0, z_dim], dtype=torch.float32)
+    idx = (np.arange(lo, hi, dtype=np.uint64)[:, None] * np.uint64(z_dim) + np.arange(z_dim, dtype=np.uint64)[None, :]) * np.uint64(2)
+
+    def mix(v):
+        with np.errstate(over='ignore'):
+            v = v + np.uint64(0x9E3779B97F4A7C15) * (np.uint64(seed) + np.uint64(1))
+            v = (v ^ (v >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            v = (v ^ (v >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            return v ^ (v >> np.uint64(31))
+    u1 = ((mix(idx) >> np.uint64(11)).astype(np.float64) + 1.0) / 9007199254740993.0          # (0, 1)
+    u2 = (mix(idx + np.uint64(1)) >> np.uint64(11)).astype(np.float64) / 9007199254740992.0   # [0, 1)
+    z = np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
+    return torch.from_numpy(z.astype(np.float32))
+
+
 class VolumePredictor:
     """Runs the generator over this rank's block of output slices of a volume.
 
@@ -79,15 +131,45 @@ class VolumePredictor:
     def latents(self, lo, hi, seed):
         """z of every output slice, a function of (seed, slice index) only, so the result does not depend on how
         the volume is sharded."""
-        z = torch.empty([max(hi - lo, 0), self.z_dim], dtype=torch.float32)
-        for r, i in enumerate(range(lo, hi)):
-            g = torch.Generator().manual_seed(int(seed) * 1000003 + i)
-            z[r] = torch.randn(self.z_dim, generator=g)
-        return z
+        return latents_for(lo, hi, int(seed), self.z_dim)
+
+    def predict_patches(self, volume, thickness=1, seed=0, patch=(256, 256), stride=(32, 32), halo=(8, 8)):
+        """The reference's patch-wise prediction of this rank's block of slices for volumes whose slices are larger than the
+        generator's field (models/predictor.py:144-202): every slice is cut into patches (patch_grid), every patch of every
+        slice goes through the generator (its 4-slice stack is cut at the same window), the halo is removed on the sides that
+        are not volume borders, the remainders are accumulated and the visit counts normalise the sum.  All patches of a
+        slice share the slice's z and c.  -> (y [n,1,H,W] float32, (lo, hi))."""
+        vol = np.asarray(volume)
+        D, H, W = vol.shape
+        lo, hi = slice_partition(D, self.world_size, self.rank)
+        n = max(hi - lo, 0)
+        grid = patch_grid(H, W, patch, stride)
+        acc = np.zeros((n, 1, H, W), dtype=np.float32)
+        cnt = np.zeros((n, 1, H, W), dtype=np.uint8)
+        x_full, c = build_stacks(vol, lo, hi, thickness)
+        z = self.latents(lo, hi, seed)
+        items = [(r, y0, x0) for r in range(n) for (y0, x0) in grid]
+        with torch.no_grad():
+            for b0 in range(0, len(items), self.batch):
+                chunk = items[b0:b0 + self.batch]
+                xb = np.stack([x_full[r, :, y0:y0 + patch[0], x0:x0 + patch[1]] for r, y0, x0 in chunk])
+                rows = [r for r, _, _ in chunk]
+                yb = self.run(z[rows].to(self.device), torch.from_numpy(c[rows]).to(self.device),
+                              torch.from_numpy(xb).to(self.device)).float().cpu().numpy()
+                for (r, y0, x0), pred in zip(chunk, yb):
+                    py, iy = halo_window(y0, patch[0], H, halo[0])
+                    px, ix = halo_window(x0, patch[1], W, halo[1])
+                    acc[r, :, iy, ix] += pred[:, py, px]
+                    cnt[r, :, iy, ix] += 1
+        return torch.from_numpy(acc / np.maximum(cnt, 1)), (lo, hi)
 
     def __call__(self, volume, thickness=1, seed=0):
         D = int(np.asarray(volume).shape[0])
         lo, hi = slice_partition(D, self.world_size, self.rank)
+        res = getattr(getattr(self.G, 'synthesis', None), 'img_resolution', None)
+        if res is not None and tuple(np.asarray(volume).shape[1:]) != (res, res):
+            # slices larger than the generator's field: the reference's patch / halo / averaging procedure
+            return self.predict_patches(volume, thickness, seed, patch=(res, res))
         if self.device.type == 'cuda' and hi > lo:
             return self._run_pipelined(np.asarray(volume), lo, hi, thickness, seed), (lo, hi)
         x, c = build_stacks(volume, lo, hi, thickness)

@@ -95,3 +95,76 @@ def test_two_rank_gloo_equals_single_rank(D, t):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert np.array_equal(full, single.numpy())
+
+
+# ---- patch-wise prediction: data/utils.py:85-124 + models/predictor.py:17-51,144-202 restated literally -------------------
+def _ref_gen_indices(i, k, s):
+    assert i >= k
+    for j in range(0, i - k + 1, s):
+        yield j
+    if j + k < i:
+        yield i - k
+
+
+def _ref_remove_halo(patch, index, shape, patch_halo):
+    def _new_slices(slicing, max_size, pad):
+        if slicing.start == 0:
+            p_start, i_start = 0, 0
+        else:
+            p_start, i_start = pad, slicing.start + pad
+        if slicing.stop == max_size:
+            p_stop, i_stop = None, max_size
+        else:
+            p_stop, i_stop = (-pad if pad != 0 else 1), slicing.stop - pad
+        return slice(p_start, p_stop), slice(i_start, i_stop)
+    D, H, W = shape
+    i_c, i_z, i_y, i_x = index
+    p_z, i_z = _new_slices(i_z, D, patch_halo[0])
+    p_y, i_y = _new_slices(i_y, H, patch_halo[1])
+    p_x, i_x = _new_slices(i_x, W, patch_halo[2])
+    return patch[(slice(0, patch.shape[0]), p_z, p_y, p_x)], (i_c, i_z, i_y, i_x)
+
+
+@pytest.mark.parametrize('H,W,patch,stride,halo', [(40, 56, 32, 8, 4), (32, 32, 32, 8, 4), (70, 33, 32, 16, 8), (48, 48, 32, 16, 0)])
+def test_patchwise_prediction_matches_the_reference_procedure(H, W, patch, stride, halo):
+    from afcm_b200.predictor import gen_indices, patch_grid
+    assert gen_indices(H, patch, stride) == list(_ref_gen_indices(H, patch, stride))
+    rng = np.random.RandomState(1)
+    D = 5
+    vol = rng.randint(0, 256, size=(D, H, W)).astype(np.uint8)
+    pred = VolumePredictor(None, batch=7, run=_fake_run, device='cpu', z_dim=4)
+    y, blk = pred.predict_patches(vol, thickness=1, seed=3, patch=(patch, patch), stride=(stride, stride), halo=(halo, halo))
+    assert blk == (0, D) and y.shape == (D, 1, H, W)
+    # the reference loops: accumulate un-haloed patches, count visits, divide
+    x_full, c = build_stacks(vol, 0, D, 1)
+    z = pred.latents(0, D, 3)
+    pm = np.zeros((1, D, H, W), np.float32); nm = np.zeros((1, D, H, W), np.uint8)
+    for zi in range(D):
+        for y0 in _ref_gen_indices(H, patch, stride):
+            for x0 in _ref_gen_indices(W, patch, stride):
+                out = _fake_run(z[zi:zi + 1], torch.from_numpy(c[zi:zi + 1]),
+                                torch.from_numpy(x_full[zi:zi + 1, :, y0:y0 + patch, x0:x0 + patch])).numpy()[0]      # [1,p,p]
+                index = (slice(0, 1), slice(zi, zi + 1), slice(y0, y0 + patch), slice(x0, x0 + patch))
+                u, ui = _ref_remove_halo(out[:, None], index, (D, H, W), (0, halo, halo))
+                pm[ui] += u; nm[ui] += 1
+    assert nm.min() >= 1
+    np.testing.assert_allclose(y.numpy()[:, 0], (pm / nm)[0], rtol=1e-6, atol=1e-7)
+
+
+def test_noninteger_thickness_matches_reference_arithmetic():
+    """thickness 2.5 (SURVEY 8(d) config 3): idx_A = int((i // t) * t) and c = (i - idx_A) / t as the reference computes them."""
+    D, t = 23, 2.5
+    for i in range(D):
+        a, sl, c = stack_indices(i, D, t)
+        ra, rsl, rc = _ref_indices(i, D, t)
+        assert a == ra and np.float32(c) == rc[0]
+        assert [None if v is None else int(v) for v in rsl] == sl
+
+
+def test_latents_do_not_depend_on_the_sharding():
+    pred = VolumePredictor(None, run=_fake_run, device='cpu', z_dim=512)
+    full = pred.latents(0, 40, 7)
+    parts = torch.cat([pred.latents(0, 13, 7), pred.latents(13, 14, 7), pred.latents(14, 40, 7)])
+    assert torch.equal(full, parts)
+    assert not torch.equal(full, pred.latents(0, 40, 8))
+    assert abs(float(full.mean())) < 0.03 and abs(float(full.std()) - 1.0) < 0.03 and torch.isfinite(full).all()
