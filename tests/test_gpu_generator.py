@@ -194,3 +194,21 @@ def test_pipelined_generator_matches_direct_call(golden_tiny):
         for (z, c, x), y in zip(batches, outs):
             ref = G(z.to(dev), c.to(dev), x.to(dev), noise_mode='const').cpu()
             assert rel_err(y.numpy(), ref.numpy()) < 1e-6
+
+
+def test_checkpoint_round_trip_on_gpu(golden_tiny, tmp_path):
+    """a reference-format checkpoint file written from the GPU module loads into a fresh GPU module
+    (models/base_model.py:144-199 restated in afcm_b200/checkpoint.py) and the forward reproduces the golden output."""
+    from afcm_b200.checkpoint import load_network, save_network
+    from afcm_b200.networks_stylegan3 import afcm_generator
+    dev = torch.device('cuda:0')
+    g = golden_tiny
+    G = _load_tiny(g, dev)
+    path = save_network(G, str(tmp_path), 'latest', 'G_ema')
+    G2 = afcm_generator(seed=123, device=dev, **TINY)
+    res = load_network(G2, path)
+    assert not res.missing_keys and not res.unexpected_keys
+    with torch.no_grad():
+        y = G2(torch.as_tensor(g['z'], device=dev), torch.as_tensor(g['c'], device=dev), torch.as_tensor(g['x'], device=dev),
+               noise_mode='const')
+    assert rel_err(y.cpu().numpy(), g['y']) < 1e-4
