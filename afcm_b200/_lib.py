@@ -40,6 +40,9 @@ SIGNATURES = {
     'afcm_filtered_lrelu_tc': (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp,           # x xs xdt y ys ydt b skip
                                     _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i,        # N C xh xw yh yw fu n fd n
                                     _i, _i, _i, _i, _i, _i, _f, _f, _f, _f, _i, _vp]),
+    'afcm_filtered_lrelu_tc_signs': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i,
+                                          _i, _i, _i, _i, _i, _i, _f, _f, _f, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp]),
+    'afcm_absmax': (_i, [_vp, _i64, _vp, _vp]),
     'afcm_filtered_lrelu_tc_padded': (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp,           # x xs xdt y ys ydt b skip
                                     _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i,        # N C xh xw yh yw fu n fd n
                                     _i, _i, _i, _i, _i, _i, _f, _f, _f, _f, _i, _i, _vp]),  # up down pads gain slope clamp scale flip stream

@@ -53,6 +53,11 @@ struct FlrTcParams {
     int xs_h, ys_h;                                      // row strides (host-checked to fit 32 bits)
     int C, xh, xw, yh, yw;
     int zero_cols;                                        // columns [yw, yw + zero_cols) of every output row are written as zeros (0 or 2)
+    // sign tensor (training step): uint8 [N, C, sign_h, 4 sign_nw], 2 bits per up-sampled sample (OPS/filtered_lrelu.cpp:87-94);
+    // written by the forward (SIGN == 1), read by the backward (SIGN == 2) at the offset (s_ox, s_oy)
+    uint32_t* signs;
+    int sign_h, sign_nw, s_ox, s_oy;
+    const float* amax;                                    // SIGN == 2: device pointer to max|x| (operand scaling into the fp16 range) or null
     int strips, segs, seg_wblocks;                        // 16-column strips, row segments of 8*seg_wblocks rows
     int units;                                            // strips * segs: warps per plane
     unsigned total_warps;
@@ -134,6 +139,60 @@ __device__ __forceinline__ uint32_t h2_min(uint32_t a, uint32_t b)
     return r;
 }
 
+// ---- sign tensor helpers (lane-level model: tools/flr_sign_pack_model.py; hardware check: tools/microbench/sign_pack_check.cu)
+// codes of the two packed samples of u (pre-activation in units of the clamp) and a = sat(u) - sat(-slope u):
+// bits 0-1 = code of the low half, bits 16-17 = code of the high half; 1 = negative, 2 = clamped (overrides)
+__device__ __forceinline__ uint32_t ftc_codes(uint32_t u, uint32_t a)
+{
+    uint32_t neg, cl;
+    const uint32_t zero = 0u, one = 0x3c003c00u;
+    asm("set.lt.u32.f16x2 %0, %1, %2;" : "=r"(neg) : "r"(u), "r"(zero));
+    const uint32_t mag = a & 0x7fff7fffu;
+    asm("set.ge.u32.f16x2 %0, %1, %2;" : "=r"(cl) : "r"(mag), "r"(one));
+    return (neg & ~cl & 0x00010001u) | (cl & 0x00020002u);
+}
+// c[q][h]: codes of row block q (rows 8 q + 2 t + {0, 1}) and register h (column 8 h + g) of one block of 16 up-sampled columns.
+// Returns the 32-bit word (16 codes, column i at bits 2 i) of row 8 (g >> 2) + 2 t + ((g >> 1) & 1); valid on the lanes with even g.
+__device__ __forceinline__ uint32_t ftc_sign_block_word(const uint32_t (&c)[2][2], unsigned lane)
+{
+    const uint32_t sh = 2u * (lane >> 2);
+    uint32_t P[2][2];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        P[q][0] = (__byte_perm(c[q][0], c[q][1], 0x4400) & 0x00030003u) << sh;
+        P[q][1] = (__byte_perm(c[q][0], c[q][1], 0x6622) & 0x00030003u) << sh;
+    }
+    const bool g2 = (lane & 16u) != 0, g1 = (lane & 8u) != 0;
+    uint32_t R[2];
+#pragma unroll
+    for (int pp = 0; pp < 2; pp++) {
+        const uint32_t send = g2 ? P[0][pp] : P[1][pp], keep = g2 ? P[1][pp] : P[0][pp];
+        R[pp] = keep | __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    const uint32_t send = g1 ? R[0] : R[1], keep = g1 ? R[1] : R[0];
+    const uint32_t S = keep | __shfl_xor_sync(0xffffffffu, send, 8);
+    return S | __shfl_xor_sync(0xffffffffu, S, 4);
+}
+// read direction: the word of row (q, p) lives on lane 4 (4 q + 2 p) + t; every lane fetches its four rows and extracts the codes
+// of its two columns.  m[q][h] = packed half2 multipliers (1, slope, 0) for register h of row block q.
+__device__ __forceinline__ void ftc_sign_block_mult(uint32_t word_of_my_row, unsigned lane, uint32_t h_one_slope, uint32_t (&m)[2][2])
+{
+    const unsigned t = lane & 3u, sh = 2u * (lane >> 2);
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        uint32_t w[2];
+#pragma unroll
+        for (int pp = 0; pp < 2; pp++) w[pp] = __shfl_sync(0xffffffffu, word_of_my_row, (int)(4u * (4u * q + 2u * pp) + t)) >> sh;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint32_t c0 = (w[0] >> (16 * h)) & 3u, c1 = (w[1] >> (16 * h)) & 3u;
+            const uint32_t lo = c0 >= 2u ? 0u : __byte_perm(h_one_slope, 0u, c0 ? 0x4432 : 0x4410);
+            const uint32_t hi = c1 >= 2u ? 0u : __byte_perm(h_one_slope, 0u, c1 ? 0x4432 : 0x4410);
+            m[q][h] = lo | (hi << 16);
+        }
+    }
+}
+
 // 8- or 4-byte asynchronous global -> shared copy; src_bytes == 0 zero-fills without reading
 template <int BYTES>
 __device__ __forceinline__ void cp_async(uint32_t dst, const void* src, int src_bytes)
@@ -148,7 +207,9 @@ template <typename T> struct Pair;
 template <> struct Pair<float> { typedef float2 type; };
 template <> struct Pair<__half> { typedef uint32_t type; };
 
-template <int U, int D, typename TIN, typename TOUT, int ACT, bool FAST>
+// SIGN: 0 = inference (no sign tensor), 1 = forward of the training step (writes the sign tensor), 2 = backward (the op with
+// up / down exchanged; the activation is replaced by the multiplier 1 / slope / 0 the stored code selects, OPS/filtered_lrelu.cu:562-572)
+template <int U, int D, typename TIN, typename TOUT, int ACT, bool FAST, int SIGN = 0>
 struct FtcWarp {
     // FAST: no bias and no skip tensor (the fast inference path: the convolution epilogue has already added the
     // bias).  Zero-filled halo samples then need no masking after the copy and the epilogue has no skip loads.
@@ -162,9 +223,13 @@ struct FtcWarp {
     // constant fragments (the FIR taps); b2r = b2 with the two K halves exchanged (kept as separate registers so
     // that either order is a ready-made operand pair)
     uint32_t a1[Geo::NPH][4], b2[U][2], b2r[U][2], a3[NAL][4], b4[NREL][2];
-    uint32_t h_one, h_nslope, h_slope, h_cl, h_ncl, h_bias;
+    uint32_t h_one, h_nslope, h_slope, h_cl, h_ncl, h_bias, h_one_slope;
     const FlrTcParams& p;
     int g, t;
+    unsigned lane_id;
+    uint32_t* sgn_plane;         // SIGN: sign words of this plane
+    int cur_blk;                 // SIGN: index of the input row block converted last
+    float in_scale, post_scale;  // SIGN == 2: operand scale (a power of two) applied at the input conversion, and its inverse applied to the fp32 result
     // strip state
     const TIN* xf;               // next row block to fetch: plane base + (its first row + g) rows + ix + 2t
     const TIN* xsafe;            // row 0 of the plane at this lane's column origin (source of zero-size copies)
@@ -191,7 +256,7 @@ struct FtcWarp {
     uint32_t P[2][MB][2];        // R1 of the last two input row blocks (slot = block & 1): D-fragments [J 16][Y 8]
     uint32_t carry[JB];          // lower half (rows +8..+15) of the last window of R3
 
-    __device__ FtcWarp(const FlrTcParams& p_, int lane) : p(p_), g(lane >> 2), t(lane & 3) {}
+    __device__ FtcWarp(const FlrTcParams& p_, int lane) : p(p_), g(lane >> 2), t(lane & 3), lane_id((unsigned)lane), sgn_plane(nullptr), cur_blk(0), in_scale(1.f), post_scale(1.f) {}
 
     __device__ void load_consts(const float (*tab)[FTC_TAB])
     {
@@ -244,6 +309,7 @@ struct FtcWarp {
         h_slope = pack_h2(p.slope, p.slope);
         h_cl = pack_h2(p.act_clamp, p.act_clamp);
         h_ncl = pack_h2(-p.act_clamp, -p.act_clamp);
+        h_one_slope = pack_h2(1.f, p.slope);
     }
 
     __device__ void begin_strip(int unit, int plane)
@@ -253,6 +319,7 @@ struct FtcWarp {
         const TIN* xplane = (const TIN*)p.x + n * p.xs_n + c * p.xs_c;
         bias = (!FAST && p.b) ? p.b[c] : 0.f;
         h_bias = pack_h2(bias, bias);
+        if (SIGN) sgn_plane = p.signs + (long long)plane * p.sign_h * p.sign_nw;
         ix = strip * Geo::IXS + p.ix0;
         iy = seg * p.iy_step + p.iy0;
         k0 = strip * 16;
@@ -324,6 +391,7 @@ struct FtcWarp {
     }
     __device__ __forceinline__ uint32_t cvt_pair(const float2& v) const
     {
+        if (SIGN == 2) return pack_h2(v.x * in_scale, v.y * in_scale);        // backward: no bias, gradients scaled into the fp16 range
         return FAST ? pack_h2(v.x, v.y) : pack_h2(v.x + bias, v.y + bias);
     }
     __device__ __forceinline__ uint32_t cvt_pair(const uint32_t& v) const
@@ -340,6 +408,7 @@ struct FtcWarp {
     __device__ __forceinline__ void convert(int yb, uint32_t (&in)[Geo::NC])
     {
         cp_async_wait<FTC_PD - 1>();
+        if (SIGN) cur_blk = yb;
         const uint32_t src = ring + rd;
         rd = (rd + (uint32_t)STAGE_BYTES) & RING_MASK;
         RawT raw[Geo::NC];
@@ -400,19 +469,54 @@ struct FtcWarp {
     template <int CUR, int NB0, int MODE, bool NARROW>
     __device__ __forceinline__ void chunk(int al, uint32_t (&win)[JB][2], uint32_t (&X)[JB])
     {
+        // SIGN: the fragment element (J = 16 mb + 8 h + g, V = 8 (NB0 + q) + 2 t + p) of this chunk is the up-sampled sample
+        //   row uy = D w0 + 8 U (cur_blk - 1) + 8 NB0 + V' - sy,   column ux = D k0 + J - sx     of the sign tensor
+        // (tools/flr_tc_emu.py, tests/test_flr_tc_emu.py); after the packing butterfly the lanes with even g hold one row each
+        const int sgn_row = SIGN ? D * w0 + 8 * U * (cur_blk - 1) + 8 * NB0 + 8 * (g >> 2) + 2 * t + ((g >> 1) & 1) - p.sy : 0;
+        uint32_t T[MB + 1];                      // SIGN == 1: packed words of the column blocks of this lane's row
+        uint32_t sw[MB + 2];                     // SIGN == 2: the stored words this lane's row needs (column blocks + shift spill)
+        int sshift = 0;
+        if (SIGN == 1) {
+#pragma unroll
+            for (int i = 0; i <= MB; i++) T[i] = 0u;
+        }
+        if (SIGN == 2) {
+            // columns ex = D k0 + 16 mb + j - sx + s_ox: word (ex0 >> 4) + mb, shifted by 2 (ex0 & 15) bits; outside the tensor = code 0
+            const int ex0 = D * k0 - p.sx + p.s_ox;
+            const int wi0 = ex0 >> 4;
+            sshift = 2 * (ex0 & 15);
+            const int ey = sgn_row + p.s_oy;
+            const bool rok = !(g & 1) && ey >= 0 && ey < p.sign_h;
+            const uint32_t* rowp = sgn_plane + (long long)(rok ? ey : 0) * p.sign_nw;
+#pragma unroll
+            for (int i = 0; i < MB + 2; i++) {
+                const int wi = wi0 + i;
+                sw[i] = (rok && wi >= 0 && wi < p.sign_nw) ? __ldg(rowp + wi) : 0u;
+            }
+        }
 #pragma unroll
         for (int mb = 0; mb < (NARROW ? Geo::MBN : MB); mb++) {
             const uint32_t quad[4] = {P[0][mb][0], P[0][mb][1], P[1][mb][0], P[1][mb][1]};
             uint32_t e[2][2];
+            uint32_t mlt[2][2];
+            if (SIGN == 2) ftc_sign_block_mult(__funnelshift_r(sw[mb], sw[mb + 1], sshift), lane_id, h_one_slope, mlt);
+            uint32_t cod[2][2];
 #pragma unroll
             for (int q = 0; q < 2; q++) {
                 uint32_t d[2];
                 // slot 0 supplies k 0..7: if it holds the current block the two K halves of the constant swap
                 if (CUR == 1) mma_h(d, quad, b2[NB0 + q][0], b2[NB0 + q][1]);
                 else mma_h(d, quad, b2r[NB0 + q][0], b2r[NB0 + q][1]);
-                e[q][0] = act2(d[0]);
-                e[q][1] = act2(d[1]);
+                if (SIGN == 2) {
+                    e[q][0] = h2_mul(d[0], mlt[q][0]);
+                    e[q][1] = h2_mul(d[1], mlt[q][1]);
+                } else {
+                    e[q][0] = act2(d[0]);
+                    e[q][1] = act2(d[1]);
+                    if (SIGN == 1) { cod[q][0] = ftc_codes(d[0], e[q][0]); cod[q][1] = ftc_codes(d[1], e[q][1]); }
+                }
             }
+            if (SIGN == 1) T[mb] = ftc_sign_block_word(cod, lane_id);
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const int jb = 2 * mb + h;
@@ -428,6 +532,22 @@ struct FtcWarp {
                     asm("add.rn.f16x2 %0, %1, %2;" : "=r"(X[jb]) : "r"(carry[jb]), "r"(win[jb][0]));
                     carry[jb] = win[jb][1];
                 }
+            }
+        }
+        if (SIGN == 1) {
+            // ownership: a strip stores the D aligned words of its own 16 D up-sampled columns (the last strip every word up to the
+            // end of the row), a segment the rows of its own output rows (the last one the rest); sign columns count from the
+            // first sample the down filter reads: word w = column blocks w and w + 1 funnel-shifted by 2 sx bits
+            const int strip = k0 >> 4;
+            int n_own = (strip == p.strips - 1) ? p.sign_nw - D * strip : D;
+            if (n_own > MB) n_own = MB;
+            const int row_lo = max(D * w0, 0);
+            const int row_hi = (w0 + 8 * p.seg_wblocks >= p.yh) ? p.sign_h : D * (w0 + 8 * p.seg_wblocks);
+            if (!(g & 1) && sgn_row >= row_lo && sgn_row < row_hi) {
+                uint32_t* rowp = sgn_plane + (long long)sgn_row * p.sign_nw + D * strip;
+#pragma unroll
+                for (int w = 0; w < MB; w++)
+                    if (w < n_own) rowp[w] = __funnelshift_r(T[w], T[w + 1], 2 * p.sx);
             }
         }
     }
@@ -455,6 +575,7 @@ struct FtcWarp {
                 const uint32_t quad[4] = {X0[2 * kc], X1[2 * kc], X0[2 * kc + 1], X1[2 * kc + 1]};
                 mma_f(c, quad, b4[rel][0], b4[rel][1]);
             }
+            if (SIGN == 2) { c[0] *= post_scale; c[1] *= post_scale; c[2] *= post_scale; c[3] *= post_scale; }
             const bool has_skip = !FAST && p.skip != nullptr;
             const long long kofs = (const TOUT*)p.skip - (const TOUT*)p.y;      // used only when has_skip
             if (!EDGE) {
@@ -641,12 +762,19 @@ struct FtcWarp {
 #ifndef AFCM_FTC_MINB24
 #define AFCM_FTC_MINB24 2
 #endif
-template <int U, int D, typename TIN, typename TOUT, int ACT, bool FAST>
-__global__ void __launch_bounds__(FTC_WARPS * 32, (U == 2 && D == 4) ? AFCM_FTC_MINB24 : (U == 4 ? 4 : AFCM_FTC_MINB22))
+template <int U, int D, typename TIN, typename TOUT, int ACT, bool FAST, int SIGN>
+__global__ void __launch_bounds__(FTC_WARPS * 32, (U == 2 && D == 4) ? AFCM_FTC_MINB24 : (SIGN ? 3 : (U == 4 ? 4 : AFCM_FTC_MINB22)))
 flr_tc_kernel(const __grid_constant__ FlrTcParams p)
 {
     // zero-padded tap tables (index e + FTC_TAB_OFS): the fragments below index them with per-lane offsets
     __shared__ float tab[4][FTC_TAB];
+    // SIGN == 2 (backward): gradients may lie far below the fp16 range; the operands are scaled by a power of two that brings
+    // max|x| (a device-side scalar written by afcm_absmax) to ~256, the fp32 result is scaled back in emit()
+    float in_scale = 1.f;
+    if (SIGN == 2 && p.amax) {
+        const float a = *p.amax;
+        if (a > 0.f && a < 3.0e38f) in_scale = exp2f(fminf(fmaxf(floorf(log2f(256.f / a)), -60.f), 60.f));
+    }
     for (int i = threadIdx.x; i < FTC_TAB; i += blockDim.x) {
         const int e = i - FTC_TAB_OFS;
         const bool u_ok = e >= 0 && e < 6 * U, d_ok = e >= 0 && e < 6 * D;
@@ -658,8 +786,10 @@ flr_tc_kernel(const __grid_constant__ FlrTcParams p)
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     extern __shared__ __align__(16) uint8_t ring_smem[];
-    typedef FtcWarp<U, D, TIN, TOUT, ACT, FAST> W;
+    typedef FtcWarp<U, D, TIN, TOUT, ACT, FAST, SIGN> W;
     W w(p, lane);
+    w.in_scale = in_scale;               // applied to the DATA at the input conversion (the taps are fp16 operands themselves)
+    w.post_scale = 1.f / in_scale;
     w.ring = (uint32_t)__cvta_generic_to_shared(ring_smem) + (uint32_t)(warp * W::WARP_RING_BYTES + lane * W::RAW_BYTES);
     w.load_consts(tab);
     // Persistent warps: the grid is one resident wave, every warp walks over (plane, segment, strip) units with the tap
@@ -678,7 +808,7 @@ static int floor_mod(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
 
 static int g_ftc_waves = 16;          // 0: one warp per unit (no persistence); n: at most n resident waves of CTAs (8..16 measured best)
 
-template <int U, int D, typename TIN, typename TOUT, int ACT, bool FAST>
+template <int U, int D, typename TIN, typename TOUT, int ACT, bool FAST, int SIGN = 0>
 static int launch_tc(FlrTcParams& p, int N, cudaStream_t st)
 {
     p.strips = ceil_div(p.yw + p.zero_cols, 16);
@@ -697,18 +827,18 @@ static int launch_tc(FlrTcParams& p, int N, cudaStream_t st)
     if (planes * p.units > 0x7fffffffLL) { set_error("filtered_lrelu_tc: too many strips"); return AFCM_ERR_INVALID; }
     p.total_warps = (unsigned)(planes * p.units);
     unsigned blocks = (p.total_warps + FTC_WARPS - 1) / FTC_WARPS;
-    const int smem = FTC_WARPS * FtcWarp<U, D, TIN, TOUT, ACT, FAST>::WARP_RING_BYTES;
+    const int smem = FTC_WARPS * FtcWarp<U, D, TIN, TOUT, ACT, FAST, SIGN>::WARP_RING_BYTES;
     // one resident wave (persistent warps); g_ftc_waves > 1 launches that many waves' worth of CTAs (tuning switch)
     static int resident = 0;                  // per instantiation: CTAs per SM x SMs
     if (!resident) {
         int per_sm = 0, sms = 0, dev = 0;
         AFCM_CUDA(cudaGetDevice(&dev));
         AFCM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        AFCM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flr_tc_kernel<U, D, TIN, TOUT, ACT, FAST>, FTC_WARPS * 32, smem));
+        AFCM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flr_tc_kernel<U, D, TIN, TOUT, ACT, FAST, SIGN>, FTC_WARPS * 32, smem));
         resident = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 148);
     }
     if (g_ftc_waves > 0 && blocks > (unsigned)(resident * g_ftc_waves)) blocks = (unsigned)(resident * g_ftc_waves);
-    flr_tc_kernel<U, D, TIN, TOUT, ACT, FAST><<<blocks, FTC_WARPS * 32, smem, st>>>(p);
+    flr_tc_kernel<U, D, TIN, TOUT, ACT, FAST, SIGN><<<blocks, FTC_WARPS * 32, smem, st>>>(p);
     AFCM_LAUNCH_CHECK();
     count_launch();
     return AFCM_OK;
@@ -730,9 +860,50 @@ static int dispatch_act(FlrTcParams& p, int N, int up, int down, int act, cudaSt
     return dispatch_geo<TIN, TOUT, FTC_ACT_MINMAX, false>(p, N, up, down, st);
 }
 
+// max|x| of a dense fp32 tensor into out[0] (a device scalar, zeroed by the launcher): |x| >= 0, so the float bit patterns order
+// like unsigned integers and one atomicMax per block is enough; NaN / Inf inputs are ignored (the scale must stay finite)
+__global__ void __launch_bounds__(256)
+absmax_kernel(const float4* __restrict__ x4, const float* __restrict__ x, long long n4, long long n, unsigned* __restrict__ out)
+{
+    float m = 0.f;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += gridDim.x * 256LL) {
+        const float4 v = x4[i];
+        m = fmaxf(fmaxf(m, fminf(fabsf(v.x), 3.0e38f)), fmaxf(fminf(fabsf(v.y), 3.0e38f), fmaxf(fminf(fabsf(v.z), 3.0e38f), fminf(fabsf(v.w), 3.0e38f))));
+    }
+    if (blockIdx.x == 0)
+        for (long long i = 4 * n4 + threadIdx.x; i < n; i += 256) m = fmaxf(m, fminf(fabsf(x[i]), 3.0e38f));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ float sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 1; w < 8; w++) m = fmaxf(m, sm[w]);
+        atomicMax(out, __float_as_uint(m));
+    }
+}
+
 }  // namespace afcm
 
 using namespace afcm;
+
+extern "C" int afcm_absmax(const float* x, int64_t n, float* out, void* stream)
+{
+    AFCM_CHECK_ARG(x && out && n > 0, "empty problem");
+    AFCM_CHECK_ARG(((uintptr_t)x & 15) == 0, "x must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    AFCM_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
+    const long long n4 = n / 4;
+    long long blocks = (n4 + 256 * 8 - 1) / (256 * 8);
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    absmax_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(x), x, n4, (long long)n, reinterpret_cast<unsigned*>(out));
+    AFCM_LAUNCH_CHECK();
+    count_launch();
+    return AFCM_OK;
+}
 
 extern "C" int afcm_filtered_lrelu_tc_set_waves(int waves) { g_ftc_waves = waves < 0 ? 0 : waves; return AFCM_OK; }
 
@@ -748,6 +919,15 @@ extern "C" int afcm_filtered_lrelu_tc(const void* x, const int64_t* xs, int x_dt
                                          up, down, px0, px1, py0, py1, gain, slope, clamp, out_scale, flip_filter, 0, stream);
 }
 
+static int flr_tc_run(const void* x, const int64_t* xs, int x_dtype, void* y, const int64_t* ys, int y_dtype,
+                      const float* b, const void* skip,
+                      int N, int C, int xh, int xw, int yh, int yw,
+                      const float* fu_host, int fu_taps, const float* fd_host, int fd_taps,
+                      int up, int down, int px0, int px1, int py0, int py1,
+                      float gain, float slope, float clamp, float out_scale, int flip_filter,
+                      int zero_pad_cols, int sign_mode, void* signs, int sign_h, int sign_wb, int s_ox, int s_oy, const float* amax,
+                      void* stream);
+
 extern "C" int afcm_filtered_lrelu_tc_padded(const void* x, const int64_t* xs, int x_dtype, void* y, const int64_t* ys, int y_dtype,
                                              const float* b, const void* skip,
                                              int N, int C, int xh, int xw, int yh, int yw,
@@ -755,6 +935,46 @@ extern "C" int afcm_filtered_lrelu_tc_padded(const void* x, const int64_t* xs, i
                                              int up, int down, int px0, int px1, int py0, int py1,
                                              float gain, float slope, float clamp, float out_scale, int flip_filter,
                                              int zero_pad_cols, void* stream)
+{
+    return flr_tc_run(x, xs, x_dtype, y, ys, y_dtype, b, skip, N, C, xh, xw, yh, yw, fu_host, fu_taps, fd_host, fd_taps, up, down,
+                      px0, px1, py0, py1, gain, slope, clamp, out_scale, flip_filter, zero_pad_cols, AFCM_SIGN_NONE, nullptr, 0, 0, 0, 0,
+                      nullptr, stream);
+}
+
+// The training-step variant of the register-chained kernel: fp32 planes in and out, sign tensor written (forward) or read (backward,
+// the op with up / down exchanged) in the reference's format, interchangeable with afcm_filtered_lrelu / afcm_filtered_lrelu_tcs.
+// sign_mode AFCM_SIGN_WRITE: signs [N,C,sign_h,sign_wb] uint8 as sized by afcm_filtered_lrelu_sign_size, (sx, sy) = 0, a finite
+// clamp in [2^-10, 2^10].  AFCM_SIGN_READ: (sx, sy) = sign offsets (OPS/filtered_lrelu.py:258-259); amax = device pointer to max|x|
+// (afcm_absmax) or NULL: the fp16 operands are scaled by the power of two that brings it to ~256, the fp32 result is scaled back.
+extern "C" int afcm_filtered_lrelu_tc_signs(const void* x, const int64_t* xs, void* y, const int64_t* ys, const float* b,
+                                            int N, int C, int xh, int xw, int yh, int yw,
+                                            const float* fu_host, int fu_taps, const float* fd_host, int fd_taps,
+                                            int up, int down, int px0, int px1, int py0, int py1,
+                                            float gain, float slope, float clamp, int flip_filter,
+                                            int sign_mode, void* signs, int sign_h, int sign_wb, int sx, int sy, const float* amax,
+                                            void* stream)
+{
+    AFCM_CHECK_ARG(sign_mode == AFCM_SIGN_WRITE || sign_mode == AFCM_SIGN_READ, "sign_mode must be AFCM_SIGN_WRITE or AFCM_SIGN_READ");
+    AFCM_CHECK_ARG(signs && sign_h > 0 && sign_wb > 0 && (sign_wb & 3) == 0 && ((uintptr_t)signs & 3) == 0,
+                   "the sign tensor must be given, 4-byte aligned, with a row length that is a multiple of 4 bytes");
+    if (sign_mode == AFCM_SIGN_WRITE) {
+        int sh = 0, swb = 0;
+        afcm_filtered_lrelu_sign_size(yh, yw, down, fd_taps, &sh, &swb);
+        AFCM_CHECK_ARG(sign_h == sh && sign_wb == swb, "sign tensor has shape [%d,%d], expected [%d,%d]", sign_h, sign_wb, sh, swb);
+        AFCM_CHECK_ARG(sx == 0 && sy == 0, "sign offsets must be zero when writing signs");
+    }
+    return flr_tc_run(x, xs, AFCM_F32, y, ys, AFCM_F32, b, nullptr, N, C, xh, xw, yh, yw, fu_host, fu_taps, fd_host, fd_taps, up, down,
+                      px0, px1, py0, py1, gain, slope, clamp, 1.f, flip_filter, 0, sign_mode, signs, sign_h, sign_wb, sx, sy, amax, stream);
+}
+
+static int flr_tc_run(const void* x, const int64_t* xs, int x_dtype, void* y, const int64_t* ys, int y_dtype,
+                      const float* b, const void* skip,
+                      int N, int C, int xh, int xw, int yh, int yw,
+                      const float* fu_host, int fu_taps, const float* fd_host, int fd_taps,
+                      int up, int down, int px0, int px1, int py0, int py1,
+                      float gain, float slope, float clamp, float out_scale, int flip_filter,
+                      int zero_pad_cols, int sign_mode, void* signs, int sign_h, int sign_wb, int s_ox, int s_oy, const float* amax,
+                      void* stream)
 {
     AFCM_CHECK_ARG(zero_pad_cols == 0 || (zero_pad_cols == 2 && ys && ys[2] >= yw + 2), "zero_pad_cols must be 0, or 2 with a row pitch >= yw + 2");
     AFCM_CHECK_ARG(x && y && xs && ys, "x, y and their strides must be given");
@@ -820,6 +1040,18 @@ extern "C" int afcm_filtered_lrelu_tc_padded(const void* x, const int64_t* xs, i
         p.kdy[t] = f / u_scale;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    if (sign_mode != AFCM_SIGN_NONE) {
+        p.signs = (uint32_t*)signs; p.sign_h = sign_h; p.sign_nw = sign_wb >> 2; p.s_ox = s_ox; p.s_oy = s_oy; p.amax = amax;
+        if (sign_mode == AFCM_SIGN_WRITE) {
+            if (act != FTC_ACT_SAT) { set_error("filtered_lrelu_tc_signs: the sign-write kernel needs a clamp in [2^-10, 2^10]"); return AFCM_ERR_UNSUPPORTED; }
+            if (up == 2 && down == 2) return launch_tc<2, 2, float, float, FTC_ACT_SAT, false, 1>(p, N, st);
+            if (up == 4 && down == 2) return launch_tc<4, 2, float, float, FTC_ACT_SAT, false, 1>(p, N, st);
+            return launch_tc<2, 4, float, float, FTC_ACT_SAT, false, 1>(p, N, st);
+        }
+        if (up == 2 && down == 2) return launch_tc<2, 2, float, float, FTC_ACT_MINMAX, false, 2>(p, N, st);
+        if (up == 4 && down == 2) return launch_tc<4, 2, float, float, FTC_ACT_MINMAX, false, 2>(p, N, st);
+        return launch_tc<2, 4, float, float, FTC_ACT_MINMAX, false, 2>(p, N, st);
+    }
 #ifdef AFCM_MINI_U           // development switch: instantiate one kernel only (fast SASS inspection with tools/sass_loops.py)
     return launch_tc<AFCM_MINI_U, AFCM_MINI_D, __half, __half, FTC_ACT_SAT, true>(p, N, st);
 #else

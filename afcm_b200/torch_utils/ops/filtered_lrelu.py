@@ -10,15 +10,30 @@ from . import upfirdn2d as _upfirdn2d
 
 
 # Implementation of the autograd (training) path: 'exact' = the fp32 kernel (afcm_filtered_lrelu, the parity path),
-# 'tc' = the tensor-core kernel with the same sign tensor (afcm_filtered_lrelu_tcs: fp16 operands in the forward,
-# bf16 in the backward, fp32 accumulation and activation).  Inference without a graph is not affected.
+# 'tcs' = the shared-memory-tiled tensor-core kernel with the same sign tensor (afcm_filtered_lrelu_tcs: fp16 operands in the
+# forward, bf16 in the backward, fp32 accumulation and activation), 'tc' = the register-chained tensor-core kernel with the sign
+# tensor (afcm_filtered_lrelu_tc_signs: fp16 operands, the backward scaled into the fp16 range by max|dy|; falls back to 'tcs' /
+# 'exact' for calls it has no specialisation for).  All three write and read the SAME sign tensor.  Inference is not affected.
 train_impl = 'exact'
 
 
 def set_train_impl(impl):
     global train_impl
-    assert impl in ('exact', 'tc')
+    assert impl in ('exact', 'tc', 'tcs')
     train_impl = impl
+
+
+_amax_buf = {}
+tc_sign_calls = 0            # calls served by afcm_filtered_lrelu_tc_signs (tests check that the kernel really ran)
+
+
+def _absmax(x):
+    """max|x| as a device scalar (no host synchronisation): the operand scale of the fp16 backward."""
+    buf = _amax_buf.get(x.device)
+    if buf is None:
+        buf = _amax_buf[x.device] = torch.zeros([1], dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().afcm_absmax(_lib.ptr(x), x.numel(), _lib.ptr(buf), _lib.stream_ptr(x.device)))
+    return buf
 
 
 def _get_filter_size(f):
@@ -98,8 +113,28 @@ def _run_fused(x, fu, fd, b, si, up, down, px0, px1, py0, py1, sx, sy, gain, slo
         skip = skip.contiguous()
     # algorithmic bytes: x read once + y written once (+ the skip read when fused)
     nbytes = x.element_size() * (x.numel() + y.numel() * (2 if skip is not None else 1))
-    use_tc = (train_impl == 'tc' and mode != _lib.SIGN_NONE and x.dtype == torch.float32 and fu_h is not None and
-              fd_h is not None and (up, down) in ((2, 2), (2, 4), (4, 2)) and fu_n == 6 * up and fd_n == 6 * down and
+    tc_geo = (mode != _lib.SIGN_NONE and x.dtype == torch.float32 and fu_h is not None and fd_h is not None and
+              (up, down) in ((2, 2), (2, 4), (4, 2)) and fu_n == 6 * up and fd_n == 6 * down)
+    # measured per geometry at batch 32 (tools/flr_train_bench.py): the register-chained kernel wins the forward everywhere and
+    # the up 2 / down 2 backward; the backward kernels with a 24-tap filter (up 4 / down 2 and up 2 / down 4: 6 column blocks per
+    # warp, two CTAs per SM) lose to the shared-memory tiled kernel on planes it tiles well
+    tcs_better = mode == _lib.SIGN_READ and (up, down) != (2, 2) and min(yh, yw) >= 48
+    if (train_impl == 'tc' and tc_geo and not tcs_better and skip is None and out_scale == 1.0 and xw % 2 == 0 and yw % 2 == 0 and
+            (mode == _lib.SIGN_READ or (1.0 / 1024 <= clamp <= 1024))):
+        # the register-chained kernel with the sign tensor (csrc/flr_tc.cu, SIGN = 1 / 2)
+        xc = x if (x.stride(3) == 1 and all(int(v) % 2 == 0 for v in x.stride()[:3]) and x.data_ptr() % 8 == 0) else x.contiguous()
+        amax = _absmax(xc if xc.is_contiguous() else xc.contiguous()) if mode == _lib.SIGN_READ else None
+        rc = _lib.timed('filtered_lrelu', nbytes, lambda: L.afcm_filtered_lrelu_tc_signs(
+            _lib.ptr(xc), _lib.i64x4(xc.stride()), _lib.ptr(y), _lib.i64x4(y.stride()), _lib.ptr(b),
+            N, C, xh, xw, yh, yw, _lib.np_ptr(fu_h), fu_n, _lib.np_ptr(fd_h), fd_n, up, down, px0, px1, py0, py1,
+            gain, slope, clamp, int(bool(flip_filter)), mode, _lib.ptr(s), sh, swb, int(sx), int(sy), _lib.ptr(amax),
+            _lib.stream_ptr(x.device)))
+        _lib.check(rc, allow_unsupported=True)
+        if rc == 0:
+            global tc_sign_calls
+            tc_sign_calls += 1
+            return y, so, 0
+    use_tc = (train_impl in ('tc', 'tcs') and tc_geo and
               min(yh, yw) >= 48)      # its 32x32 / 16x16 tiles waste most of a small plane: the exact kernel is faster there
     if use_tc:
         # forward (sign write): fp16 operands; backward (sign read): bf16 operands keep the gradients' exponent range

@@ -416,7 +416,7 @@ def run_train(args, rank, world):
         conv2d_gradfix.set_conv_impl('f32')
     else:
         conv2d_gradfix.set_conv_impl('tc', torch.bfloat16)           # bf16 operands (gradient range), fp32 accumulation/storage
-        flr_op.set_train_impl('exact' if args.precision == 'tc' else 'tc')   # 'fast': tensor-core filtered_lrelu with sign tensor
+        flr_op.set_train_impl('exact' if args.precision == 'tc' else args.flr_train)   # 'fast': tensor-core filtered_lrelu with sign tensor
     G = afcm_generator(seed=0, device=dev).train()
     tr = GeneratorTrainer(G, lr=0.0025, betas=(0.0, 0.99))
     z, c, x = synthetic_inputs(B, seed=rank, as_uint8=True)
@@ -518,6 +518,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=64)
+    ap.add_argument('--flr-train', default='tc', choices=['tc', 'tcs'], help="training workload: 'tc' = register-chained filtered_lrelu with sign tensor, 'tcs' = the shared-memory tiled kernel")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-fp32-leg', action='store_true', help='skip the extra fp32-path timing of the forward workload')
     ap.add_argument('--precision', default='fast', choices=['fast', 'tc', 'fp32'])

@@ -107,6 +107,22 @@ int afcm_filtered_lrelu_tc_padded(const void* x, const int64_t* xs, int x_dtype,
                            int up, int down, int px0, int px1, int py0, int py1,
                            float gain, float slope, float clamp, float out_scale, int flip_filter,
                            int zero_pad_cols, void* stream);
+/* The register-chained tensor-core kernel WITH the sign tensor (the generator training step): fp32 planes in and out, fp16
+ * operands.  AFCM_SIGN_WRITE = forward (signs [N,C,sign_h,sign_wb] uint8 in the reference's format, OPS/filtered_lrelu.cpp:87-94,
+ * bit-compatible with afcm_filtered_lrelu; needs a clamp in [2^-10, 2^10]); AFCM_SIGN_READ = backward (the op with up / down
+ * exchanged, OPS/filtered_lrelu.py:252-263; sx, sy = sign offsets; the activation is the multiplier 1 / slope / 0 the stored code
+ * selects, OPS/filtered_lrelu.cu:562-572).  amax: device pointer to max|x| written by afcm_absmax, or NULL -- the backward scales its
+ * fp16 operands by the power of two that brings max|x| to ~256 (gradients lie far below the fp16 range) and scales the fp32
+ * result back. */
+int afcm_filtered_lrelu_tc_signs(const void* x, const int64_t* xs, void* y, const int64_t* ys, const float* b,
+                                 int N, int C, int xh, int xw, int yh, int yw,
+                                 const float* fu_host, int fu_taps, const float* fd_host, int fd_taps,
+                                 int up, int down, int px0, int px1, int py0, int py1,
+                                 float gain, float slope, float clamp, int flip_filter,
+                                 int sign_mode, void* signs, int sign_h, int sign_wb, int sx, int sy, const float* amax,
+                                 void* stream);
+/* out[0] = max|x| over n dense fp32 values (x 16-byte aligned), NaN / Inf ignored; stays on the device. */
+int afcm_absmax(const float* x, int64_t n, float* out, void* stream);
 /* Scheduling of afcm_filtered_lrelu_tc for tuning (process-global, not part of the stable ABI): n >= 1 = persistent warps,
  * at most n resident waves of CTAs (default 16, the measured optimum); 0 = one warp per 16-column strip. */
 int afcm_filtered_lrelu_tc_set_waves(int waves);

@@ -34,7 +34,7 @@ for name, C, H, up, dn, fu, fd, pad, cnt in CASES:
     x = torch.randn(N, C, H, H, device=dev, requires_grad=True)
     b = torch.zeros(C, device=dev, requires_grad=True)
     row = [name]
-    for impl in ('exact', 'tc'):
+    for impl in ('exact', 'tcs', 'tc'):
         filtered_lrelu.set_train_impl(impl)
         y = filtered_lrelu.filtered_lrelu(x, fu=fu, fd=fd, b=b, up=up, down=dn, padding=pad, gain=2 ** 0.5, slope=0.2, clamp=256)
         g = torch.randn_like(y)
