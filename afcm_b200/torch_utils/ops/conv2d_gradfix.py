@@ -291,24 +291,86 @@ def conv2d_train(x, w, padding, icoef=None, ocoef=None, pre_scale=1.0, normalize
     return _ConvFn.apply(x, wp, icoef, ocoef, int(padding), impl or conv_impl)
 
 
+def _pair(v):
+    if isinstance(v, (tuple, list)):
+        assert len(v) == 2
+        return int(v[0]), int(v[1])
+    return int(v), int(v)
+
+
+def _conv_unit(x, w, pad):
+    """Stride-1, groups-1 convolution on the native kernels with a symmetric integer padding."""
+    if needs_grad(x, w):
+        return conv2d_train(x, w, int(pad))
+    return conv2d_native(x, w, int(pad))
+
+
 def conv2d(input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
-    """Drop-in for conv2d_gradfix.conv2d (reference :37-40) for the configurations the generator uses:
-    stride 1, dilation 1, groups 1, square 1x1 / 3x3 kernels, symmetric integer padding.  Differentiable
-    (first order) with respect to input, weight and bias."""
+    """Drop-in for conv2d_gradfix.conv2d (OPS/conv2d_gradfix.py:37-40, CM/torch_utils/ops/conv2d_gradfix.py): square 1x1 / 3x3
+    kernels, dilation 1, any stride, (py, px) padding and group count.  The generator path (stride 1, groups 1, symmetric
+    padding) is ONE native kernel; the other forms, used by the discriminator and the CoModGAN baseline generator (CM/layers.py,
+    CM/generator.py:614-836 through conv2d_resample), are compositions of native kernels: unequal padding = zero padding with
+    upfirdn2d, stride s = stride-1 convolution followed by keeping every s-th sample (upfirdn2d down), groups = one convolution
+    per group.  Differentiable (first order) with respect to input, weight and bias."""
+    from . import upfirdn2d
     assert isinstance(input, torch.Tensor)
-    if isinstance(padding, (tuple, list)):
-        assert padding[0] == padding[1]
-        padding = padding[0]
-    if stride not in (1, (1, 1)) or dilation not in (1, (1, 1)) or groups != 1:
-        raise NotImplementedError('afcm conv2d supports stride=1, dilation=1, groups=1 only')
-    if needs_grad(input, weight, bias):
-        y = conv2d_train(input, weight, int(padding))
+    if _pair(dilation) != (1, 1):
+        raise NotImplementedError('afcm conv2d supports dilation 1 only')
+    sy, sx = _pair(stride)
+    py, px = _pair(padding)
+    groups = int(groups)
+    if groups > 1:
+        N, C, H, W = input.shape
+        O = weight.shape[0]
+        assert C % groups == 0 and O % groups == 0 and weight.shape[1] == C // groups
+        ci, co = C // groups, O // groups
+        ys = [conv2d(input[:, g * ci:(g + 1) * ci].contiguous(), weight[g * co:(g + 1) * co].contiguous(), None, (sy, sx), (py, px))
+              for g in range(groups)]
+        y = torch.cat(ys, dim=1)
     else:
-        y = conv2d_native(input, weight, int(padding))
+        x = input
+        if py != px:
+            x = upfirdn2d.upfirdn2d(x, None, padding=[px, px, py, py])          # explicit zero padding (native kernel)
+            pad = 0
+        else:
+            pad = py
+        kh = weight.shape[2]
+        if pad > kh - 1:                                                        # the native kernels take up to "full" padding
+            x = upfirdn2d.upfirdn2d(x, None, padding=[pad - (kh - 1)] * 4)
+            pad = kh - 1
+        y = _conv_unit(x, weight, pad)
+        if (sy, sx) != (1, 1):
+            y = upfirdn2d.upfirdn2d(y, None, down=[sx, sy])                      # keep every s-th sample
     if bias is not None:
         y = y + bias.reshape(1, -1, 1, 1)
     return y
 
 
-def conv_transpose2d(*args, **kwargs):
-    raise NotImplementedError('conv_transpose2d is not on the AFCM stylegan3 generator path')
+def conv_transpose2d(input, weight, bias=None, stride=1, padding=0, output_padding=0, groups=1, dilation=1):
+    """Drop-in for conv2d_gradfix.conv_transpose2d (OPS/conv2d_gradfix.py:42, used by conv2d_resample for up-sampling layers,
+    CM/torch_utils/ops/conv2d_resample.py:127-141): weight [Cin, Cout / groups, kh, kw].  Evaluated as the stride-1 convolution
+    of the zero-inserted input with the flipped, transposed weight -- zero insertion and the k-1-p border by the native upfirdn2d
+    kernel, the convolution by the native convolution kernels."""
+    from . import upfirdn2d
+    if _pair(dilation) != (1, 1) or _pair(output_padding) != (0, 0):
+        raise NotImplementedError('afcm conv_transpose2d supports dilation 1 and output_padding 0 only')
+    sy, sx = _pair(stride)
+    py, px = _pair(padding)
+    groups = int(groups)
+    Cin, Cog, kh, kw = weight.shape
+    assert input.shape[1] == Cin and Cin % groups == 0
+    if groups > 1:
+        cig = Cin // groups
+        ys = [conv_transpose2d(input[:, g * cig:(g + 1) * cig].contiguous(), weight[g * cig:(g + 1) * cig].contiguous(), None, (sy, sx), (py, px))
+              for g in range(groups)]
+        y = torch.cat(ys, dim=1)
+    else:
+        # zero insertion leaves s - 1 zeros behind the last sample: the transposed convolution's grid ends at the sample itself
+        bx0, bx1 = kw - 1 - px, kw - 1 - px - (sx - 1)
+        by0, by1 = kh - 1 - py, kh - 1 - py - (sy - 1)
+        x = upfirdn2d.upfirdn2d(input, None, up=[sx, sy], padding=[bx0, bx1, by0, by1])
+        w = weight.flip([2, 3]).transpose(0, 1).contiguous()                    # [Cout, Cin, kh, kw], correlation form
+        y = _conv_unit(x, w, 0)
+    if bias is not None:
+        y = y + bias.reshape(1, -1, 1, 1)
+    return y
