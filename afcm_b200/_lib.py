@@ -72,6 +72,7 @@ SIGNATURES = {
     'afcm_conv2d_wgrad_tc': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'afcm_conv2d_wgrad_tc_workspace': (_i64, [_i, _i, _i, _i, _i, _i]),
     'afcm_conv2d_wgrad_tc5': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    'afcm_ema_lerp': (_i, [_vp, _vp, _i64, _f, _vp]),
     'afcm_adam_step': (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _i, _f, _i, _vp]),
     'afcm_conv_tc_debug_buffer': (_vp, [_i]),
     'afcm_conv_tc_set_stages': (_i, [_i]),

@@ -311,9 +311,31 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     }
 }
 
+// ---- generator EMA (train.py:74-75): p_ema = lerp(p, p_ema, beta) = p + beta (p_ema - p), over the flat parameter buffers ------
+__global__ void __launch_bounds__(256)
+ema_lerp_kernel(float* __restrict__ p_ema, const float* __restrict__ p, long long n, float beta)
+{
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const float a = p[i];
+        p_ema[i] = fmaf(beta, p_ema[i] - a, a);
+    }
+}
+
 }  // namespace afcm
 
 using namespace afcm;
+
+extern "C" int afcm_ema_lerp(float* param_ema, const float* param, int64_t n, float beta, void* stream)
+{
+    AFCM_CHECK_ARG(param_ema && param && n > 0, "empty problem");
+    long long blocks = (n + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    ema_lerp_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(param_ema, param, (long long)n, beta);
+    AFCM_LAUNCH_CHECK();
+    count_launch();
+    return AFCM_OK;
+}
 
 extern "C" int afcm_plane_dot_scale(float* a, const float* b, const float* div, const float* coef, float* out,
                                     int64_t planes, int64_t hw, void* stream)

@@ -153,6 +153,43 @@ class FusedAdam:
         conv2d_gradfix.clear_prepared_weights()
 
 
+def ema_beta(batch_size, ema_kimgs=10, total_iters=None, ramp=None):
+    """train.py:69-73: ema_nimg = ema_kimgs * 1000, optionally ramped with the iteration count; beta = 0.5 ** (batch / ema_nimg)."""
+    ema_nimg = ema_kimgs * 1000
+    if ramp is not None:
+        ema_nimg = min(ema_nimg, total_iters * ramp)
+    return 0.5 ** (batch_size / max(ema_nimg, 1e-8))
+
+
+class GeneratorEMA:
+    """G_ema of the reference (models/comodgan_model.py:16, train.py:67-77): a deep copy of the generator in eval mode whose
+    parameters follow p_ema = lerp(p, p_ema, beta) after every optimizer step and whose buffers are copied.  Both parameter
+    sets live in flat fp32 buffers (FlatParams), so the update is ONE kernel (afcm_ema_lerp) over 58.5 M values."""
+
+    def __init__(self, G, flat):
+        import copy
+        assert isinstance(flat, FlatParams)
+        self.src, self.src_flat = G, flat
+        self.G_ema = copy.deepcopy(G).eval()
+        for p in self.G_ema.parameters():
+            p.requires_grad_(True)                    # FlatParams collects the trainable parameters: same order as the source
+        self.flat = FlatParams(self.G_ema, 64 << 20)
+        self.flat.flat.copy_(flat.flat)
+        for p in self.G_ema.parameters():
+            p.requires_grad_(False)
+        assert self.flat.flat.numel() == flat.flat.numel()
+
+    def update(self, beta):
+        _lib.require_cuda(self.flat.flat)
+        with torch.no_grad():
+            _lib.check(_lib.lib().afcm_ema_lerp(_lib.ptr(self.flat.flat), _lib.ptr(self.src_flat.flat), self.flat.flat.numel(),
+                                                float(beta), _lib.stream_ptr(self.flat.flat.device)))
+            for b_ema, b in zip(self.G_ema.buffers(), self.src.buffers()):           # train.py:76-77
+                b_ema.copy_(b)
+        from .torch_utils.ops import conv2d_gradfix
+        conv2d_gradfix.clear_prepared_weights()       # the kernel moved the weights behind autograd's version counters
+
+
 class GeneratorTrainer:
     """One data-parallel generator training step: loss = mean |G(z, c, x) - target| (L1, the reconstruction term of
     models/stylegan3_model.py:124-131; the discriminator is outside the north-star path)."""

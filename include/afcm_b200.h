@@ -300,6 +300,9 @@ int afcm_conv2d_wgrad_tc5(const void* dyp, const void* xp, float* dw, void* work
 int afcm_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                    float lr, float beta1, float beta2, float eps, int step, float grad_scale, int scrub,
                    void* stream);
+/* Generator EMA (train.py:67-77): param_ema[i] = lerp(param[i], param_ema[i], beta) = param + beta (param_ema - param) over a
+ * flat buffer of n fp32 parameters. */
+int afcm_ema_lerp(float* param_ema, const float* param, int64_t n, float beta, void* stream);
 
 /* ---------------------------------------------------------------------------------------------- */
 /* small fused kernels                                                                              */

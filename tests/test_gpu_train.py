@@ -235,6 +235,32 @@ def test_trainer_step_single_gpu(golden_tiny, golden_tiny_grads):
     assert l2.item() < loss.item()          # the step reduces the loss on the same batch
 
 
+def test_generator_ema_update(golden_tiny, golden_tiny_grads):
+    """G_ema (train.py:67-77): after an optimizer step p_ema = lerp(p, p_ema, beta) for every parameter, buffers copied; beta as
+    train.py:69-73."""
+    from afcm_b200.training import GeneratorEMA, GeneratorTrainer, ema_beta
+    assert abs(ema_beta(16, 10) - 0.5 ** (16 / 10000)) < 1e-12 and abs(ema_beta(16, 10, total_iters=100, ramp=0.05) - 0.5 ** (16 / 5)) < 1e-12
+    dev = torch.device('cuda:0')
+    g, gg = golden_tiny, golden_tiny_grads
+    G = _tiny(g, dev)
+    tr = GeneratorTrainer(G, lr=1e-3, betas=(0.0, 0.99))
+    ema = GeneratorEMA(G, tr.flat)
+    before = {n: p.detach().clone() for n, p in ema.G_ema.named_parameters()}
+    assert all(torch.equal(before[n], p.detach()) for n, p in G.named_parameters())
+    args = [torch.as_tensor(g[k], device=dev) for k in ('z', 'c', 'x')] + [torch.as_tensor(gg['target'], device=dev)]
+    tr.step(*args)
+    beta = ema_beta(2, 0.001)                      # a beta far from 0 and 1 so that both operands matter
+    ema.update(beta)
+    new = dict(G.named_parameters())
+    for n, p in ema.G_ema.named_parameters():
+        ref = torch.lerp(new[n].detach(), before[n], beta)
+        assert torch.allclose(p.detach(), ref, rtol=1e-6, atol=1e-8), n
+        assert not p.requires_grad
+    with torch.no_grad():                          # the copy runs like the generator
+        y = ema.G_ema(*args[:3], noise_mode='const')
+    assert torch.isfinite(y).all()
+
+
 def test_two_gpu_nccl_training_step():
     """World size 2 over NCCL (skipped on a single-GPU box): tools/train_check_dist.py under torchrun."""
     import json
