@@ -62,6 +62,7 @@ SIGNATURES = {
     'afcm_conv2d_f32': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'afcm_conv_weight_prep': (_i, [_vp, _i, _i, _i, _f, _i, _vp, _vp, _i, _vp, _vp]),
     'afcm_modconv_coefs': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    'afcm_modconv_coefs_ema': (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp]),
     'afcm_conv_tc_plane_elems': (_i64, [_i, _i, _i]),
     'afcm_conv_tc_pack': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'afcm_conv2d_tc': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -134,7 +134,7 @@ weight_prep_kernel(const float* __restrict__ w, int Co, int Ci, int KK, float pr
 // ---- modulation coefficients ----------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 modconv_icoef_kernel(const float* __restrict__ styles, const float* __restrict__ input_gain, float* __restrict__ icoef,
-                     int total, int demodulate)
+                     int total, int demodulate, int gain_rsqrt)
 {
     __shared__ float red[32];
     __shared__ float s_r;
@@ -155,19 +155,19 @@ modconv_icoef_kernel(const float* __restrict__ styles, const float* __restrict__
         __syncthreads();
         r = s_r;
     }
-    const float g = input_gain ? *input_gain : 1.f;
+    const float g = input_gain ? (gain_rsqrt ? rsqrtf(*input_gain) : *input_gain) : 1.f;     // gain_rsqrt: the pointer is magnitude_ema (NET:346)
     for (int i = tid; i < total; i += 1024) icoef[i] = styles[i] * r * g;
 }
 
 __global__ void __launch_bounds__(256)
 modconv_ocoef_kernel(const float* __restrict__ icoef, const float* __restrict__ wsq, const float* __restrict__ input_gain,
-                     float* __restrict__ ocoef, int N, int Ci, int Co, int demodulate)
+                     float* __restrict__ ocoef, int N, int Ci, int Co, int demodulate, int gain_rsqrt)
 {
     const int lane = threadIdx.x & 31;
     const int o = blockIdx.x * 8 + (threadIdx.x >> 5), n = blockIdx.y;
     if (o >= Co) return;
     if (!demodulate) { if (lane == 0) ocoef[n * Co + o] = 1.f; return; }
-    const float g = input_gain ? *input_gain : 1.f;
+    const float g = input_gain ? (gain_rsqrt ? rsqrtf(*input_gain) : *input_gain) : 1.f;
     float s = 0.f;
     for (int i = lane; i < Ci; i += 32) { const float v = icoef[n * Ci + i]; s += wsq[(long long)o * Ci + i] * v * v; }
 #pragma unroll
@@ -219,16 +219,22 @@ extern "C" int afcm_conv_weight_prep(const float* w, int Co, int Ci, int ksize, 
 extern "C" int afcm_modconv_coefs(const float* styles, const float* wsq, const float* input_gain,
                                   float* icoef, float* ocoef, int N, int Ci, int Co, int demodulate, void* stream)
 {
+    return afcm_modconv_coefs_ema(styles, wsq, input_gain, 0, icoef, ocoef, N, Ci, Co, demodulate, stream);
+}
+
+extern "C" int afcm_modconv_coefs_ema(const float* styles, const float* wsq, const float* input_gain, int gain_rsqrt,
+                                      float* icoef, float* ocoef, int N, int Ci, int Co, int demodulate, void* stream)
+{
     AFCM_CHECK_ARG(styles && icoef, "styles and icoef must be given");
     AFCM_CHECK_ARG(N > 0 && Ci > 0 && Co > 0, "empty problem");
     AFCM_CHECK_ARG(!demodulate || (wsq && ocoef), "demodulation needs wsq and ocoef");
     AFCM_CHECK_ARG(N <= 65535, "batch too large");
     cudaStream_t st = (cudaStream_t)stream;
-    modconv_icoef_kernel<<<1, 1024, 0, st>>>(styles, input_gain, icoef, N * Ci, demodulate);
+    modconv_icoef_kernel<<<1, 1024, 0, st>>>(styles, input_gain, icoef, N * Ci, demodulate, gain_rsqrt);
     AFCM_LAUNCH_CHECK();
     count_launch();
     if (ocoef) {
-        modconv_ocoef_kernel<<<dim3(ceil_div(Co, 8), N), 256, 0, st>>>(icoef, wsq, input_gain, ocoef, N, Ci, Co, demodulate);
+        modconv_ocoef_kernel<<<dim3(ceil_div(Co, 8), N), 256, 0, st>>>(icoef, wsq, input_gain, ocoef, N, Ci, Co, demodulate, gain_rsqrt);
         AFCM_LAUNCH_CHECK();
         count_launch();
     }

@@ -22,12 +22,14 @@ from .torch_utils.ops.filtered_lrelu import _run_fused as _flrelu_fused
 
 
 @misc.profiled_function
-def modulated_conv2d(x, w, s, demodulate=True, padding=0, input_gain=None, impl=None, out_dtype=None, bias=None):
+def modulated_conv2d(x, w, s, demodulate=True, padding=0, input_gain=None, impl=None, out_dtype=None, bias=None, input_gain_rsqrt=False):
     """NET:25-64.  x [N,I,H,W], w [O,I,k,k], s [N,I]; input_gain [] / [I] / [N,I] or None.
 
     The reference materialises a per-sample weight w*s*d*g and runs a grouped conv.  Here the same
     product is evaluated as  d[n,o] * conv(x * (s_hat*g)[n,i], w_hat)  -- modulation on the activation
     side, demodulation in the GEMM epilogue -- so no [N,O,I,k,k] tensor exists.
+    `input_gain_rsqrt` (not in the reference signature): `input_gain` is the layer's magnitude_ema buffer itself and the
+    coefficient kernel applies the rsqrt of NET:346.
     """
     _lib.require_cuda(x, w, s)
     N = int(x.shape[0])
@@ -36,7 +38,7 @@ def modulated_conv2d(x, w, s, demodulate=True, padding=0, input_gain=None, impl=
     misc.assert_shape(x, [N, I, None, None])
     misc.assert_shape(s, [N, I])
     if conv2d_gradfix.needs_grad(x, w, s):
-        return _modulated_conv2d_train(x, w, s, demodulate, padding, input_gain, impl, bias)
+        return _modulated_conv2d_train(x, w, s, demodulate, padding, input_gain.rsqrt() if input_gain_rsqrt else input_gain, impl, bias)
     L = _lib.lib()
     s = s.contiguous().float()
     gain_scalar = None
@@ -44,12 +46,14 @@ def modulated_conv2d(x, w, s, demodulate=True, padding=0, input_gain=None, impl=
         if input_gain.numel() == 1:
             gain_scalar = input_gain.reshape(1).float().contiguous()
         else:
+            input_gain = input_gain.rsqrt() if input_gain_rsqrt else input_gain
+            input_gain_rsqrt = False
             s = (s * input_gain.expand(N, I)) if not demodulate else s    # per-channel gains handled below
     ent = conv2d_gradfix.prepare_weight(w, 1.0, bool(demodulate), want_wsq=bool(demodulate))
     icoef = torch.empty([N, I], dtype=torch.float32, device=x.device)
     ocoef = torch.empty([N, O], dtype=torch.float32, device=x.device) if demodulate else None
-    _lib.check(L.afcm_modconv_coefs(_lib.ptr(s), _lib.ptr(ent.get('wsq')), _lib.ptr(gain_scalar), _lib.ptr(icoef),
-                                    _lib.ptr(ocoef), N, I, O, int(bool(demodulate)), _lib.stream_ptr(x.device)))
+    _lib.check(L.afcm_modconv_coefs_ema(_lib.ptr(s), _lib.ptr(ent.get('wsq')), _lib.ptr(gain_scalar), int(bool(input_gain_rsqrt)),
+                                        _lib.ptr(icoef), _lib.ptr(ocoef), N, I, O, int(bool(demodulate)), _lib.stream_ptr(x.device)))
     if input_gain is not None and input_gain.numel() != 1 and demodulate:
         icoef = icoef * input_gain.expand(N, I)        # rare general form (NET:55-57); AFCM passes a scalar
     return conv2d_gradfix.conv2d_native(x, w, int(padding), icoef=icoef, ocoef=ocoef, pre_scale=1.0,
@@ -379,7 +383,7 @@ class SynthesisLayer(_AliasFreeLayerBase):
                             out_half_width, conv_kernel, filter_size, lrelu_upsampling, use_radial_filters, is_torgb,
                             is_critically_sampled)
 
-    def _torgb_fused(self, x, styles, input_gain, out_scale):
+    def _torgb_fused(self, x, styles, input_gain, out_scale, gain_rsqrt=False):
         """ToRGB in one kernel (afcm_torgb): 1x1 modulated conv without demodulation + bias + clamp + output scale."""
         L = _lib.lib()
         N, I, H, W = x.shape
@@ -389,8 +393,8 @@ class SynthesisLayer(_AliasFreeLayerBase):
         s = styles.contiguous().float()
         icoef = torch.empty([N, I], dtype=torch.float32, device=x.device)
         st = _lib.stream_ptr(x.device)
-        _lib.check(L.afcm_modconv_coefs(_lib.ptr(s), None, _lib.ptr(input_gain.reshape(1).float().contiguous()),
-                                        _lib.ptr(icoef), None, N, I, O, 0, st))
+        _lib.check(L.afcm_modconv_coefs_ema(_lib.ptr(s), None, _lib.ptr(input_gain.reshape(1).float().contiguous()), int(bool(gain_rsqrt)),
+                                            _lib.ptr(icoef), None, N, I, O, 0, st))
         y = torch.empty([N, O, H, W], dtype=torch.float32, device=x.device)
         clamp = float(self.conv_clamp) if self.conv_clamp is not None else -1.0
         rc = _lib.timed('torgb', float(x.element_size() * x.numel() + 4 * y.numel()), lambda: L.afcm_torgb(
@@ -404,12 +408,16 @@ class SynthesisLayer(_AliasFreeLayerBase):
                 update_emas=False, out_scale=1.0, out_dtype=None, conv_ready=False):
         assert noise_mode in ['random', 'const', 'none']
         misc.assert_shape(x, [None, self.in_channels, int(self.in_size[1]), int(self.in_size[0])])
-        misc.assert_shape(w, [x.shape[0], self.w_dim])
+        # `global_w is None`: the caller hands over the concatenation [w, img_global] itself (SynthesisNetwork builds it for all
+        # layers with one kernel instead of one torch.cat per layer, NET:349-352)
+        misc.assert_shape(w, [x.shape[0], self.w_dim + (self.affine.in_features - self.w_dim if global_w is None else 0)])
         if update_emas:
             magnitude_cur = x.detach().to(torch.float32).square().mean()
             self.magnitude_ema.copy_(magnitude_cur.lerp(self.magnitude_ema, self.magnitude_ema_beta))
-        input_gain = self.magnitude_ema.rsqrt()
-        if self.cond_mod:
+        # no autograd graph: the coefficient kernels apply rsqrt(magnitude_ema) themselves (NET:346), no tiny kernel per layer
+        ema_in_kernel = not torch.is_grad_enabled()
+        input_gain = self.magnitude_ema if ema_in_kernel else self.magnitude_ema.rsqrt()
+        if self.cond_mod and global_w is not None:
             w = torch.cat((w, global_w), 1)
         styles = self.affine(w)
         if self.is_torgb:
@@ -419,12 +427,12 @@ class SynthesisLayer(_AliasFreeLayerBase):
             x_skip = E_features[self.out_size[0]]
         fast = conv2d_gradfix.fast_path() and not torch.is_grad_enabled()
         if fast and self.is_torgb:
-            y = self._torgb_fused(x, styles, input_gain, out_scale)
+            y = self._torgb_fused(x, styles, input_gain, out_scale, ema_in_kernel)
             if y is not None:
                 return y
         fast = fast and not self.is_torgb
         x = modulated_conv2d(x=x if fast else x.float(), w=self.weight, s=styles, padding=self.conv_kernel - 1,
-                             demodulate=(not self.is_torgb), input_gain=input_gain,
+                             demodulate=(not self.is_torgb), input_gain=input_gain, input_gain_rsqrt=ema_in_kernel,
                              out_dtype=conv2d_gradfix.act_dtype if fast else None,
                              bias=self.bias.detach().float() if fast else None)
         gain = 1 if self.is_torgb else np.sqrt(2)
@@ -656,7 +664,14 @@ class SynthesisNetwork(torch.nn.Module):
         img_global = self.dropout(g)
         res_idx = 1
         last = len(self.layer_names) - 1
-        for idx, (name, w) in enumerate(zip(self.layer_names, ws[1:])):               # NET:691-698
+        ws_layers = ws[1:]
+        pre_cat = not torch.is_grad_enabled() and all(getattr(self, n).cond_mod for n in self.layer_names)
+        if pre_cat:
+            # [w_l, img_global] of every layer in ONE concatenation (the reference concatenates inside each layer, NET:349-352)
+            L_ = len(self.layer_names)
+            wcat = torch.cat([torch.stack(ws_layers[:L_], 0), img_global.unsqueeze(0).expand(L_, -1, -1)], dim=2)
+            ws_layers = wcat.unbind(0)
+        for idx, (name, w) in enumerate(zip(self.layer_names, ws_layers)):            # NET:691-698
             nxt = min(idx + 1, last)
             if (self.sizes[idx] != self.sizes[nxt]) and self.sizes[idx] != self.sizes[0]:
                 include_skip = self.skip_connects[res_idx]
@@ -667,7 +682,7 @@ class SynthesisNetwork(torch.nn.Module):
             # fast path: activations stay fp16 up to and including the input of the fused ToRGB kernel
             od = None
             feeds_conv = idx + 1 <= last and getattr(self, self.layer_names[idx + 1]).conv_kernel == 3
-            x = getattr(self, name)(x, w, img_global, E_features, include_skip, out_scale=scale, out_dtype=od,
+            x = getattr(self, name)(x, w, None if pre_cat else img_global, E_features, include_skip, out_scale=scale, out_dtype=od,
                                     conv_ready=feeds_conv, **layer_kwargs)
         misc.assert_shape(x, [None, self.img_channels_out, self.img_resolution, self.img_resolution])
         return x.to(torch.float32)

@@ -220,6 +220,10 @@ int afcm_conv_weight_prep(const float* w, int Co, int Ci, int ksize, float pre_s
  * ocoef = 1.  icoef[n,i] = s_hat[n,i] * input_gain (input_gain: device scalar pointer or NULL). */
 int afcm_modconv_coefs(const float* styles, const float* wsq, const float* input_gain,
                        float* icoef, float* ocoef, int N, int Ci, int Co, int demodulate, void* stream);
+/* The same with the input gain given as the layer's magnitude_ema buffer: gain_rsqrt != 0 applies rsqrt to *input_gain in the
+ * kernel (input_gain = magnitude_ema.rsqrt(), NET:346), which keeps a separate tiny kernel per layer out of the forward. */
+int afcm_modconv_coefs_ema(const float* styles, const float* wsq, const float* input_gain, int gain_rsqrt,
+                           float* icoef, float* ocoef, int N, int Ci, int Co, int demodulate, void* stream);
 
 /* tcgen05 / TMEM implicit-GEMM path (16-bit operands, fp32 accumulation in tensor memory).
  * Step 1: pack activations into the conv-ready layout  xp [N, H*(W+2), Ci_pad8] 16-bit: channel-innermost
