@@ -473,13 +473,22 @@ struct FtcWarp {
         //   row uy = D w0 + 8 U (cur_blk - 1) + 8 NB0 + V' - sy,   column ux = D k0 + J - sx     of the sign tensor
         // (tools/flr_tc_emu.py, tests/test_flr_tc_emu.py); after the packing butterfly the lanes with even g hold one row each
         const int sgn_row = SIGN ? D * w0 + 8 * U * (cur_blk - 1) + 8 * NB0 + 8 * (g >> 2) + 2 * t + ((g >> 1) & 1) - p.sy : 0;
-        uint32_t T[MB + 1];                      // SIGN == 1: packed words of the column blocks of this lane's row
+        // SIGN == 1: word w of this lane's row = column blocks w and w + 1 funnel-shifted by 2 sx bits: a sliding pair of packed block
+        // words is enough (no array of MB + 1 words: the up 2 / down 4 kernel has no registers to spare).  Ownership: a strip stores
+        // the D aligned words of its own 16 D up-sampled columns (the last strip every word up to the end of the row), a segment
+        // the rows of its own output rows (the last one the rest)
+        uint32_t Tprev = 0u;
+        uint32_t* sgn_wp = nullptr;              // where word 0 of this lane's row goes, or null (row not owned / odd g)
+        int n_own = 0;
+        if (SIGN == 1) {
+            const int strip = k0 >> 4;
+            n_own = (strip == p.strips - 1) ? p.sign_nw - D * strip : D;
+            const int row_lo = max(D * w0, 0);
+            const int row_hi = (w0 + 8 * p.seg_wblocks >= p.yh) ? p.sign_h : D * (w0 + 8 * p.seg_wblocks);
+            if (!(g & 1) && sgn_row >= row_lo && sgn_row < row_hi) sgn_wp = sgn_plane + (long long)sgn_row * p.sign_nw + D * strip;
+        }
         uint32_t sw[MB + 2];                     // SIGN == 2: the stored words this lane's row needs (column blocks + shift spill)
         int sshift = 0;
-        if (SIGN == 1) {
-#pragma unroll
-            for (int i = 0; i <= MB; i++) T[i] = 0u;
-        }
         if (SIGN == 2) {
             // columns ex = D k0 + 16 mb + j - sx + s_ox: word (ex0 >> 4) + mb, shifted by 2 (ex0 & 15) bits; outside the tensor = code 0
             const int ex0 = D * k0 - p.sx + p.s_ox;
@@ -516,7 +525,11 @@ struct FtcWarp {
                     if (SIGN == 1) { cod[q][0] = ftc_codes(d[0], e[q][0]); cod[q][1] = ftc_codes(d[1], e[q][1]); }
                 }
             }
-            if (SIGN == 1) T[mb] = ftc_sign_block_word(cod, lane_id);
+            if (SIGN == 1) {
+                const uint32_t Tcur = ftc_sign_block_word(cod, lane_id);
+                if (mb >= 1 && sgn_wp && mb - 1 < n_own) sgn_wp[mb - 1] = __funnelshift_r(Tprev, Tcur, 2 * p.sx);
+                Tprev = Tcur;
+            }
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const int jb = 2 * mb + h;
@@ -534,21 +547,13 @@ struct FtcWarp {
                 }
             }
         }
-        if (SIGN == 1) {
-            // ownership: a strip stores the D aligned words of its own 16 D up-sampled columns (the last strip every word up to the
-            // end of the row), a segment the rows of its own output rows (the last one the rest); sign columns count from the
-            // first sample the down filter reads: word w = column blocks w and w + 1 funnel-shifted by 2 sx bits
-            const int strip = k0 >> 4;
-            int n_own = (strip == p.strips - 1) ? p.sign_nw - D * strip : D;
-            if (n_own > MB) n_own = MB;
-            const int row_lo = max(D * w0, 0);
-            const int row_hi = (w0 + 8 * p.seg_wblocks >= p.yh) ? p.sign_h : D * (w0 + 8 * p.seg_wblocks);
-            if (!(g & 1) && sgn_row >= row_lo && sgn_row < row_hi) {
-                uint32_t* rowp = sgn_plane + (long long)sgn_row * p.sign_nw + D * strip;
+        if (SIGN == 1 && sgn_wp) {
+            // the last computed block pairs with an all-zero block; words beyond the computed blocks (narrow strips) are zero
+            constexpr int NB = NARROW ? Geo::MBN : MB;
+            if (NB - 1 < n_own) sgn_wp[NB - 1] = __funnelshift_r(Tprev, 0u, 2 * p.sx);
 #pragma unroll
-                for (int w = 0; w < MB; w++)
-                    if (w < n_own) rowp[w] = __funnelshift_r(T[w], T[w + 1], 2 * p.sx);
-            }
+            for (int w = NB; w < MB; w++)
+                if (w < n_own) sgn_wp[w] = 0u;
         }
     }
 
@@ -762,8 +767,11 @@ struct FtcWarp {
 #ifndef AFCM_FTC_MINB24
 #define AFCM_FTC_MINB24 2
 #endif
+#ifndef AFCM_FTC_MINB_SIGN          // CTAs per SM of the sign-tensor variants (up 2 / down 2 and up 4 / down 2)
+#define AFCM_FTC_MINB_SIGN 4
+#endif
 template <int U, int D, typename TIN, typename TOUT, int ACT, bool FAST, int SIGN>
-__global__ void __launch_bounds__(FTC_WARPS * 32, (U == 2 && D == 4) ? AFCM_FTC_MINB24 : (SIGN ? 3 : (U == 4 ? 4 : AFCM_FTC_MINB22)))
+__global__ void __launch_bounds__(FTC_WARPS * 32, (U == 2 && D == 4) ? AFCM_FTC_MINB24 : (SIGN ? AFCM_FTC_MINB_SIGN : (U == 4 ? 4 : AFCM_FTC_MINB22)))
 flr_tc_kernel(const __grid_constant__ FlrTcParams p)
 {
     // zero-padded tap tables (index e + FTC_TAB_OFS): the fragments below index them with per-lane offsets

@@ -328,8 +328,9 @@ def run_ours(args, rank, world):
 
     def ncu_traffic(pattern):
         """DRAM read+write bytes per launch of the kernels whose name contains `pattern`, from the committed ncu pass over
-        this same command at batch 64 (profiles/traffic_bench_b64.json, written by tools/summarize_profiles.py)."""
-        path = os.path.join(ROOT, 'profiles', 'traffic_bench_b64.json')
+        this same command at batch 64 (profiles/r02_traffic_bench_b64.json, written by tools/summarize_profiles.py from the launch
+        list profiles/r02_launches_final.txt)."""
+        path = os.path.join(ROOT, 'profiles', 'r02_traffic_bench_b64.json')
         if B != 64 or args.precision != 'fast' or not os.path.exists(path):
             return None
         ent = [v for k, v in json.load(open(path)).items() if pattern in k]
