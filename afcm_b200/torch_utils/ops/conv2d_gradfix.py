@@ -193,7 +193,7 @@ class _ConvFn(torch.autograd.Function):
                                          N, Ci, H, W, Co, k, padding, st))
         ctx.padding, ctx.use_tc, ctx.tc_dtype = padding, use_tc, tc_dtype
         need_y = ocoef is not None and ctx.needs_input_grad[3]
-        need_x = (not use_tc) or (icoef is not None and ctx.needs_input_grad[2])
+        need_x = (not use_tc) or (icoef is not None and ctx.needs_input_grad[2]) or (icoef is None and ocoef is None and ctx.needs_input_grad[1])
         ctx.save_for_backward(x if need_x else None, wp, icoef, ocoef, y if need_y else None, xp)
         ctx.xshape = (N, Ci, H, W)
         return y
@@ -201,6 +201,19 @@ class _ConvFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, wp, icoef, ocoef, y, xp = ctx.saved_tensors
+        if torch.is_grad_enabled() and icoef is None and ocoef is None:
+            # backward under create_graph=True (the R1 penalty of the discriminator step, models/comodgan_model.py:128-161):
+            # the gradients are themselves built from differentiable Functions, like the reference's conv2d_gradfix
+            # (OPS/conv2d_gradfix.py:83-198 of the upstream op): dx = conv(dy, flip(w)^T), dw = Wgrad(dy, x)
+            k, pad = wp.shape[2], ctx.padding
+            impl = 'tc' if ctx.use_tc else 'f32'
+            dx = dw = None
+            if ctx.needs_input_grad[0]:
+                dx = _ConvFn.apply(dy, wp.flip(2, 3).transpose(0, 1), None, None, k - 1 - pad, impl)
+            if ctx.needs_input_grad[1]:
+                xs = x if x is not None else _unpack_like(ctx)
+                dw = _WgradFn.apply(dy, xs, pad, k, impl)
+            return dx, dw, None, None, None, None
         L = _lib.lib()
         dy = dy.contiguous().float()
         N, Ci, H, W = ctx.xshape
@@ -254,6 +267,41 @@ class _ConvFn(torch.autograd.Function):
                 _lib.check(L.afcm_conv2d_wgrad_f32(_lib.ptr(dy), _lib.ptr(x), _lib.ptr(icoef), _lib.ptr(ocoef), _lib.ptr(dw),
                                                    N, Ci, H, W, Co, k, pad, st))
         return dx, dw, d_icoef, d_ocoef, None, None
+
+
+def _unpack_like(ctx):
+    raise RuntimeError('afcm conv2d: second-order gradients need the saved fp32 input (run the convolution with impl="f32" or keep x)')
+
+
+class _WgradFn(torch.autograd.Function):
+    """dw[o,i,ky,kx] = sum_{n,p} dy[n,o,p] x[n,i,p + (ky - pad, kx - pad)] as a differentiable Function (needed only when the
+    backward pass itself is differentiated: R1).  Its own gradients are convolutions again:
+        d(dy) = conv(x, g, pad),      d(x) = conv(dy, flip(g)^T, k - 1 - pad)      for g = grad of the loss w.r.t. dw."""
+
+    @staticmethod
+    def forward(ctx, dy, x, pad, k, impl):
+        L = _lib.lib()
+        dy = dy.contiguous().float()
+        x = x.contiguous().float()
+        N, Ci, H, W = x.shape
+        Co = dy.shape[1]
+        dw = torch.empty([Co, Ci, k, k], dtype=torch.float32, device=x.device)
+        _lib.check(L.afcm_conv2d_wgrad_f32(_lib.ptr(dy), _lib.ptr(x), None, None, _lib.ptr(dw), N, Ci, H, W, Co, k, pad,
+                                           _lib.stream_ptr(x.device)))
+        ctx.save_for_backward(dy, x)
+        ctx.pad, ctx.k, ctx.impl = pad, k, impl
+        return dw
+
+    @staticmethod
+    def backward(ctx, g):
+        dy, x = ctx.saved_tensors
+        pad, k, impl = ctx.pad, ctx.k, ctx.impl
+        d_dy = d_x = None
+        if ctx.needs_input_grad[0]:
+            d_dy = _ConvFn.apply(x, g, None, None, pad, impl)
+        if ctx.needs_input_grad[1]:
+            d_x = _ConvFn.apply(dy, g.flip(2, 3).transpose(0, 1), None, None, k - 1 - pad, impl)
+        return d_dy, d_x, None, None, None
 
 
 def _pack(x, coef, dtype):

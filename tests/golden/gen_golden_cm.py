@@ -45,6 +45,15 @@ def main():
     torch.nn.functional.softplus(-D(img_g, c)).mean().backward()
     out['D.dimg'] = img_g.grad.numpy()
     out.update({'D.G.' + k: p.grad.numpy() for k, p in D.named_parameters() if p.grad is not None})
+    # R1 regularisation (models/comodgan_model.py:128-161): gradient of the squared input-gradient norm -- a double backward
+    for p in D.parameters():
+        p.grad = None
+    img_r = img.clone().requires_grad_(True)
+    r1_grads = torch.autograd.grad(outputs=[D(img_r, c).sum()], inputs=[img_r], create_graph=True, only_inputs=True)[0]
+    pen = r1_grads.square().sum([1, 2, 3])
+    (pen * (10.0 / 2)).mean().backward()
+    out['D.r1_pen'] = pen.detach().numpy()
+    out.update({'D.R1.' + k: p.grad.numpy() for k, p in D.named_parameters() if p.grad is not None})
 
     torch.manual_seed(2)
     G = CoModGenerator(**G_CFG).eval()

@@ -146,3 +146,56 @@ def _resample_ref(x, w, f, up, down, padding, groups):
     if down > 1:
         x = _upfirdn_ref(x, f, down=down)
     return x
+
+
+@pytest.mark.parametrize('k,pad,stride', [(3, 1, 1), (3, 2, 1), (1, 0, 1), (3, 1, 2), (3, 0, 1)])
+def test_conv2d_double_backward_matches_torch(k, pad, stride):
+    """Second-order gradients of conv2d_gradfix.conv2d (the R1 penalty differentiates the data gradient of every discriminator
+    convolution): gradient of |d(sum y r)/dx|^2 with respect to x-independent inputs w and r-weighted y, against torch's own
+    double backward in float64."""
+    import torch.nn.functional as F
+    from afcm_b200.torch_utils.ops import conv2d_gradfix
+    dev = torch.device('cuda:0')
+    gen = torch.Generator().manual_seed(11)
+    x0 = torch.randn(2, 5, 10, 12, generator=gen)
+    w0 = torch.randn(7, 5, k, k, generator=gen) * 0.3
+    r = torch.randn(2, 7, (10 + 2 * pad - k) // stride + 1, (12 + 2 * pad - k) // stride + 1, generator=gen)
+
+    def penalty(conv, x, w, rr):
+        y = conv(x, w)
+        gx, = torch.autograd.grad((y * rr).sum() + (y ** 2).sum() * 0.5, x, create_graph=True)
+        return gx.square().sum()
+
+    x = x0.double().requires_grad_(True); w = w0.double().requires_grad_(True)
+    penalty(lambda a, b: F.conv2d(a, b, stride=stride, padding=pad), x, w, r.double()).backward()
+    ref_dx, ref_dw = x.grad.clone(), w.grad.clone()
+    xg = x0.to(dev).requires_grad_(True); wg = w0.to(dev).requires_grad_(True)
+    penalty(lambda a, b: conv2d_gradfix.conv2d(a, b, stride=stride, padding=pad), xg, wg, r.to(dev)).backward()
+    assert rel_err(xg.grad.cpu().numpy(), ref_dx.numpy()) < 1e-4
+    assert rel_err(wg.grad.cpu().numpy(), ref_dw.numpy()) < 1e-4
+
+
+def test_reference_discriminator_r1_penalty(monkeypatch, golden_cm):
+    """The R1 regularisation step of the reference (models/comodgan_model.py:128-161) on the swapped operators: the input
+    gradient is taken with create_graph=True and its squared norm is differentiated again -- through the native convolution
+    (differentiable backward, conv2d_gradfix._ConvFn / _WgradFn), bias_act (second-order kernel) and upfirdn2d."""
+    gen = _reference_cm(monkeypatch)
+    g = golden_cm
+    dev = torch.device('cuda:0')
+    torch.manual_seed(0)
+    D = _load(gen.CoModDiscriminator(**D_CFG).eval(), g, 'D.P.', dev)
+    for p in D.parameters():
+        p.requires_grad_(True)
+    img, c = torch.as_tensor(g['D.img'], device=dev).requires_grad_(True), torch.as_tensor(g['D.c'], device=dev)
+    r1_grads = torch.autograd.grad(outputs=[D(img, c).sum()], inputs=[img], create_graph=True, only_inputs=True)[0]
+    pen = r1_grads.square().sum([1, 2, 3])
+    assert rel_err(pen.detach().cpu().numpy(), g['D.r1_pen']) < 1e-4
+    (pen * (10.0 / 2)).mean().backward()
+    worst = 0.0
+    for k, p in D.named_parameters():
+        key = 'D.R1.' + k
+        if key in g.files and np.abs(g[key]).max() > 0:
+            assert p.grad is not None, k
+            worst = max(worst, rel_err(p.grad.cpu().numpy(), g[key]))
+    print('R1 penalty parameter gradients: worst rel err %.2e' % worst)
+    assert worst < 1e-3
