@@ -78,6 +78,7 @@ SIGNATURES = {
     'afcm_conv_tc_debug_buffer': (_vp, [_i]),
     'afcm_conv_tc_set_stages': (_i, [_i]),
     'afcm_conv_tc_set_rowreuse': (_i, [_i]),
+    'afcm_fully_connected_grouped': (_i, [_i, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _vp]),
     'afcm_fully_connected': (_i, [_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _f, _f, _i, _f, _f, _vp]),
     'afcm_normalize_2nd_moment': (_i, [_vp, _i64, _vp, _i64, _i, _i, _f, _vp]),
     'afcm_adaptive_avgpool': (_i, [_vp, _vp, _i64, _i, _i, _i, _i, _vp]),

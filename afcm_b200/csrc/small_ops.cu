@@ -238,6 +238,58 @@ static int launch_torgb(const void* x, const float* w, const float* icoef, const
     return AFCM_OK;
 }
 
+// ---- grouped fully connected: up to FCG_MAX independent linear layers with the same input width in ONE launch (the 15 affine
+// layers of the synthesis network, NET:349-352: each maps its own [N, 1536] style input to the layer's channel count) ----------
+constexpr int FCG_MAX = 16;
+struct FcGroupParams {
+    const float* x[FCG_MAX]; const float* w[FCG_MAX]; const float* b[FCG_MAX]; float* y[FCG_MAX];
+    int out_f[FCG_MAX]; float ag[FCG_MAX];
+    long long ldx;
+    int N, in_f, groups;
+    float wg, bg;
+};
+
+__global__ void __launch_bounds__(FC_WARPS * 32)
+fc_grouped_kernel(const __grid_constant__ FcGroupParams p)
+{
+    const int grp = blockIdx.z;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int o = blockIdx.x * FC_WARPS + warp;
+    const int n0 = blockIdx.y * FC_NB;
+    const int out_f = p.out_f[grp];
+    if (o >= out_f) return;
+    const float* x = p.x[grp];
+    const float* wr = p.w[grp] + (long long)o * p.in_f;
+    float acc[FC_NB];
+#pragma unroll
+    for (int j = 0; j < FC_NB; j++) acc[j] = 0.f;
+    for (int i = lane * 4; i < p.in_f; i += 128) {                    // in_f % 4 == 0 and 16-byte aligned rows (host-checked)
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + i));
+#pragma unroll
+        for (int j = 0; j < FC_NB; j++) {
+            if (n0 + j < p.N) {
+                const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (long long)(n0 + j) * p.ldx + i));
+                acc[j] += xv.x * wv.x + xv.y * wv.y + xv.z * wv.z + xv.w * wv.w;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < FC_NB; j++) {
+        float v = acc[j];
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+        acc[j] = v;
+    }
+    if (lane < FC_NB && n0 + lane < p.N) {
+        float v = 0.f;
+#pragma unroll
+        for (int j = 0; j < FC_NB; j++) if (j == lane) v = acc[j];
+        const float* b = p.b[grp];
+        v = v * p.wg + (b ? b[o] * p.bg : 0.f);
+        p.y[grp][(long long)(n0 + lane) * out_f + o] = v * p.ag[grp];      // linear activation (NET:349: affine layers)
+    }
+}
+
 static unsigned grid_for(long long total, int per_sm)
 {
     long long blocks = (total + 255) / 256;
@@ -264,6 +316,31 @@ extern "C" int afcm_fully_connected(const float* x, int64_t ldx, const float* w,
     cudaStream_t st = (cudaStream_t)stream;
     if (vec) fc_kernel<true><<<grid, FC_WARPS * 32, 0, st>>>(x, ldx, w, b, y, ldy, N, in_features, out_features, weight_gain, bias_gain, act, alpha, act_gain);
     else fc_kernel<false><<<grid, FC_WARPS * 32, 0, st>>>(x, ldx, w, b, y, ldy, N, in_features, out_features, weight_gain, bias_gain, act, alpha, act_gain);
+    AFCM_LAUNCH_CHECK();
+    count_launch();
+    return AFCM_OK;
+}
+
+extern "C" int afcm_fully_connected_grouped(int groups, const float* const* x, int64_t ldx, const float* const* w, const float* const* b,
+                                            float* const* y, const int* out_features, const float* out_gain,
+                                            int N, int in_features, float weight_gain, float bias_gain, void* stream)
+{
+    AFCM_CHECK_ARG(groups >= 1 && groups <= FCG_MAX, "1..%d groups", FCG_MAX);
+    AFCM_CHECK_ARG(x && w && y && out_features && N > 0 && in_features > 0, "empty problem");
+    AFCM_CHECK_ARG(in_features % 4 == 0 && ldx % 4 == 0 && ldx >= in_features, "the input width and row stride must be multiples of 4");
+    FcGroupParams p;
+    memset(&p, 0, sizeof(p));
+    int max_out = 0;
+    for (int g = 0; g < groups; g++) {
+        AFCM_CHECK_ARG(x[g] && w[g] && y[g] && out_features[g] > 0, "group %d: null pointer or empty output", g);
+        AFCM_CHECK_ARG((((uintptr_t)x[g] | (uintptr_t)w[g]) & 15) == 0, "group %d: x and w must be 16-byte aligned", g);
+        p.x[g] = x[g]; p.w[g] = w[g]; p.b[g] = b ? b[g] : nullptr; p.y[g] = y[g]; p.out_f[g] = out_features[g];
+        p.ag[g] = out_gain ? out_gain[g] : 1.f;
+        if (out_features[g] > max_out) max_out = out_features[g];
+    }
+    p.ldx = ldx; p.N = N; p.in_f = in_features; p.groups = groups; p.wg = weight_gain; p.bg = bias_gain;
+    dim3 grid(ceil_div(max_out, FC_WARPS), ceil_div(N, FC_NB), groups);
+    fc_grouped_kernel<<<grid, FC_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
     AFCM_LAUNCH_CHECK();
     count_launch();
     return AFCM_OK;

@@ -405,9 +405,11 @@ class SynthesisLayer(_AliasFreeLayerBase):
         return y if rc == 0 else None
 
     def forward(self, x, w, global_w, E_features=None, include_skip=True, noise_mode='random', force_fp32=False,
-                update_emas=False, out_scale=1.0, out_dtype=None, conv_ready=False):
+                update_emas=False, out_scale=1.0, out_dtype=None, conv_ready=False, styles=None):
         assert noise_mode in ['random', 'const', 'none']
         misc.assert_shape(x, [None, self.in_channels, int(self.in_size[1]), int(self.in_size[0])])
+        # `styles`: this layer's affine output, already computed by the caller (SynthesisNetwork runs the affine layers of all
+        # synthesis layers in one grouped launch, incl. the ToRGB scale of NET:353-355)
         # `global_w is None`: the caller hands over the concatenation [w, img_global] itself (SynthesisNetwork builds it for all
         # layers with one kernel instead of one torch.cat per layer, NET:349-352)
         misc.assert_shape(w, [x.shape[0], self.w_dim + (self.affine.in_features - self.w_dim if global_w is None else 0)])
@@ -417,11 +419,12 @@ class SynthesisLayer(_AliasFreeLayerBase):
         # no autograd graph: the coefficient kernels apply rsqrt(magnitude_ema) themselves (NET:346), no tiny kernel per layer
         ema_in_kernel = not torch.is_grad_enabled()
         input_gain = self.magnitude_ema if ema_in_kernel else self.magnitude_ema.rsqrt()
-        if self.cond_mod and global_w is not None:
-            w = torch.cat((w, global_w), 1)
-        styles = self.affine(w)
-        if self.is_torgb:
-            styles = styles * (1 / np.sqrt(self.in_channels * (self.conv_kernel ** 2)))
+        if styles is None:
+            if self.cond_mod and global_w is not None:
+                w = torch.cat((w, global_w), 1)
+            styles = self.affine(w)
+            if self.is_torgb:
+                styles = styles * (1 / np.sqrt(self.in_channels * (self.conv_kernel ** 2)))
         x_skip = None
         if E_features is not None and include_skip:
             x_skip = E_features[self.out_size[0]]
@@ -643,6 +646,30 @@ class SynthesisNetwork(torch.nn.Module):
         _lib.check(_lib.lib().afcm_pad_input(_lib.ptr(img), _lib.ptr(y), lut, N * C, H, W, m, _lib.stream_ptr(img.device)))
         return y
 
+    def _grouped_affines(self, wcat):
+        """styles of every synthesis layer from wcat [L, N, w_dim + global_w_dim] in ONE launch (afcm_fully_connected_grouped): the
+        affine layers depend on the mapped styles only (NET:349-352), ToRGB's 1/sqrt(C k^2) style scale (NET:353-355) included.
+        Returns None (the layers then run their own affine) when the layers do not share one input width."""
+        import ctypes
+        layers = [getattr(self, n) for n in self.layer_names]
+        L_, N, in_f = wcat.shape
+        if L_ > 16 or any(l.affine.in_features != in_f or l.affine.activation != 'linear' or l.affine.bias is None for l in layers):
+            return None
+        a0 = layers[0].affine
+        if any(l.affine.weight_gain != a0.weight_gain or l.affine.bias_gain != a0.bias_gain for l in layers):
+            return None
+        outs = [torch.empty([N, l.affine.out_features], dtype=torch.float32, device=wcat.device) for l in layers]
+        vp = ctypes.c_void_p * L_
+        xs = vp(*[wcat[i].data_ptr() for i in range(L_)])
+        wp = vp(*[l.affine.weight.data_ptr() for l in layers])
+        bp = vp(*[l.affine.bias.data_ptr() for l in layers])
+        yp = vp(*[o.data_ptr() for o in outs])
+        of = (ctypes.c_int * L_)(*[l.affine.out_features for l in layers])
+        gains = (ctypes.c_float * L_)(*[(1 / np.sqrt(l.in_channels * (l.conv_kernel ** 2))) if l.is_torgb else 1.0 for l in layers])
+        _lib.check(_lib.lib().afcm_fully_connected_grouped(L_, xs, in_f, wp, bp, yp, of, gains, N, in_f, float(a0.weight_gain),
+                                                           float(a0.bias_gain), _lib.stream_ptr(wcat.device)))
+        return outs
+
     def forward(self, ws, img_in, **layer_kwargs):
         misc.assert_shape(ws, [None, self.num_ws, self.w_dim])
         _lib.require_cuda(ws, img_in)
@@ -666,11 +693,13 @@ class SynthesisNetwork(torch.nn.Module):
         last = len(self.layer_names) - 1
         ws_layers = ws[1:]
         pre_cat = not torch.is_grad_enabled() and all(getattr(self, n).cond_mod for n in self.layer_names)
+        styles_all = None
         if pre_cat:
             # [w_l, img_global] of every layer in ONE concatenation (the reference concatenates inside each layer, NET:349-352)
             L_ = len(self.layer_names)
             wcat = torch.cat([torch.stack(ws_layers[:L_], 0), img_global.unsqueeze(0).expand(L_, -1, -1)], dim=2)
             ws_layers = wcat.unbind(0)
+            styles_all = self._grouped_affines(wcat)
         for idx, (name, w) in enumerate(zip(self.layer_names, ws_layers)):            # NET:691-698
             nxt = min(idx + 1, last)
             if (self.sizes[idx] != self.sizes[nxt]) and self.sizes[idx] != self.sizes[0]:
@@ -683,7 +712,7 @@ class SynthesisNetwork(torch.nn.Module):
             od = None
             feeds_conv = idx + 1 <= last and getattr(self, self.layer_names[idx + 1]).conv_kernel == 3
             x = getattr(self, name)(x, w, None if pre_cat else img_global, E_features, include_skip, out_scale=scale, out_dtype=od,
-                                    conv_ready=feeds_conv, **layer_kwargs)
+                                    conv_ready=feeds_conv, styles=None if styles_all is None else styles_all[idx], **layer_kwargs)
         misc.assert_shape(x, [None, self.img_channels_out, self.img_resolution, self.img_resolution])
         return x.to(torch.float32)
 

@@ -317,6 +317,13 @@ int afcm_fully_connected(const float* x, int64_t ldx, const float* w, const floa
                          int N, int in_features, int out_features,
                          float weight_gain, float bias_gain, int act, float alpha, float act_gain,
                          void* stream);
+/* `groups` (<= 16) independent linear layers of the same input width in ONE launch: y[g] [N, out_features[g]] =
+ * (x[g] [N, in_features] (row stride ldx) * w[g]^T * weight_gain + b[g] * bias_gain) * out_gain[g]; x, w, b, y are HOST arrays of
+ * device pointers.  The 15 affine layers of the synthesis network (NET:349-352) depend only on the mapped styles, so the whole
+ * set runs before the first synthesis layer instead of one small launch in front of every convolution. */
+int afcm_fully_connected_grouped(int groups, const float* const* x, int64_t ldx, const float* const* w, const float* const* b,
+                                 float* const* y, const int* out_features, const float* out_gain,
+                                 int N, int in_features, float weight_gain, float bias_gain, void* stream);
 
 /* normalize_2nd_moment of MappingNetwork (NET:142,146): y = x * rsqrt(mean(x^2, dim=1) + eps). */
 int afcm_normalize_2nd_moment(const float* x, int64_t ldx, float* y, int64_t ldy, int N, int F, float eps,
