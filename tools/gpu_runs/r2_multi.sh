@@ -9,7 +9,7 @@ else
 fi
 timeout 900 $RUN bench.py --workload train --gpus $N --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r02_bench_train_n$N.json 2> gpurun_out/r02_bench_train_n$N.err; echo "train rc=$?"
 cat gpurun_out/r02_nccl_n${N}_*.log | grep -hE "NCCL INFO (comm|ncclCommInitRank).*nranks.*COMPLETE|NVLS multicast|Connected all (rings|trees)|Connected NVLS" | sort | uniq -c | sort -rn | head -14 > gpurun_out/r02_nccl_n$N.txt; rm -f gpurun_out/r02_nccl_n${N}_*.log
-for T in 5 2.5; do
+for T in ${VOLUME_T:-5 2.5}; do
   timeout 600 $RUN tools/volume_bench.py --slices 256 --thickness $T --batch 32 > gpurun_out/r02_volume_n${N}_t$T.json 2> gpurun_out/r02_volume_n${N}_t$T.err; echo "volume t=$T rc=$?"
 done
 python - <<PY
