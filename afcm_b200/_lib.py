@@ -76,6 +76,8 @@ SIGNATURES = {
     'afcm_ema_lerp': (_i, [_vp, _vp, _i64, _f, _vp]),
     'afcm_adam_step': (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _i, _f, _i, _vp]),
     'afcm_conv_tc_debug_buffer': (_vp, [_i]),
+    'afcm_conv_tc_trace': (_i, [_vp]),
+    'afcm_conv_tc_set_issuers': (_i, [_i]),
     'afcm_conv_tc_set_stages': (_i, [_i]),
     'afcm_conv_tc_set_rowreuse': (_i, [_i]),
     'afcm_fully_connected_grouped': (_i, [_i, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _vp]),

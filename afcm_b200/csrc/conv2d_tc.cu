@@ -61,6 +61,7 @@ struct TcParams {
     int BN, n_tiles, m_tiles, cblocks;     // channel tile, #channel tiles, #pixel tiles per sample, ceil(Ci/64)
     int total_tiles;
     int stages;                            // TMA -> MMA ring depth (2 .. TC_MAX_STAGES)
+    int issuers;                           // MMA-issuing warps: 1, or 2 taking alternate tiles (not in pipeline mode 2)
     int rowreuse;                          // 1: one A tile of 136 pixels per (ky, channel block) serves the three kx taps;
                                            // 2: the same with separate rings for the A rows and the per-tap weight tiles
     int a_stages;                          // mode 2: depth of the A ring (`stages` is the depth of the B ring)
@@ -70,8 +71,33 @@ struct TcParams {
     const __half* xn;       // ASW: [N, Ci, H, W] fp16 activations (NCHW, contiguous)
     const float* icoef;     // ASW: [N, Ci] modulation coefficients or null
     int pitched;            // ASW: the planes are stored at the row pitch W + 2 with zero pad pixels: the flat plane exists in memory
+    long long* trace;       // development aid: (code << 48 | clock64) records of CTA 0 per role (0 TMA, 1 MMA, 2 epilogue group 0), or null
     unsigned* dbg;          // mapped host memory for progress markers (AFCM_TC_DEBUG), or null
     int dbg_mode;           // debug bisection switches (see afcm_conv_tc_debug_buffer)
+};
+
+// Slot sequence of the TMA -> MMA ring, as every role of the kernel walks it.  With two MMA issuers the ring is split into two
+// halves used by alternate tiles of the CTA: each slot then has one consumer that takes its fills in order (an mbarrier
+// parity wait cannot tell fill f from fill f + 2, so two consumers must not share a slot).
+struct TcRing {
+    int depth, issuers, h, stage, st0, st1;
+    uint32_t phase, ph0, ph1;
+    __device__ TcRing(int stages, int issuers_)
+        : depth(issuers_ == 2 ? stages >> 1 : stages), issuers(issuers_), h(0), stage(0), st0(0), st1(0), phase(0), ph0(0), ph1(0) {}
+    __device__ __forceinline__ void begin_tile(int it) { h = issuers == 2 ? (it & 1) : 0; stage = h ? st1 : st0; phase = h ? ph1 : ph0; }
+    __device__ __forceinline__ void end_tile() { if (h) { st1 = stage; ph1 = phase; } else { st0 = stage; ph0 = phase; } }
+    __device__ __forceinline__ int slot() const { return h * depth + stage; }
+    __device__ __forceinline__ void next() { if (++stage == depth) { stage = 0; phase ^= 1; } }
+};
+
+constexpr int TC_TRACE_SLOTS = 4096;
+struct TcTrace {
+    long long* base; int n;
+    __device__ TcTrace(long long* t, int role, bool on) : base(t && on && blockIdx.x == 0 ? t + role * TC_TRACE_SLOTS : nullptr), n(0) {}
+    __device__ __forceinline__ void mark(int code)
+    {
+        if (base && n < TC_TRACE_SLOTS) base[n++] = ((long long)code << 48) | (clock64() & 0xffffffffffffLL);
+    }
 };
 
 __device__ __forceinline__ uint32_t pack_tc(float lo, float hi, __half*);
@@ -141,6 +167,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
+            TcTrace tr(p.trace, 0, true);
             int stage = 0; uint32_t phase = 0;
             if (p.bres) {
                 mbar_expect_tx(bfull, (uint32_t)res_bytes);
@@ -173,8 +200,11 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         }
                     }
                 }
-            } else
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            } else {
+            TcRing rg(p.stages, p.issuers);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
+                rg.begin_tile(it);
                 const int nt = tile % p.n_tiles;
                 const int r = tile / p.n_tiles;
                 const int mt = r % p.m_tiles, n = r / p.m_tiles;
@@ -183,31 +213,40 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     if (p.bres) {
                         if (ASW) break;                                  // the stage holds the A tile only: nothing for TMA to do
                         const int ky = kb / p.cblocks, cb = kb - ky * p.cblocks;
-                        mbar_wait(&empty[stage], phase ^ 1, p.dbg, 0x100u | (unsigned)stage);
-                        mbar_expect_tx(&full[stage], (uint32_t)TC_AROW_BYTES);
-                        tma_load_3d(ring + stage * stage_bytes, &map_a2, &full[stage], cb * TC_BK, p0 + (ky - p.pad) * p.Wp - p.pad, n);
-                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                        const int stage = rg.slot();
+                        mbar_wait(&empty[stage], rg.phase ^ 1, p.dbg, 0x100u | (unsigned)stage);
+                        tr.mark(1);
+                        if ((p.dbg_mode & 64) && ky > 0) {              // timing experiment (wrong results): one A tile per output tile instead of three
+                            mbar_expect_tx(&full[stage], 0u);
+                        } else {
+                            mbar_expect_tx(&full[stage], (uint32_t)TC_AROW_BYTES);
+                            tma_load_3d(ring + stage * stage_bytes, &map_a2, &full[stage], cb * TC_BK, p0 + (ky - p.pad) * p.Wp - p.pad, n);
+                        }
+                        rg.next();
                         continue;
                     }
                     if (p.rowreuse) {
                         // stage = (ky, channel block): one A tile of 136 consecutive flat pixels starting at the kx = 0
                         // tap + the three B tiles of that kernel row; kx becomes a 128-byte offset of the A descriptor
                         const int ky = kb / p.cblocks, cb = kb - ky * p.cblocks;
-                        mbar_wait(&empty[stage], phase ^ 1, p.dbg, 0x100u | (unsigned)stage);
+                        const int stage = rg.slot();
+                        mbar_wait(&empty[stage], rg.phase ^ 1, p.dbg, 0x100u | (unsigned)stage);
                         uint8_t* sa = ring + stage * stage_bytes;
-                        mbar_expect_tx(&full[stage], (uint32_t)(ASW ? stage_bytes - TC_AROW_BYTES : stage_bytes));
-                        if (!ASW) tma_load_3d(sa, &map_a2, &full[stage], cb * TC_BK, p0 + (ky - p.pad) * p.Wp - p.pad, n);
+                        const bool skip_a = !ASW && (p.dbg_mode & 64) && ky > 0;     // timing experiment, see above
+                        mbar_expect_tx(&full[stage], (uint32_t)((ASW || skip_a) ? stage_bytes - TC_AROW_BYTES : stage_bytes));
+                        if (!ASW && !skip_a) tma_load_3d(sa, &map_a2, &full[stage], cb * TC_BK, p0 + (ky - p.pad) * p.Wp - p.pad, n);
 #pragma unroll
                         for (int kx = 0; kx < 3; kx++)
                             tma_load_3d(sa + TC_AROW_BYTES + kx * b_bytes, &map_b, &full[stage], cb * TC_BK, o0, ky * 3 + kx);
-                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                        rg.next();
                         continue;
                     }
                     const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
                     const int ky = tap / 3, kx = tap - ky * 3;
                     const int shift = (ky - p.pad) * p.Wp + (kx - p.pad);
                     dbg_mark(p.dbg, 10, (unsigned)kb + 1);
-                    mbar_wait(&empty[stage], phase ^ 1, p.dbg, 0x100u | (unsigned)stage);
+                    const int stage = rg.slot();
+                    mbar_wait(&empty[stage], rg.phase ^ 1, p.dbg, 0x100u | (unsigned)stage);
                     dbg_mark(p.dbg, 11, (unsigned)kb + 1);
                     uint8_t* sa = ring + stage * stage_bytes;
                     uint32_t bytes = (uint32_t)stage_bytes;
@@ -225,16 +264,22 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         dbg_mark(p.dbg, 15, (unsigned)kb + 1);
                     }
                     if (blockIdx.x == 0) dbg_mark(p.dbg, 0, (unsigned)(kb + 1) | ((unsigned)tile << 16));
-                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    rg.next();
                 }
+                rg.end_tile();
+            }
             }
         }
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
+    } else if (warp == 1 || (warp == 2 && p.issuers == 2)) {
+        // ================= MMA issuer(s) =================
         // The whole warp runs the loops and the barrier waits (warp-uniform control flow); one elected lane issues.
+        // With two issuers (warps 1 and 2) the CTA's tiles alternate between them, each with its own accumulator: a satisfied
+        // mbarrier try_wait still costs ~90 clocks and the tcgen05.mma queue is only a few instructions deep, so a single
+        // issuer leaves the tensor pipe idle between stages (measured timeline: profiles/r02_conv_tc_trace.txt).
         if (!(p.dbg_mode & 8)) {
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
+            const int iss = warp - 1;
             const uint32_t smem_base = smem_u32(smem), ring_base = smem_u32(ring);
             const uint32_t b_step16 = (p.bres ? (uint32_t)(p.cblocks * b_bytes) : (uint32_t)b_bytes) >> 4;
             if (p.bres) { mbar_wait(bfull, 0, p.dbg, 0x500u); tc_fence_after(); }
@@ -271,15 +316,27 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     }
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
-            } else
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            } else {
+            TcTrace tr(p.trace, 1, lane == 0 && iss == 0);
+            TcRing rg(p.stages, p.issuers);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it++) {
+                if (p.issuers == 2) {
+                    if ((it & 1) != iss) continue;                      // the other issuer's tile (in the other half of the ring)
+                    acc = iss; acc_phase = (uint32_t)(it >> 1) & 1u;
+                }
+                rg.begin_tile(it);
+                tr.mark(10);
                 mbar_wait(&tempty[acc], acc_phase ^ 1, p.dbg, 0x200u | (unsigned)acc);
                 tc_fence_after();
+                tr.mark(11);
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256);
                 int ky_ = 0, cb_ = 0;                                   // row-reuse mode: kb = ky_ * cblocks + cb_
                 for (int kb = 0; kb < kblocks; kb++) {
-                    mbar_wait(&full[stage], phase, p.dbg, 0x300u | (unsigned)stage);
+                    const int stage = rg.slot();
+                    mbar_wait(&full[stage], rg.phase, p.dbg, 0x300u | (unsigned)stage);
                     tc_fence_after();
+                    tr.mark(12);
                     const uint32_t sa = ring_base + (uint32_t)(stage * stage_bytes);
                     const bool last = kb == kblocks - 1;
                     if (p.rowreuse) {
@@ -316,9 +373,12 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         }
                     }
                     __syncwarp();
-                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    tr.mark(13);
+                    rg.next();
                 }
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                rg.end_tile();
+                if (p.issuers != 2 && ++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
             }
         }
     } else if (warp >= 4 && warp < 12 && !(p.dbg_mode & 8)) {
@@ -327,38 +387,74 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // the accumulator: with small channel tiles the store loop, not the MMA, bounds the tile time.
         const int wq = warp & 3, grp = (warp - 4) >> 2;
         const int et = threadIdx.x - 128;
+        TcTrace tr(p.trace, 2, et == 0);
         int acc = 0; uint32_t acc_phase = 0;
         const long long ohw = (long long)p.OH * p.OW;
         const long long cstride = ohw * (p.y_half ? 2 : 4);          // bytes between output channels
+        // fp16 planes with even row lengths: neighbouring lanes (an even / odd pixel of the same row) exchange halves, so that
+        // every lane stores one 4-byte pixel pair of one channel -- half the store instructions and conversions of the
+        // element-wise path below
+        const bool paired = p.y_half && !(p.OW & 1) && !(p.Wp & 1) && !(p.OH * p.OW & 1);
+        int coef_key0 = -1, coef_key1 = -1;                          // (sample, channel tile) whose coefficients each buffer holds
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const int nt = tile % p.n_tiles;
             const int r = tile / p.n_tiles;
             const int mt = r % p.m_tiles, n = r / p.m_tiles;
             const int o0 = nt * p.BN;
-            for (int j = et; j < p.BN; j += 256) {
-                const int o = o0 + j;
-                s_ocoef[acc * 256 + j] = (o < p.Co) ? (p.ocoef ? p.ocoef[(long long)n * p.Co + o] : 1.f) : 0.f;
-                s_bias[acc * 256 + j] = (o < p.Co && p.bias) ? p.bias[o] : 0.f;
+            const int key = n * p.n_tiles + nt;
+            const bool reload = key != (acc ? coef_key1 : coef_key0);      // the same for every epilogue thread
+            if (reload) {
+                for (int j = et; j < p.BN; j += 256) {
+                    const int o = o0 + j;
+                    s_ocoef[acc * 256 + j] = (o < p.Co) ? (p.ocoef ? p.ocoef[(long long)n * p.Co + o] : 1.f) : 0.f;
+                    s_bias[acc * 256 + j] = (o < p.Co && p.bias) ? p.bias[o] : 0.f;
+                }
+                if (acc) coef_key1 = key; else coef_key0 = key;
             }
+            tr.mark(20);
             mbar_wait(&tfull[acc], acc_phase, p.dbg, 0x400u | (unsigned)acc);
             tc_fence_after();
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            tr.mark(21);
+            if (reload) asm volatile("bar.sync 1, 256;" ::: "memory");
+            tr.mark(23);
             const int pix = mt * TC_BM + wq * 32 + lane;
             const int oy = pix / p.Wp, ox = pix - oy * p.Wp;
             const bool ok = oy < p.OH && ox < p.OW;
             char* ybase = reinterpret_cast<char*>(p.y) +
                           (((long long)n * p.Co + o0) * ohw + (long long)oy * p.OW + ox) * (p.y_half ? 2 : 4);
+            // paired path: the even lane's address, the odd lane one channel further on
+            char* ypair = ybase - (lane & 1) * 2 + (lane & 1) * cstride;
             for (int c0 = grp * 32; c0 < p.BN; c0 += 64) {
                 uint32_t v[32];
                 if (!(p.dbg_mode & 32)) {
                     tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * 256 + c0), v);
                     tmem_ld_wait();
                 }
-                if (ok && !(p.dbg_mode & 16)) {
-                    const float4* oc4 = reinterpret_cast<const float4*>(s_ocoef + acc * 256 + c0);
-                    const float4* bi4 = reinterpret_cast<const float4*>(s_bias + acc * 256 + c0);
+                tr.mark(24);
+                if (p.dbg_mode & 16) continue;
+                const float4* oc4 = reinterpret_cast<const float4*>(s_ocoef + acc * 256 + c0);
+                const float4* bi4 = reinterpret_cast<const float4*>(s_bias + acc * 256 + c0);
+                const int nch = min(32, p.Co - o0 - c0);               // channels of this chunk that exist
+                if (paired) {
+                    char* q = ypair + c0 * cstride;
+                    const int myc = lane & 1;                          // this lane stores channels 2 j + myc
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; j4++) {
+                        const float4 oc = oc4[j4], bi = bi4[j4];
+                        const float r0 = fmaf(__uint_as_float(v[4 * j4 + 0]), oc.x, bi.x), r1 = fmaf(__uint_as_float(v[4 * j4 + 1]), oc.y, bi.y);
+                        const float r2 = fmaf(__uint_as_float(v[4 * j4 + 2]), oc.z, bi.z), r3 = fmaf(__uint_as_float(v[4 * j4 + 3]), oc.w, bi.w);
+                        const uint32_t w01 = pack_tc(r0, r1, (__half*)nullptr), w23 = pack_tc(r2, r3, (__half*)nullptr);
+                        const uint32_t p01 = __shfl_xor_sync(0xffffffffu, w01, 1), p23 = __shfl_xor_sync(0xffffffffu, w23, 1);
+                        // even lane: (own low half, partner's low half) = channel 2j of pixels (L, L + 1); odd lane: (partner's
+                        // high half, own high half) = channel 2j + 1 of pixels (L - 1, L)
+                        const uint32_t o01 = myc ? __byte_perm(p01, w01, 0x7632) : __byte_perm(w01, p01, 0x5410);
+                        const uint32_t o23 = myc ? __byte_perm(p23, w23, 0x7632) : __byte_perm(w23, p23, 0x5410);
+                        if (ok && 4 * j4 + myc < nch) *reinterpret_cast<uint32_t*>(q) = o01;
+                        if (ok && 4 * j4 + 2 + myc < nch) *reinterpret_cast<uint32_t*>(q + 2 * cstride) = o23;
+                        q += 4 * cstride;
+                    }
+                } else if (ok) {
                     char* q = ybase + c0 * cstride;
-                    const int nch = min(32, p.Co - o0 - c0);               // channels of this chunk that exist
                     if (nch >= 32) {
 #pragma unroll
                         for (int j4 = 0; j4 < 8; j4++) {
@@ -391,6 +487,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
             tc_fence_before();
             __syncwarp();
+            tr.mark(22);
             if (lane == 0) mbar_arrive(&tempty[acc]);
             if (blockIdx.x == 0 && et == 0) dbg_mark(p.dbg, 4, (unsigned)tile + 1);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -450,9 +547,11 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             y0 = (pp0 + 4 * p.Wp) / p.Wp - 4;                                      // floor(pp0 / Wp): pp0 >= -2 Wp - 2
             a0 = ((p.pitched ? pp0 : pp0 - 2 * y0) >> 3) << 3;                    // floor to a multiple of 8 (also for negatives)
         };
-        int stage = 0; uint32_t phase = 0;
+        TcRing rg(nst, two_rings ? 1 : p.issuers);
         int rs = 0; uint32_t rph = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int tit = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, tit++) {
+            rg.begin_tile(tit);
             for (int ky = 0; ky < 3; ky++) {
                 int n, pp0, y0, a0;
                 tile_origin(tile, ky, n, pp0, y0, a0);
@@ -496,10 +595,21 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             if (x >= p.Wp) { x -= p.Wp; y++; }
                         }
                     }
+                    // The raw slot may be refilled once the loads have RETURNED, not merely issued: the arrive is handled by the
+                    // barrier unit and overtakes loads still queued behind the tensor core's operand reads in the shared-memory
+                    // pipe (measured: with a 2-deep operand ring the refill then lands under the last loads of a warp -- 16 of
+                    // 16 runs of a 128 -> 128 channel layer wrong in a few dozen pixels).  Hence a data dependency the compiler
+                    // cannot fold: the barrier address gets (OR of every loaded register) & dbg_mode added, and dbg_mode is a
+                    // kernel parameter that is always 0 on this path.
+                    uint32_t loaded = 0u;
+#pragma unroll
+                    for (int it = 0; it < NIT; it++) loaded |= v0[it] | v1[it];
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&rempty[rs]);                       // the raw slot may be refilled
+                    if (lane == 0)
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&rempty[rs]) + (loaded & (uint32_t)p.dbg_mode)) : "memory");
                     if (++rs == p.raw_stages) { rs = 0; rph ^= 1; }
-                    mbar_wait(&emptyb[stage], phase ^ 1, p.dbg, 0x800u | (unsigned)stage);
+                    const int stage = rg.slot();
+                    mbar_wait(&emptyb[stage], rg.phase ^ 1, p.dbg, 0x800u | (unsigned)stage);
                     const uint32_t dst = smem_u32(abase + stage * sbytes);
 #pragma unroll
                     for (int it = 0; it < NIT; it++) {
@@ -519,9 +629,10 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     fence_proxy_async();                                           // generic-proxy stores -> visible to tcgen05.mma
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&fullb[stage]);
-                    if (++stage == nst) { stage = 0; phase ^= 1; }
+                    rg.next();
                 }
             }
+            rg.end_tile();
         }
     }
 
@@ -702,6 +813,7 @@ static unsigned* g_dbg_host = nullptr;
 static unsigned* g_dbg_dev = nullptr;
 static int g_dbg_mode = 0;
 static int g_force_stages = 0;
+static int g_issuers = 1;            // two issuers measured: 64-channel packed layers 0.29 -> 0.26 ms, nothing on the direct path
 static int g_rowreuse = -1;          // -1 automatic, 0 / 1 forced
 static int g_bres = 1;               // resident weights allowed
 
@@ -725,6 +837,7 @@ extern "C" void* afcm_conv_tc_debug_buffer(int enable)
 
 // Tuning aid (not part of the stable ABI): force the TMA->MMA ring depth (0 = automatic).
 extern "C" int afcm_conv_tc_set_stages(int stages) { g_force_stages = stages; return AFCM_OK; }
+extern "C" int afcm_conv_tc_set_issuers(int n) { g_issuers = n == 2 ? 2 : 1; return AFCM_OK; }
 // -1 automatic, 0 per-tap pipeline, 1 row-reuse (resident weights where they fit), 2 row-reuse with streamed weights,
 // 4 row-reuse with separate A / B rings for every layer
 extern "C" int afcm_conv_tc_set_rowreuse(int mode)
@@ -771,6 +884,9 @@ extern "C" int afcm_conv2d_tc(const void* xp, const void* w_tc, const float* oco
 
 // The same convolution reading the fp16 NCHW activations directly (no packed copy): y[n,o] = ocoef[n,o] * conv(icoef[n,i] * x[n,i], w) + bias[o].
 // Full padding (2) only; W even and x 4-byte aligned (the planes are read as aligned pixel pairs); fp16 operands.
+static long long* g_tc_trace = nullptr;
+extern "C" int afcm_conv_tc_trace(void* dev_buffer) { g_tc_trace = (long long*)dev_buffer; return AFCM_OK; }
+
 static int g_asw_pitch = 0;        // row pitch of the planes handed to conv2d_tc_launch by afcm_conv2d_tc_nchw (W or W + 2)
 
 extern "C" int afcm_conv2d_tc_nchw(const void* x, int x_pitch, const float* icoef, const void* w_tc, const float* ocoef, const float* bias, void* y,
@@ -801,7 +917,7 @@ static int conv2d_tc_launch(const void* xp, const void* xn, const float* icoef, 
     TcParams p;
     memset(&p, 0, sizeof(p));
     p.ocoef = ocoef; p.bias = bias; p.y = y; p.y_half = y_dtype == AFCM_F16; p.dbg = g_dbg_dev; p.dbg_mode = asw ? 0 : g_dbg_mode;
-    p.xn = (const __half*)xn; p.icoef = icoef;
+    p.xn = (const __half*)xn; p.icoef = icoef; p.trace = g_tc_trace;
     p.N = N; p.Ci = Ci; p.Co = Co; p.H = H; p.W = W; p.Wp = W + 2; p.pad = pad;
     p.OH = H + 2 * pad - 2; p.OW = W + 2 * pad - 2;
     p.n_tiles = ceil_div(Co, 256);
@@ -901,6 +1017,7 @@ static int conv2d_tc_launch(const void* xp, const void* xn, const float* icoef, 
     }
     if (stages < 2) { set_error("conv2d_tc: not enough shared memory for the pipeline"); return AFCM_ERR_UNSUPPORTED; }
     p.stages = stages;
+    p.issuers = (p.rowreuse != 2 && g_issuers == 2 && stages >= 4) ? 2 : 1;   // each issuer needs at least a double-buffered half
     int grid = sm_count();
     if (grid > p.total_tiles) grid = p.total_tiles;
     if (asw) {

@@ -260,6 +260,8 @@ int afcm_conv2d_tc_nchw(const void* x, int x_pitch, const float* icoef, const vo
 int afcm_conv_tc_set_stages(int stages);
 int afcm_conv_tc_set_rowreuse(int mode);   /* A-tile reuse across the kx taps: -1 automatic, 0 off, 1 on, 2 on without resident weights */
 void* afcm_conv_tc_debug_buffer(int enable);
+int afcm_conv_tc_set_issuers(int n);         /* development switch: 1 (default) or 2 MMA-issuing warps per CTA */
+int afcm_conv_tc_trace(void* dev_buffer);    /* timeline records of CTA 0 (3 roles x 4096 int64: code << 48 | clock64); NULL switches it off */
 
 /* ---------------------------------------------------------------------------------------------- */
 /* convolution gradients -- the backward pass the reference obtains from autograd of F.conv2d (cuDNN)  */

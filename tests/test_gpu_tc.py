@@ -144,6 +144,38 @@ def test_conv2d_tc_rowreuse_modes_exact(mode):
         _lib.lib().afcm_conv_tc_set_rowreuse(-1)
 
 
+@pytest.mark.parametrize('shape', [(1, 128, 128, 276, 276), (1, 181, 181, 276, 276), (1, 128, 96, 276, 276), (1, 64, 64, 276, 276)])
+def test_conv2d_tc_direct_nchw_is_repeatable(shape):
+    """Regression test of a shared-memory race in the direct-NCHW convolution: the producer warps released a raw TMA slot
+    when their loads from it had been issued, not when they had returned; with the shallow operand rings of the 96..192
+    channel layers the refill then landed under the last loads (a few dozen wrong pixels per launch, timing dependent).
+    Many tiles per CTA, several launches, each bit-identical to the packed path -- with one and with two MMA issuers."""
+    from afcm_b200 import _lib
+    from afcm_b200.torch_utils.ops import conv2d_gradfix
+    N, Ci, Co, H, W = shape
+    dev = torch.device('cuda:0')
+    g = torch.Generator(device='cpu').manual_seed(5)
+    x = torch.randn(N, Ci, H, W, generator=g).to(dev).half()
+    w = torch.randn(Co, Ci, 3, 3, generator=g).to(dev)
+    bias = torch.randn(Co, generator=g).to(dev)
+    conv2d_gradfix.set_conv_impl('f32', torch.float16)
+    run = lambda: conv2d_gradfix.conv2d_native(x, w, 2, pre_scale=1.0 / np.sqrt(Ci * 9), impl='tc', out_dtype=torch.float16, bias=bias)
+    try:
+        conv2d_gradfix.direct_nchw = False
+        _lib.lib().afcm_conv_tc_set_issuers(1)
+        ref = run()
+        for issuers in (1, 2):
+            _lib.lib().afcm_conv_tc_set_issuers(issuers)
+            for direct in (False, True):
+                conv2d_gradfix.direct_nchw = direct
+                for rep in range(6):
+                    got = run()
+                    assert torch.equal(got, ref), (issuers, direct, rep, int((got != ref).sum()))
+    finally:
+        conv2d_gradfix.direct_nchw = True
+        _lib.lib().afcm_conv_tc_set_issuers(1)
+
+
 @pytest.mark.parametrize('shape', [(2, 64, 64, 36, 36), (1, 4, 64, 52, 52), (2, 91, 181, 30, 22), (1, 181, 256, 38, 36), (2, 512, 512, 36, 36),
                                    (1, 362, 512, 20, 84), (1, 128, 96, 276, 276), (1, 96, 300, 20, 20), (3, 8, 16, 8, 130)])
 @pytest.mark.parametrize('mod', [False, True])

@@ -65,6 +65,8 @@ def main():
     B = args.batch
     if os.environ.get('AFCM_TC_ROWREUSE'):
         _lib.lib().afcm_conv_tc_set_rowreuse(int(os.environ['AFCM_TC_ROWREUSE']))
+    if os.environ.get('AFCM_TC_ISSUERS'):
+        _lib.lib().afcm_conv_tc_set_issuers(int(os.environ['AFCM_TC_ISSUERS']))
     if os.environ.get('AFCM_TC_DBG'):
         _lib.lib().afcm_conv_tc_debug_buffer(int(os.environ['AFCM_TC_DBG']) << 8)
     if os.environ.get('AFCM_FTC_WAVES'):
