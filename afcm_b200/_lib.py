@@ -65,6 +65,7 @@ SIGNATURES = {
     'afcm_modconv_coefs_ema': (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp]),
     'afcm_conv_tc_plane_elems': (_i64, [_i, _i, _i]),
     'afcm_conv_tc_pack': (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    'afcm_conv_tc_pack_pitched': (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'afcm_conv2d_tc': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'afcm_conv2d_tc_nchw': (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     'afcm_plane_dot_scale': (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),

@@ -666,12 +666,12 @@ __device__ __forceinline__ uint32_t pack_tc(float lo, float hi, __nv_bfloat16*)
 template <typename TIN, typename TC>
 __global__ void __launch_bounds__(256)
 tc_pack_pairs_kernel(const TIN* __restrict__ x, const float* __restrict__ icoef, TC* __restrict__ xp,
-                     int Ci, int c_pad, int H, int W, int Wp, int rows)
+                     int Ci, int c_pad, int H, int W, int Wp, int rows, int pitch)
 {
     __shared__ uint32_t tile[128][33];
     const int n = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 128;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const long long plane = (long long)H * W;
+    const long long plane = (long long)H * pitch;              // pitch = W, or W + 2 for planes stored with zero pad columns
     int yy[2], xx[2];
     bool ok[2];
 #pragma unroll
@@ -691,7 +691,7 @@ tc_pack_pairs_kernel(const TIN* __restrict__ x, const float* __restrict__ icoef,
         for (int it = 0; it < 2; it++) {
             float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
             if (ok[it]) {
-                const long long o = (long long)yy[it] * W + xx[it];
+                const long long o = (long long)yy[it] * pitch + xx[it];
                 if (c_ok0) a = load_pair(xc + o);
                 if (c_ok1) b = load_pair(xc + plane + o);
             }
@@ -717,7 +717,7 @@ tc_pack_pairs_kernel(const TIN* __restrict__ x, const float* __restrict__ icoef,
 template <typename TIN, typename TC>
 __global__ void __launch_bounds__(256)
 tc_pack_kernel(const TIN* __restrict__ x, const float* __restrict__ icoef, TC* __restrict__ xp,
-               int Ci, int c_pad, int H, int W, int Wp, int rows)
+               int Ci, int c_pad, int H, int W, int Wp, int rows, int pitch)
 {
     __shared__ float tile[64][65];
     const int n = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
@@ -731,7 +731,7 @@ tc_pack_kernel(const TIN* __restrict__ x, const float* __restrict__ icoef, TC* _
         const int c = c0 + cq * 16 + j;
         float v = 0.f;
         if (pix_ok && c < Ci) {
-            v = (float)x[(((long long)n * Ci + c) * H + yy) * W + xx];
+            v = (float)x[(((long long)n * Ci + c) * H + yy) * pitch + xx];
             if (icoef) v *= icoef[n * Ci + c];
         }
         tile[cq * 16 + j][px] = v;
@@ -753,16 +753,16 @@ tc_pack_kernel(const TIN* __restrict__ x, const float* __restrict__ icoef, TC* _
 }
 
 template <typename TIN, typename TC>
-static void launch_pack(const void* x, const float* icoef, void* xp, int N, int Ci, int H, int W, cudaStream_t st)
+static void launch_pack(const void* x, int pitch, const float* icoef, void* xp, int N, int Ci, int H, int W, cudaStream_t st)
 {
     const int Wp = W + 2, rows = H * Wp, c_pad = (Ci + 7) & ~7;
-    const bool pairs = !(W & 1) && ((uintptr_t)x % (2 * sizeof(TIN))) == 0;
+    const bool pairs = !(W & 1) && !(pitch & 1) && ((uintptr_t)x % (2 * sizeof(TIN))) == 0;
     if (pairs) {
         dim3 grid(ceil_div(rows, 128), ceil_div(c_pad, 64), N);
-        tc_pack_pairs_kernel<TIN, TC><<<grid, 256, 0, st>>>((const TIN*)x, icoef, (TC*)xp, Ci, c_pad, H, W, Wp, rows);
+        tc_pack_pairs_kernel<TIN, TC><<<grid, 256, 0, st>>>((const TIN*)x, icoef, (TC*)xp, Ci, c_pad, H, W, Wp, rows, pitch);
     } else {
         dim3 grid(ceil_div(rows, 64), ceil_div(c_pad, 64), N);
-        tc_pack_kernel<TIN, TC><<<grid, 256, 0, st>>>((const TIN*)x, icoef, (TC*)xp, Ci, c_pad, H, W, Wp, rows);
+        tc_pack_kernel<TIN, TC><<<grid, 256, 0, st>>>((const TIN*)x, icoef, (TC*)xp, Ci, c_pad, H, W, Wp, rows, pitch);
     }
 }
 
@@ -852,24 +852,31 @@ extern "C" int64_t afcm_conv_tc_plane_elems(int H, int W, int Ci)
     return (int64_t)H * (W + 2) * ((Ci + 7) & ~7);           // [H*(W+2) flat pixels][Ci padded to 8]
 }
 
-extern "C" int afcm_conv_tc_pack(const void* x, int x_dtype, const float* icoef, void* xp, int tc_dtype,
-                                 int N, int Ci, int H, int W, void* stream)
+extern "C" int afcm_conv_tc_pack_pitched(const void* x, int x_dtype, int x_pitch, const float* icoef, void* xp, int tc_dtype,
+                                         int N, int Ci, int H, int W, void* stream)
 {
     AFCM_CHECK_ARG(x && xp && N > 0 && Ci > 0 && H > 0 && W > 0, "empty problem");
     AFCM_CHECK_ARG(x_dtype == AFCM_F32 || x_dtype == AFCM_F16, "x must be float32 or float16");
     AFCM_CHECK_ARG(tc_dtype == AFCM_F16 || tc_dtype == AFCM_BF16, "tc dtype must be F16 or BF16");
     AFCM_CHECK_ARG(N <= 65535, "batch too large");
+    AFCM_CHECK_ARG(x_pitch >= W, "the row pitch must be at least the width");
     cudaStream_t st = (cudaStream_t)stream;
     if (x_dtype == AFCM_F32) {
-        if (tc_dtype == AFCM_BF16) launch_pack<float, __nv_bfloat16>(x, icoef, xp, N, Ci, H, W, st);
-        else launch_pack<float, __half>(x, icoef, xp, N, Ci, H, W, st);
+        if (tc_dtype == AFCM_BF16) launch_pack<float, __nv_bfloat16>(x, x_pitch, icoef, xp, N, Ci, H, W, st);
+        else launch_pack<float, __half>(x, x_pitch, icoef, xp, N, Ci, H, W, st);
     } else {
-        if (tc_dtype == AFCM_BF16) launch_pack<__half, __nv_bfloat16>(x, icoef, xp, N, Ci, H, W, st);
-        else launch_pack<__half, __half>(x, icoef, xp, N, Ci, H, W, st);
+        if (tc_dtype == AFCM_BF16) launch_pack<__half, __nv_bfloat16>(x, x_pitch, icoef, xp, N, Ci, H, W, st);
+        else launch_pack<__half, __half>(x, x_pitch, icoef, xp, N, Ci, H, W, st);
     }
     AFCM_LAUNCH_CHECK();
     count_launch();
     return AFCM_OK;
+}
+
+extern "C" int afcm_conv_tc_pack(const void* x, int x_dtype, const float* icoef, void* xp, int tc_dtype,
+                                 int N, int Ci, int H, int W, void* stream)
+{
+    return afcm_conv_tc_pack_pitched(x, x_dtype, W, icoef, xp, tc_dtype, N, Ci, H, W, stream);
 }
 
 static int conv2d_tc_launch(const void* xp, const void* xn, const float* icoef, const void* w_tc, const float* ocoef, const float* bias, void* y,

@@ -11,6 +11,8 @@ Module switches (process-wide, like the reference's `enabled` flag):
                 filtered_lrelu -> fp16 NCHW -> pack; only meaningful with conv_impl 'tc')
 """
 import numpy as np
+import os
+
 import torch
 
 from ... import _lib
@@ -19,6 +21,16 @@ conv_impl = 'f32'
 tc_dtype = torch.float16
 act_dtype = torch.float32
 direct_nchw = True                   # tensor-core path, fp16 activations, full padding: the GEMM reads the NCHW planes itself (no pack pass)
+hybrid_pack = os.environ.get('AFCM_HYBRID_PACK', '0') == '1'   # opt-in: pack + GEMM on the layers where it is faster in isolation, see _prefers_pack
+
+
+def _prefers_pack(Ci, Co, H, W):
+    """Direct-NCHW or pack + GEMM, per layer geometry (profiles/r02_layer_bench_conv_issuers1.json, batch 32): with few input
+    channels on large planes the producer warps of the direct kernel, not the tensor core, set the pace (64 -> 64 channels at
+    276 px: 0.51 ms direct against 0.13 + 0.29 ms), from ~128 input channels on the direct kernel wins or ties.  Inside the
+    forward step the switch is neutral (60.1 against 60.4 ms at batch 64: -2.5 ms of GEMM, +1.8 ms of pack, and the step is
+    power-capped), so it is off by default: one kernel per convolution."""
+    return hybrid_pack and Ci <= 96 and H * W >= 200 * 200
 wgrad_impl = 'tcgen05'               # tensor-core weight gradient: 'tcgen05' (TMEM accumulators) | 'mma' (mma.sync + atomics)
 enabled = False                      # kept for API compatibility with the reference module
 weight_gradients_disabled = False
@@ -128,10 +140,11 @@ def conv2d_native(x, w, padding, icoef=None, ocoef=None, pre_scale=1.0, normaliz
     st = _lib.stream_ptr(x.device)
     ent = prepare_weight(w, pre_scale, normalize, want_tc=use_tc)
     flops = 2.0 * N * Co * Ci * kh * kw * OH * OW
-    if use_tc and direct_nchw and padding == 2 and x.dtype == torch.float16 and tc_dtype == torch.float16 and W % 2 == 0:
+    # planes stored at the pitch W + 2 with zero pad columns (filtered_lrelu.conv_ready_empty), or dense
+    pitch = W + 2 if x.stride() == (Ci * H * (W + 2), H * (W + 2), W + 2, 1) else (W if x.is_contiguous() else 0)
+    if use_tc and direct_nchw and padding == 2 and x.dtype == torch.float16 and tc_dtype == torch.float16 and W % 2 == 0 \
+            and not _prefers_pack(Ci, Co, H, W):
         # no packed copy of the activations -- the kernel's producer warps build the A tiles from the planes.
-        # Dense planes (pitch W) or planes stored at the pitch W + 2 with zero pad columns (filtered_lrelu.conv_ready_empty)
-        pitch = W + 2 if x.stride() == (Ci * H * (W + 2), H * (W + 2), W + 2, 1) else (W if x.is_contiguous() else 0)
         if pitch and (H * pitch) % 8 == 0 and x.data_ptr() % 16 == 0:
             rc = _lib.timed('conv2d_tc', flops, lambda: L.afcm_conv2d_tc_nchw(
                 _lib.ptr(x), pitch, _lib.ptr(icoef), _lib.ptr(ent[('w_tc', tc_dtype)]), _lib.ptr(ocoef), _lib.ptr(bias), _lib.ptr(y),
@@ -139,13 +152,15 @@ def conv2d_native(x, w, padding, icoef=None, ocoef=None, pre_scale=1.0, normaliz
             _lib.check(rc, allow_unsupported=True)
             if rc == 0:
                 return y
-    x = x.contiguous()
+    if not (use_tc and pitch):
+        x = x.contiguous()
+        pitch = W
     if use_tc:
         plane = int(L.afcm_conv_tc_plane_elems(H, W, Ci))
         xp = torch.empty([N, plane], dtype=tc_dtype, device=x.device)
         code = _lib.dtype_code(tc_dtype)
         _lib.timed('conv_tc_pack', float(x.element_size() * x.numel() + 2 * xp.numel()), lambda: _lib.check(
-            L.afcm_conv_tc_pack(_lib.ptr(x), _lib.dtype_code(x.dtype), _lib.ptr(icoef), _lib.ptr(xp), code, N, Ci, H, W, st)))
+            L.afcm_conv_tc_pack_pitched(_lib.ptr(x), _lib.dtype_code(x.dtype), pitch, _lib.ptr(icoef), _lib.ptr(xp), code, N, Ci, H, W, st)))
         _lib.timed('conv2d_tc', flops, lambda: _lib.check(
             L.afcm_conv2d_tc(_lib.ptr(xp), _lib.ptr(ent[('w_tc', tc_dtype)]), _lib.ptr(ocoef), _lib.ptr(bias), _lib.ptr(y),
                              _lib.dtype_code(out_dtype), code, N, Ci, H, W, Co, padding, st)))

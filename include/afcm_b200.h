@@ -240,6 +240,10 @@ int afcm_modconv_coefs_ema(const float* styles, const float* wsq, const float* i
 int64_t afcm_conv_tc_plane_elems(int H, int W, int Ci);
 int afcm_conv_tc_pack(const void* x, int x_dtype, const float* icoef, void* xp, int tc_dtype,
                       int N, int Ci, int H, int W, void* stream);
+/* the same with planes stored at a row pitch of x_pitch >= W elements (the W + 2 pitch with zero pad columns that
+ * afcm_filtered_lrelu_tc_padded writes for the convolution that follows) */
+int afcm_conv_tc_pack_pitched(const void* x, int x_dtype, int x_pitch, const float* icoef, void* xp, int tc_dtype,
+                              int N, int Ci, int H, int W, void* stream);
 int afcm_conv2d_tc(const void* xp, const void* w_tc, const float* ocoef, const float* bias, void* y, int y_dtype, int tc_dtype,
                    int N, int Ci, int H, int W, int Co, int pad, void* stream);
 /* The same GEMM WITHOUT the pack step (NET:365-377 / NET:503-511: the convolution consumes what the preceding

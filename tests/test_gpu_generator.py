@@ -133,6 +133,38 @@ def test_full_generator_fast_path(golden_full):
         inference.set_precision('fp32')
 
 
+def test_full_generator_fast_path_is_deterministic():
+    """No kernel of the benchmarked path is timing dependent: five forwards of the same batch (several tiles per CTA in the
+    large layers) return bit-identical layer outputs.  (This is the test that would have caught the raw-slot race of the
+    direct-NCHW convolution, see tests/test_gpu_tc.py::test_conv2d_tc_direct_nchw_is_repeatable.)"""
+    from afcm_b200 import inference
+    from afcm_b200.networks_stylegan3 import afcm_generator
+    dev = torch.device('cuda:0')
+    G = afcm_generator(seed=0, device=dev)
+    gen = torch.Generator().manual_seed(11)
+    B = 6
+    z = torch.randn(B, 512, generator=gen).to(dev); c = torch.rand(B, 1, generator=gen).to(dev)
+    x = (torch.rand(B, 4, 256, 256, generator=gen) * 2 - 1).to(dev)
+    inference.set_precision('fast')
+    try:
+        taps = {}
+        _hook(G, taps)
+        first = None
+        for rep in range(5):
+            taps.clear()
+            with torch.no_grad():
+                y = G(z, c, x, noise_mode='const')
+            cur = {k: v.clone() for k, v in taps.items()}
+            cur['y'] = y.clone()
+            if first is None:
+                first = cur
+                continue
+            for k, v in cur.items():
+                assert torch.equal(v, first[k]), (rep, k, int((v != first[k]).sum()))
+    finally:
+        inference.set_precision('fp32')
+
+
 def test_tiny_generator_fast_path(golden_tiny):
     from afcm_b200 import inference
     dev = torch.device('cuda:0')

@@ -161,6 +161,7 @@ def test_conv2d_tc_direct_nchw_is_repeatable(shape):
     conv2d_gradfix.set_conv_impl('f32', torch.float16)
     run = lambda: conv2d_gradfix.conv2d_native(x, w, 2, pre_scale=1.0 / np.sqrt(Ci * 9), impl='tc', out_dtype=torch.float16, bias=bias)
     try:
+        conv2d_gradfix.hybrid_pack = False                  # every shape through the direct kernel
         conv2d_gradfix.direct_nchw = False
         _lib.lib().afcm_conv_tc_set_issuers(1)
         ref = run()
@@ -173,7 +174,39 @@ def test_conv2d_tc_direct_nchw_is_repeatable(shape):
                     assert torch.equal(got, ref), (issuers, direct, rep, int((got != ref).sum()))
     finally:
         conv2d_gradfix.direct_nchw = True
+        conv2d_gradfix.hybrid_pack = False
         _lib.lib().afcm_conv_tc_set_issuers(1)
+
+
+def test_conv2d_tc_hybrid_packs_pitched_planes():
+    """Few input channels on large planes: conv2d_native takes pack + GEMM instead of the direct kernel (conv2d_gradfix._prefers_pack),
+    and the pack kernel reads the planes at the W + 2 pitch filtered_lrelu_tc wrote them at -- no dense copy in between."""
+    from afcm_b200.torch_utils.ops import conv2d_gradfix
+    N, Ci, Co, H, W = 2, 64, 91, 276, 276
+    dev = torch.device('cuda:0')
+    g = torch.Generator(device='cpu').manual_seed(9)
+    x = torch.randn(N, Ci, H, W, generator=g).to(dev).half()
+    w = torch.randn(Co, Ci, 3, 3, generator=g).to(dev)
+    icoef = (torch.rand(N, Ci, generator=g) + 0.5).to(dev)
+    bias = torch.randn(Co, generator=g).to(dev)
+    conv2d_gradfix.set_conv_impl('f32', torch.float16)
+    run = lambda t: conv2d_gradfix.conv2d_native(t, w, 2, icoef=icoef, pre_scale=1.0 / np.sqrt(Ci * 9), impl='tc', out_dtype=torch.float16, bias=bias)
+    default = conv2d_gradfix.hybrid_pack
+    conv2d_gradfix.hybrid_pack = True
+    assert conv2d_gradfix._prefers_pack(Ci, Co, H, W) and not conv2d_gradfix._prefers_pack(128, Co, H, W)
+    ref = run(x)
+    xq = torch.full((N, Ci, H, W + 2), float('nan'), device=dev, dtype=torch.float16)      # the pad columns must not be read
+    xq[..., :W] = x
+    n0 = _lib_launches()
+    got = run(xq[..., :W])
+    assert _lib_launches() - n0 == 2                        # pack + GEMM, no copy kernel of ours in between
+    assert torch.equal(got, ref)
+    try:
+        conv2d_gradfix.hybrid_pack = False
+        xz = torch.zeros_like(xq); xz[..., :W] = x
+        assert torch.equal(run(xz[..., :W]), ref)           # and the direct kernel agrees bit for bit
+    finally:
+        conv2d_gradfix.hybrid_pack = default
 
 
 @pytest.mark.parametrize('shape', [(2, 64, 64, 36, 36), (1, 4, 64, 52, 52), (2, 91, 181, 30, 22), (1, 181, 256, 38, 36), (2, 512, 512, 36, 36),
@@ -196,6 +229,7 @@ def test_conv2d_tc_direct_nchw_is_bit_identical_to_pack(shape, mod):
     conv2d_gradfix.set_conv_impl('f32', torch.float16)
     run = lambda: conv2d_gradfix.conv2d_native(x, w, 2, icoef=icoef, ocoef=ocoef, pre_scale=scale, impl='tc', out_dtype=torch.float16, bias=bias)
     try:
+        conv2d_gradfix.hybrid_pack = False
         conv2d_gradfix.direct_nchw = False
         ref = run()
         conv2d_gradfix.direct_nchw = True
@@ -211,6 +245,7 @@ def test_conv2d_tc_direct_nchw_is_bit_identical_to_pack(shape, mod):
         assert _lib_launches() - n0 == (1 if (H * (W + 2)) % 8 == 0 else 2)
     finally:
         conv2d_gradfix.direct_nchw = True
+        conv2d_gradfix.hybrid_pack = False
     assert got.shape == ref.shape and torch.equal(got, ref)
     assert torch.equal(got2, ref)
 
