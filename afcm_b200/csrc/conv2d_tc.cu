@@ -61,6 +61,7 @@ struct TcParams {
     int BN, n_tiles, m_tiles, cblocks;     // channel tile, #channel tiles, #pixel tiles per sample, ceil(Ci/64)
     int total_tiles;
     int stages;                            // TMA -> MMA ring depth (2 .. TC_MAX_STAGES)
+    int nk_last;                           // UMMA_K steps of the last 64-channel block that hold real channels: ceil((Ci mod 64) / 16), 1..4
     int issuers;                           // MMA-issuing warps: 1, or 2 taking alternate tiles (not in pipeline mode 2)
     int rowreuse;                          // 1: one A tile of 136 pixels per (ky, channel block) serves the three kx taps;
                                            // 2: the same with separate rings for the A rows and the per-tap weight tiles
@@ -290,9 +291,12 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     mbar_wait(&tempty[acc], acc_phase ^ 1, p.dbg, 0x200u | (unsigned)acc);
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256);
+                    int cb2 = 0;
                     for (int rb = 0; rb < nrows; rb++) {
                         mbar_wait(&afull[as], aph, p.dbg, 0x700u | (unsigned)as);
                         const uint32_t a_lo = desc_lo(smem_base + (uint32_t)(as * TC_AROW_BYTES));
+                        const int nk = (cb2 == p.cblocks - 1) ? p.nk_last : TC_BK / 16;      // K steps of all-zero padding channels are skipped
+                        if (++cb2 == p.cblocks) cb2 = 0;
 #pragma unroll
                         for (int kx = 0; kx < 3; kx++) {
                             mbar_wait(&full[stage], phase, p.dbg, 0x300u | (unsigned)stage);
@@ -301,8 +305,9 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             if (elect_one()) {
 #pragma unroll
                                 for (int k = 0; k < TC_BK / 16; k++)
-                                    umma_f16_lohi(tmem_d, a_lo + (uint32_t)(kx * 8 + k * 2), b_lo + (uint32_t)(k * 2), TC_DESC_HI, p.idesc,
-                                                  (rb | kx | k) != 0);
+                                    if (k < nk)
+                                        umma_f16_lohi(tmem_d, a_lo + (uint32_t)(kx * 8 + k * 2), b_lo + (uint32_t)(k * 2), TC_DESC_HI, p.idesc,
+                                                      (rb | kx | k) != 0);
                                 umma_commit(&empty[stage]);
                                 if (kx == 2) {
                                     umma_commit(&aempty[as]);
@@ -343,11 +348,13 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         // weights of kernel row ky: in the stage behind the A tile, or in the resident region
                         const uint32_t sb3 = p.bres ? smem_base + (uint32_t)((ky_ * 3 * p.cblocks + cb_) * b_bytes) : sa + TC_AROW_BYTES;
                         const uint32_t a_lo = desc_lo(sa), b_lo = desc_lo(sb3);
+                        const int nk = (cb_ == p.cblocks - 1) ? p.nk_last : TC_BK / 16;          // K steps of all-zero padding channels are skipped
                         if (elect_one()) {
 #pragma unroll
                             for (int kx = 0; kx < 3; kx++) {
 #pragma unroll
                                 for (int k = 0; k < TC_BK / 16; k++) {
+                                    if (k >= nk) continue;
                                     // the kx tap is the same tile read one pixel (= one 128-byte swizzled row) further on
                                     // (the swizzle is a function of the shared-memory address, so the descriptor's
                                     // base-offset field stays 0: measured bit-exact on B200, tests/test_gpu_tc.py); one
@@ -931,6 +938,7 @@ static int conv2d_tc_launch(const void* xp, const void* xn, const float* icoef, 
     p.BN = ((ceil_div(Co, p.n_tiles) + 31) / 32) * 32;
     p.m_tiles = ceil_div((long long)p.OH * p.Wp, TC_BM);
     p.cblocks = ceil_div(Ci, TC_BK);
+    p.nk_last = ceil_div(Ci - (p.cblocks - 1) * TC_BK, 16);
     const long long total = (long long)N * p.m_tiles * p.n_tiles;
     AFCM_CHECK_ARG(total <= 0x7fffffffLL, "too many tiles");
     p.total_tiles = (int)total;
