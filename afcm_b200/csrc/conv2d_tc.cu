@@ -411,6 +411,9 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int key = n * p.n_tiles + nt;
             const bool reload = key != (acc ? coef_key1 : coef_key0);      // the same for every epilogue thread
             if (reload) {
+                // every epilogue warp has finished the tiles that read the old contents of this buffer (the warps are not
+                // synchronised per tile otherwise; found by compute-sanitizer racecheck)
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 for (int j = et; j < p.BN; j += 256) {
                     const int o = o0 + j;
                     s_ocoef[acc * 256 + j] = (o < p.Co) ? (p.ocoef ? p.ocoef[(long long)n * p.Co + o] : 1.f) : 0.f;
