@@ -1,4 +1,5 @@
-"""Repeated direct-NCHW convolutions against the packed path: counts the runs that are not bit-identical (development aid)."""
+"""Repeated direct-NCHW convolutions against the packed path at shapes of every pipeline mode: counts the launches that are not
+bit-identical (how the raw-slot race of DESIGN.md 3.1 was isolated).  usage: [ISSUERS=1,2] python tools/conv_direct_repeat.py [reps]"""
 import sys, os
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
