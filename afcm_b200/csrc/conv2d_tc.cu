@@ -51,6 +51,7 @@ constexpr int TC_RAW_MAX_STAGES = 8;    // depth of the raw ring is chosen per l
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;          // 16 KB
 constexpr int TC_AROW_PX = TC_BM + 8;                  // row-reuse mode: 128 pixels + the two pixels to the right, rounded to 8
 constexpr int TC_AROW_BYTES = TC_AROW_PX * TC_BK * 2;  // 17 KB
+constexpr int TC_AROWP_BYTES = 18 * 8 * TC_BK * 2;     // ASW on pitched planes: 144 pixels from an 8-pixel boundary (18 KB), see the producers
 constexpr int TC_TMEM_COLS = 512;
 struct TcParams {
     const float* ocoef;     // [N, Co] or null
@@ -114,10 +115,11 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int b_bytes = p.BN * TC_BK * 2;
+    const int arow_bytes = (ASW && p.pitched) ? TC_AROWP_BYTES : TC_AROW_BYTES;       // A tile of a kernel row
     const int stage_bytes = p.rowreuse == 2 ? b_bytes
-                          : (p.bres ? TC_AROW_BYTES : (p.rowreuse ? TC_AROW_BYTES + 3 * b_bytes : TC_A_BYTES + b_bytes));
+                          : (p.bres ? arow_bytes : (p.rowreuse ? arow_bytes + 3 * b_bytes : TC_A_BYTES + b_bytes));
     // in front of the ring: the resident weights (tile (tap, cb) at (tap * cblocks + cb) * b_bytes), or the A ring of mode 2
-    const int res_bytes = p.rowreuse == 2 ? p.a_stages * TC_AROW_BYTES : (p.bres ? 9 * p.cblocks * b_bytes : 0);
+    const int res_bytes = p.rowreuse == 2 ? p.a_stages * arow_bytes : (p.bres ? 9 * p.cblocks * b_bytes : 0);
     uint8_t* raw = smem;                                                // ASW: TC_RAW_STAGES raw tiles in front of everything
     if (ASW) smem += p.raw_stages * TC_RAW_BYTES;                       // 19 x 1024 bytes each: the operand tiles stay 1024-byte aligned
     uint8_t* ring = smem + res_bytes;
@@ -234,11 +236,11 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         mbar_wait(&empty[stage], rg.phase ^ 1, p.dbg, 0x100u | (unsigned)stage);
                         uint8_t* sa = ring + stage * stage_bytes;
                         const bool skip_a = !ASW && (p.dbg_mode & 64) && ky > 0;     // timing experiment, see above
-                        mbar_expect_tx(&full[stage], (uint32_t)((ASW || skip_a) ? stage_bytes - TC_AROW_BYTES : stage_bytes));
+                        mbar_expect_tx(&full[stage], (uint32_t)((ASW || skip_a) ? stage_bytes - arow_bytes : stage_bytes));
                         if (!ASW && !skip_a) tma_load_3d(sa, &map_a2, &full[stage], cb * TC_BK, p0 + (ky - p.pad) * p.Wp - p.pad, n);
 #pragma unroll
                         for (int kx = 0; kx < 3; kx++)
-                            tma_load_3d(sa + TC_AROW_BYTES + kx * b_bytes, &map_b, &full[stage], cb * TC_BK, o0, ky * 3 + kx);
+                            tma_load_3d(sa + arow_bytes + kx * b_bytes, &map_b, &full[stage], cb * TC_BK, o0, ky * 3 + kx);
                         rg.next();
                         continue;
                     }
@@ -291,12 +293,15 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     mbar_wait(&tempty[acc], acc_phase ^ 1, p.dbg, 0x200u | (unsigned)acc);
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256);
-                    int cb2 = 0;
+                    const int pp_base = ((tile / p.n_tiles) % p.m_tiles) * TC_BM - p.pad * p.Wp - p.pad;   // first pixel of the ky = 0 tile
+                    int cb2 = 0, ky2 = 0;
                     for (int rb = 0; rb < nrows; rb++) {
                         mbar_wait(&afull[as], aph, p.dbg, 0x700u | (unsigned)as);
-                        const uint32_t a_lo = desc_lo(smem_base + (uint32_t)(as * TC_AROW_BYTES));
+                        // pitched ASW tiles start at an 8-pixel boundary: the first pixel is row (pp0 mod 8) of the tile
+                        const uint32_t row0 = (ASW && p.pitched) ? (uint32_t)((pp_base + ky2 * p.Wp) & 7) : 0u;
+                        const uint32_t a_lo = desc_lo(smem_base + (uint32_t)(as * arow_bytes)) + row0 * 8u;
                         const int nk = (cb2 == p.cblocks - 1) ? p.nk_last : TC_BK / 16;      // K steps of all-zero padding channels are skipped
-                        if (++cb2 == p.cblocks) cb2 = 0;
+                        if (++cb2 == p.cblocks) { cb2 = 0; ky2++; }
 #pragma unroll
                         for (int kx = 0; kx < 3; kx++) {
                             mbar_wait(&full[stage], phase, p.dbg, 0x300u | (unsigned)stage);
@@ -336,6 +341,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 tc_fence_after();
                 tr.mark(11);
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 256);
+                const int pp_base = ((tile / p.n_tiles) % p.m_tiles) * TC_BM - p.pad * p.Wp - p.pad;       // first pixel of the ky = 0 tile
                 int ky_ = 0, cb_ = 0;                                   // row-reuse mode: kb = ky_ * cblocks + cb_
                 for (int kb = 0; kb < kblocks; kb++) {
                     const int stage = rg.slot();
@@ -346,8 +352,10 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     const bool last = kb == kblocks - 1;
                     if (p.rowreuse) {
                         // weights of kernel row ky: in the stage behind the A tile, or in the resident region
-                        const uint32_t sb3 = p.bres ? smem_base + (uint32_t)((ky_ * 3 * p.cblocks + cb_) * b_bytes) : sa + TC_AROW_BYTES;
-                        const uint32_t a_lo = desc_lo(sa), b_lo = desc_lo(sb3);
+                        const uint32_t sb3 = p.bres ? smem_base + (uint32_t)((ky_ * 3 * p.cblocks + cb_) * b_bytes) : sa + (uint32_t)arow_bytes;
+                        // pitched ASW tiles start at an 8-pixel boundary: the first pixel is row (pp0 mod 8) of the tile
+                        const uint32_t row0 = (ASW && p.pitched) ? (uint32_t)((pp_base + ky_ * p.Wp) & 7) : 0u;
+                        const uint32_t a_lo = desc_lo(sa) + row0 * 8u, b_lo = desc_lo(sb3);
                         const int nk = (cb_ == p.cblocks - 1) ? p.nk_last : TC_BK / 16;          // K steps of all-zero padding channels are skipped
                         if (elect_one()) {
 #pragma unroll
@@ -544,7 +552,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         constexpr int NIT = (TC_AROW_BLKS + 1) / 2;                                // 9 iterations of 16 pixels (the last one: 8)
         const bool two_rings = p.rowreuse == 2;
         const int nst = two_rings ? p.a_stages : p.stages;
-        const int sbytes = two_rings ? TC_AROW_BYTES : stage_bytes;
+        const int sbytes = two_rings ? arow_bytes : stage_bytes;
         uint8_t* abase = two_rings ? smem : ring;
         uint64_t* fullb = two_rings ? afull : full;
         uint64_t* emptyb = two_rings ? aempty : empty;
@@ -574,71 +582,104 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         s1 = cs + 1 < p.Ci ? p.icoef[(long long)n * p.Ci + cs + 1] : 0.f;
                     }
                     mbar_wait(&rfull[rs], rph, p.dbg, 0xa00u | (unsigned)rs);
-                    int pp = pp0 + 8 * b2 + 2 * m;                                 // flat pixel of this lane's pair in iteration 0 (even)
-                    const uint32_t src = raw_lane + (uint32_t)(rs * TC_RAW_BYTES) - (uint32_t)(2 * a0);
-                    uint32_t v0[NIT], v1[NIT];
                     if (p.pitched) {
-                        // the flat plane exists in memory (pad pixels are stored zeros, outside the plane: zero fill): a straight copy
-                        const uint32_t a = src + (uint32_t)(2 * pp);
+                        // Planes stored at the pitch W + 2 ARE the flat plane (pad pixels are stored zeros; outside the plane TMA
+                        // zero-fills), so the tile is a pure [channel][pixel] -> [pixel][channel] transposition, and it can start
+                        // at the raw tile's own 8-pixel boundary a0: the MMA descriptors skip the first (pp0 - a0) rows instead
+                        // (a row offset of a K-major SWIZZLE_128B tile is free).  ldmatrix.trans reads an 8 x 8 block (8 channel
+                        // rows x 16 bytes, conflict-free with the 304-byte raw rows) and hands every lane {channels 2t, 2t+1} of
+                        // pixel lane / 4 -- exactly the fragment stmatrix stores as the 16-byte chunk of 8 pixel rows of the
+                        // swizzled tile.  10 shared-memory instructions per warp and stage instead of 54.
+                        const uint32_t r8 = lane & 7u, mi = lane >> 3;
+                        const uint32_t rbase = smem_u32(raw) + (uint32_t)(rs * TC_RAW_BYTES) + (uint32_t)(8 * pw + (int)r8) * (TC_RAW_PX * 2) + mi * 16u;
+                        uint32_t f[18];
 #pragma unroll
-                        for (int it = 0; it < NIT; it++) {
-                            v0[it] = 0u; v1[it] = 0u;
-                            if (it < NIT - 1 || b2 == 0) {
-                                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v0[it]) : "r"(a + (uint32_t)(32 * it)) : "memory");
-                                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v1[it]) : "r"(a + (uint32_t)(32 * it + TC_RAW_PX * 2)) : "memory");
-                            }
-                        }
-                    } else {
-                        int y = y0, x = pp - y0 * p.Wp;
-                        if (x >= p.Wp) { x -= p.Wp; y++; }
+                        for (int g4 = 0; g4 < 4; g4++)
+                            asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                                         : "=r"(f[4 * g4]), "=r"(f[4 * g4 + 1]), "=r"(f[4 * g4 + 2]), "=r"(f[4 * g4 + 3]) : "r"(rbase + (uint32_t)(64 * g4)) : "memory");
+                        asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(f[16]), "=r"(f[17]) : "r"(rbase + 256u) : "memory");
+                        // release the raw slot once the loads have RETURNED (see the dense path below)
+                        uint32_t loaded = 0u;
 #pragma unroll
-                        for (int it = 0; it < NIT; it++) {
-                            // rows outside the plane / channels >= Ci were zero-filled; pad pixels x >= W are zeros by definition
-                            const bool ok = (unsigned)pp < HWp && x < p.W && (it < NIT - 1 || b2 == 0);
-                            v0[it] = 0u; v1[it] = 0u;
-                            if (ok) {
-                                const uint32_t a = src + (uint32_t)(2 * (pp - 2 * y));  // element y W + x = pp - 2y of the plane
-                                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v0[it]) : "r"(a) : "memory");
-                                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v1[it]) : "r"(a + (uint32_t)(TC_RAW_PX * 2)) : "memory");
-                            }
-                            pp += 16; x += 16;
-                            if (x >= p.Wp) { x -= p.Wp; y++; }
-                        }
-                    }
-                    // The raw slot may be refilled once the loads have RETURNED, not merely issued: the arrive is handled by the
-                    // barrier unit and overtakes loads still queued behind the tensor core's operand reads in the shared-memory
-                    // pipe (measured: with a 2-deep operand ring the refill then lands under the last loads of a warp -- 16 of
-                    // 16 runs of a 128 -> 128 channel layer wrong in a few dozen pixels).  Hence a data dependency the compiler
-                    // cannot fold: the barrier address gets (OR of every loaded register) & dbg_mode added, and dbg_mode is a
-                    // kernel parameter that is always 0 on this path.
-                    uint32_t loaded = 0u;
-#pragma unroll
-                    for (int it = 0; it < NIT; it++) loaded |= v0[it] | v1[it];
-                    __syncwarp();
-                    if (lane == 0)
-                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&rempty[rs]) + (loaded & (uint32_t)p.dbg_mode)) : "memory");
-                    if (++rs == p.raw_stages) { rs = 0; rph ^= 1; }
-                    const int stage = rg.slot();
-                    mbar_wait(&emptyb[stage], rg.phase ^ 1, p.dbg, 0x800u | (unsigned)stage);
-                    const uint32_t dst = smem_u32(abase + stage * sbytes);
-#pragma unroll
-                    for (int it = 0; it < NIT; it++) {
-                        uint32_t te = __byte_perm(v0[it], v1[it], 0x5410), to = __byte_perm(v0[it], v1[it], 0x7632);
+                        for (int j = 0; j < 18; j++) loaded |= f[j];
+                        __syncwarp();
+                        if (lane == 0)
+                            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&rempty[rs]) + (loaded & (uint32_t)p.dbg_mode)) : "memory");
+                        if (++rs == p.raw_stages) { rs = 0; rph ^= 1; }
+                        const int stage = rg.slot();
+                        mbar_wait(&emptyb[stage], rg.phase ^ 1, p.dbg, 0x800u | (unsigned)stage);
                         if (p.icoef) {                                             // fp32 product, one rounding: as the pack kernel
-                            const float2 fe = __half22float2(*reinterpret_cast<const __half2*>(&te));
-                            const float2 fo = __half22float2(*reinterpret_cast<const __half2*>(&to));
-                            te = pack_tc(fe.x * s0, fe.y * s1, (__half*)nullptr);
-                            to = pack_tc(fo.x * s0, fo.y * s1, (__half*)nullptr);
+#pragma unroll
+                            for (int j = 0; j < 18; j++) {
+                                const float2 fv = __half22float2(*reinterpret_cast<const __half2*>(&f[j]));
+                                f[j] = pack_tc(fv.x * s0, fv.y * s1, (__half*)nullptr);
+                            }
                         }
-                        if (it < NIT - 1 || b2 == 0) {
-                            const uint32_t d = dst + (uint32_t)(it * 2048);
-                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(d + off_first), "r"(b2 ? to : te) : "memory");
-                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(d + off_second), "r"(b2 ? te : to) : "memory");
+                        const uint32_t dbase = smem_u32(abase + stage * sbytes) + (mi * 8u + r8) * 128u + (((uint32_t)pw ^ r8) << 4);
+#pragma unroll
+                        for (int g4 = 0; g4 < 4; g4++)
+                            asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};"
+                                         ::"r"(dbase + (uint32_t)(4096 * g4)), "r"(f[4 * g4]), "r"(f[4 * g4 + 1]), "r"(f[4 * g4 + 2]), "r"(f[4 * g4 + 3]) : "memory");
+                        asm volatile("stmatrix.sync.aligned.m8n8.x2.shared.b16 [%0], {%1, %2};" ::"r"(dbase + 16384u), "r"(f[16]), "r"(f[17]) : "memory");
+                        fence_proxy_async();                                       // generic-proxy stores -> visible to tcgen05.mma
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&fullb[stage]);
+                    } else {
+                        int pp = pp0 + 8 * b2 + 2 * m;                                 // flat pixel of this lane's pair in iteration 0 (even)
+                        const uint32_t src = raw_lane + (uint32_t)(rs * TC_RAW_BYTES) - (uint32_t)(2 * a0);
+                        uint32_t v0[NIT], v1[NIT];
+                        {
+                            int y = y0, x = pp - y0 * p.Wp;
+                            if (x >= p.Wp) { x -= p.Wp; y++; }
+    #pragma unroll
+                            for (int it = 0; it < NIT; it++) {
+                                // rows outside the plane / channels >= Ci were zero-filled; pad pixels x >= W are zeros by definition
+                                const bool ok = (unsigned)pp < HWp && x < p.W && (it < NIT - 1 || b2 == 0);
+                                v0[it] = 0u; v1[it] = 0u;
+                                if (ok) {
+                                    const uint32_t a = src + (uint32_t)(2 * (pp - 2 * y));  // element y W + x = pp - 2y of the plane
+                                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v0[it]) : "r"(a) : "memory");
+                                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v1[it]) : "r"(a + (uint32_t)(TC_RAW_PX * 2)) : "memory");
+                                }
+                                pp += 16; x += 16;
+                                if (x >= p.Wp) { x -= p.Wp; y++; }
+                            }
                         }
+                        // The raw slot may be refilled once the loads have RETURNED, not merely issued: the arrive is handled by the
+                        // barrier unit and overtakes loads still queued behind the tensor core's operand reads in the shared-memory
+                        // pipe (measured: with a 2-deep operand ring the refill then lands under the last loads of a warp -- 16 of
+                        // 16 runs of a 128 -> 128 channel layer wrong in a few dozen pixels).  Hence a data dependency the compiler
+                        // cannot fold: the barrier address gets (OR of every loaded register) & dbg_mode added, and dbg_mode is a
+                        // kernel parameter that is always 0 on this path.
+                        uint32_t loaded = 0u;
+    #pragma unroll
+                        for (int it = 0; it < NIT; it++) loaded |= v0[it] | v1[it];
+                        __syncwarp();
+                        if (lane == 0)
+                            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&rempty[rs]) + (loaded & (uint32_t)p.dbg_mode)) : "memory");
+                        if (++rs == p.raw_stages) { rs = 0; rph ^= 1; }
+                        const int stage = rg.slot();
+                        mbar_wait(&emptyb[stage], rg.phase ^ 1, p.dbg, 0x800u | (unsigned)stage);
+                        const uint32_t dst = smem_u32(abase + stage * sbytes);
+    #pragma unroll
+                        for (int it = 0; it < NIT; it++) {
+                            uint32_t te = __byte_perm(v0[it], v1[it], 0x5410), to = __byte_perm(v0[it], v1[it], 0x7632);
+                            if (p.icoef) {                                             // fp32 product, one rounding: as the pack kernel
+                                const float2 fe = __half22float2(*reinterpret_cast<const __half2*>(&te));
+                                const float2 fo = __half22float2(*reinterpret_cast<const __half2*>(&to));
+                                te = pack_tc(fe.x * s0, fe.y * s1, (__half*)nullptr);
+                                to = pack_tc(fo.x * s0, fo.y * s1, (__half*)nullptr);
+                            }
+                            if (it < NIT - 1 || b2 == 0) {
+                                const uint32_t d = dst + (uint32_t)(it * 2048);
+                                asm volatile("st.shared.b32 [%0], %1;" ::"r"(d + off_first), "r"(b2 ? to : te) : "memory");
+                                asm volatile("st.shared.b32 [%0], %1;" ::"r"(d + off_second), "r"(b2 ? te : to) : "memory");
+                            }
+                        }
+                        fence_proxy_async();                                           // generic-proxy stores -> visible to tcgen05.mma
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&fullb[stage]);
                     }
-                    fence_proxy_async();                                           // generic-proxy stores -> visible to tcgen05.mma
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&fullb[stage]);
                     rg.next();
                 }
             }
@@ -986,7 +1027,8 @@ static int conv2d_tc_launch(const void* xp, const void* xn, const float* icoef, 
     // a single channel tile whose 9 x cblocks weight tiles fit next to a 3-deep A ring: keep the weights resident
     const int res_bytes = 9 * p.cblocks * b_bytes;
     const int raw_min = asw ? 3 * TC_RAW_BYTES : 0;
-    p.bres = p.rowreuse && g_bres != 0 && p.n_tiles == 1 && res_bytes + 3 * TC_AROW_BYTES + fixed + raw_min <= max_smem_optin();
+    p.bres = p.rowreuse && g_bres != 0 && p.n_tiles == 1 &&
+             res_bytes + 3 * ((asw && p.pitched) ? TC_AROWP_BYTES : TC_AROW_BYTES) + fixed + raw_min <= max_smem_optin();
     p.bres = p.bres && p.rowreuse == 1;
     int stages, smem;
     if (!asw) {
@@ -1002,15 +1044,16 @@ static int conv2d_tc_launch(const void* xp, const void* xn, const float* icoef, 
         // the MMA time of the stages in between, which is short for small channel tiles (384 clocks per stage at BN = 64:
         // measured 0.79 ms instead of 0.53 ms on the 64-channel layers with a 3-deep ring); the weight ring keeps >= 4 stages
         const int avail = max_smem_optin() - fixed;
+        const int arow_asw = p.pitched ? TC_AROWP_BYTES : TC_AROW_BYTES;       // pitched planes: 144-pixel tiles from an 8-pixel boundary
         p.raw_stages = 3;
         if (p.bres) {
-            stages = (avail - res_bytes - p.raw_stages * TC_RAW_BYTES) / TC_AROW_BYTES;               // A ring
+            stages = (avail - res_bytes - p.raw_stages * TC_RAW_BYTES) / arow_asw;               // A ring
             if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
-            smem = res_bytes + stages * TC_AROW_BYTES;
-        } else if (p.rowreuse == 1 && (avail - 2 * TC_RAW_BYTES) / (TC_AROW_BYTES + 3 * b_bytes) >= 2) {
+            smem = res_bytes + stages * arow_asw;
+        } else if (p.rowreuse == 1 && (avail - 2 * TC_RAW_BYTES) / (arow_asw + 3 * b_bytes) >= 2) {
             // combined stages (A row + its three weight tiles), as the packed path uses for channel tiles up to 192: one barrier
             // pair per kernel row instead of four (measured on the packed path: separate rings cost 15-40 % on these layers)
-            const int stage_bytes = TC_AROW_BYTES + 3 * b_bytes;
+            const int stage_bytes = arow_asw + 3 * b_bytes;
             stages = (avail - p.raw_stages * TC_RAW_BYTES) / stage_bytes;
             if (stages < 2) { p.raw_stages = 2; stages = (avail - p.raw_stages * TC_RAW_BYTES) / stage_bytes; }
             if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
@@ -1019,15 +1062,15 @@ static int conv2d_tc_launch(const void* xp, const void* xn, const float* icoef, 
             // the A tiles and the weight tiles get rings of their own
             p.rowreuse = 2;
             stages = 4;                                                                               // weight ring
-            auto ast = [&]() { return (avail - stages * b_bytes - p.raw_stages * TC_RAW_BYTES) / TC_AROW_BYTES; };
+            auto ast = [&]() { return (avail - stages * b_bytes - p.raw_stages * TC_RAW_BYTES) / arow_asw; };
             if (ast() < 2) p.raw_stages = 2;
             p.a_stages = ast() > 8 ? 8 : ast();
             if (p.a_stages < 2) stages = 0;
             else {
-                stages = (avail - p.a_stages * TC_AROW_BYTES - p.raw_stages * TC_RAW_BYTES) / b_bytes;   // leftover to the weights
+                stages = (avail - p.a_stages * arow_asw - p.raw_stages * TC_RAW_BYTES) / b_bytes;   // leftover to the weights
                 if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
             }
-            smem = p.a_stages * TC_AROW_BYTES + stages * b_bytes;
+            smem = p.a_stages * arow_asw + stages * b_bytes;
         }
         if (p.raw_stages > TC_RAW_MAX_STAGES) p.raw_stages = TC_RAW_MAX_STAGES;
         if (p.raw_stages < 2) stages = 0;
