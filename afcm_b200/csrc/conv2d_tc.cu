@@ -568,6 +568,84 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         TcRing rg(nst, two_rings ? 1 : p.issuers);
         int rs = 0; uint32_t rph = 0;
         int tit = 0;
+        if (p.pitched) {
+            // Planes stored at the pitch W + 2 ARE the flat plane (pad pixels are stored zeros; outside the plane TMA zero-fills), so
+            // the tile is a pure [channel][pixel] -> [pixel][channel] transposition, and it can start at the raw tile's own 8-pixel
+            // boundary a0: the MMA descriptors skip the first (pp0 - a0) rows instead (a row offset of a K-major SWIZZLE_128B tile
+            // is free).  ldmatrix.trans reads an 8 x 8 block (8 channel rows x 16 bytes, conflict-free with the 304-byte raw rows)
+            // and hands every lane {channels 2t, 2t+1} of pixel lane / 4 -- exactly the fragment stmatrix stores as the 16-byte chunk
+            // of 8 pixel rows of the swizzled tile: 10 shared-memory instructions per warp and stage instead of 54.  The loop is
+            // software-pipelined over the flattened (tile, kernel row, channel block) sequence: the raw tile of the NEXT stage is
+            // read into registers before this stage waits for its operand slot, so the two barrier round trips overlap.
+            const uint32_t r8 = lane & 7u, mi = lane >> 3;
+            const uint32_t rlane = smem_u32(raw) + (uint32_t)(8 * pw + (int)r8) * (TC_RAW_PX * 2) + mi * 16u;
+            const uint32_t dlane = (mi * 8u + r8) * 128u + (((uint32_t)pw ^ r8) << 4);
+            auto load_raw = [&](uint32_t (&f)[18], int slot) {
+                const uint32_t rbase = rlane + (uint32_t)(slot * TC_RAW_BYTES);
+#pragma unroll
+                for (int g4 = 0; g4 < 4; g4++)
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(f[4 * g4]), "=r"(f[4 * g4 + 1]), "=r"(f[4 * g4 + 2]), "=r"(f[4 * g4 + 3]) : "r"(rbase + (uint32_t)(64 * g4)) : "memory");
+                asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(f[16]), "=r"(f[17]) : "r"(rbase + 256u) : "memory");
+            };
+            uint32_t f[18], fn[18];
+            int tile = blockIdx.x, ky = 0, cb = 0;
+            bool valid = tile < p.total_tiles;
+            int rs_cur = 0;
+            if (valid) {
+                mbar_wait(&rfull[rs], rph, p.dbg, 0xa00u | (unsigned)rs);
+                load_raw(f, rs);
+                rs_cur = rs;
+                if (++rs == p.raw_stages) { rs = 0; rph ^= 1; }
+            }
+            while (valid) {
+                if (ky == 0 && cb == 0) rg.begin_tile(tit);
+                int ntile = tile, nky = ky, ncb = cb + 1;
+                if (ncb == p.cblocks) { ncb = 0; if (++nky == 3) { nky = 0; ntile += gridDim.x; } }
+                const bool nvalid = ntile < p.total_tiles;
+                // The raw slot may be refilled once the loads have RETURNED, not merely issued (see the dense path below): the
+                // arrive carries a data dependency on every loaded register that the compiler cannot fold.
+                uint32_t loaded = 0u;
+#pragma unroll
+                for (int j = 0; j < 18; j++) loaded |= f[j];
+                __syncwarp();
+                if (lane == 0)
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&rempty[rs_cur]) + (loaded & (uint32_t)p.dbg_mode)) : "memory");
+                if (nvalid) {                                                      // prefetch the next stage's raw tile
+                    mbar_wait(&rfull[rs], rph, p.dbg, 0xa00u | (unsigned)rs);
+                    load_raw(fn, rs);
+                    rs_cur = rs;
+                    if (++rs == p.raw_stages) { rs = 0; rph ^= 1; }
+                }
+                const int stage = rg.slot();
+                mbar_wait(&emptyb[stage], rg.phase ^ 1, p.dbg, 0x800u | (unsigned)stage);
+                if (p.icoef) {                                                     // fp32 product, one rounding: as the pack kernel
+                    const int n = (tile / p.n_tiles) / p.m_tiles;
+                    const int cs = cb * TC_BK + 8 * pw + 2 * q;
+                    const float s0 = cs < p.Ci ? p.icoef[(long long)n * p.Ci + cs] : 0.f;
+                    const float s1 = cs + 1 < p.Ci ? p.icoef[(long long)n * p.Ci + cs + 1] : 0.f;
+#pragma unroll
+                    for (int j = 0; j < 18; j++) {
+                        const float2 fv = __half22float2(*reinterpret_cast<const __half2*>(&f[j]));
+                        f[j] = pack_tc(fv.x * s0, fv.y * s1, (__half*)nullptr);
+                    }
+                }
+                const uint32_t dbase = smem_u32(abase + stage * sbytes) + dlane;
+#pragma unroll
+                for (int g4 = 0; g4 < 4; g4++)
+                    asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};"
+                                 ::"r"(dbase + (uint32_t)(4096 * g4)), "r"(f[4 * g4]), "r"(f[4 * g4 + 1]), "r"(f[4 * g4 + 2]), "r"(f[4 * g4 + 3]) : "memory");
+                asm volatile("stmatrix.sync.aligned.m8n8.x2.shared.b16 [%0], {%1, %2};" ::"r"(dbase + 16384u), "r"(f[16]), "r"(f[17]) : "memory");
+                fence_proxy_async();                                               // generic-proxy stores -> visible to tcgen05.mma
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&fullb[stage]);
+                rg.next();
+                if (nky == 0 && ncb == 0) { rg.end_tile(); tit++; }
+#pragma unroll
+                for (int j = 0; j < 18; j++) f[j] = fn[j];
+                tile = ntile; ky = nky; cb = ncb; valid = nvalid;
+            }
+        } else
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, tit++) {
             rg.begin_tile(tit);
             for (int ky = 0; ky < 3; ky++) {
@@ -582,104 +660,60 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         s1 = cs + 1 < p.Ci ? p.icoef[(long long)n * p.Ci + cs + 1] : 0.f;
                     }
                     mbar_wait(&rfull[rs], rph, p.dbg, 0xa00u | (unsigned)rs);
-                    if (p.pitched) {
-                        // Planes stored at the pitch W + 2 ARE the flat plane (pad pixels are stored zeros; outside the plane TMA
-                        // zero-fills), so the tile is a pure [channel][pixel] -> [pixel][channel] transposition, and it can start
-                        // at the raw tile's own 8-pixel boundary a0: the MMA descriptors skip the first (pp0 - a0) rows instead
-                        // (a row offset of a K-major SWIZZLE_128B tile is free).  ldmatrix.trans reads an 8 x 8 block (8 channel
-                        // rows x 16 bytes, conflict-free with the 304-byte raw rows) and hands every lane {channels 2t, 2t+1} of
-                        // pixel lane / 4 -- exactly the fragment stmatrix stores as the 16-byte chunk of 8 pixel rows of the
-                        // swizzled tile.  10 shared-memory instructions per warp and stage instead of 54.
-                        const uint32_t r8 = lane & 7u, mi = lane >> 3;
-                        const uint32_t rbase = smem_u32(raw) + (uint32_t)(rs * TC_RAW_BYTES) + (uint32_t)(8 * pw + (int)r8) * (TC_RAW_PX * 2) + mi * 16u;
-                        uint32_t f[18];
+                    int pp = pp0 + 8 * b2 + 2 * m;                                 // flat pixel of this lane's pair in iteration 0 (even)
+                    const uint32_t src = raw_lane + (uint32_t)(rs * TC_RAW_BYTES) - (uint32_t)(2 * a0);
+                    uint32_t v0[NIT], v1[NIT];
+                    {
+                        int y = y0, x = pp - y0 * p.Wp;
+                        if (x >= p.Wp) { x -= p.Wp; y++; }
 #pragma unroll
-                        for (int g4 = 0; g4 < 4; g4++)
-                            asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
-                                         : "=r"(f[4 * g4]), "=r"(f[4 * g4 + 1]), "=r"(f[4 * g4 + 2]), "=r"(f[4 * g4 + 3]) : "r"(rbase + (uint32_t)(64 * g4)) : "memory");
-                        asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(f[16]), "=r"(f[17]) : "r"(rbase + 256u) : "memory");
-                        // release the raw slot once the loads have RETURNED (see the dense path below)
-                        uint32_t loaded = 0u;
-#pragma unroll
-                        for (int j = 0; j < 18; j++) loaded |= f[j];
-                        __syncwarp();
-                        if (lane == 0)
-                            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&rempty[rs]) + (loaded & (uint32_t)p.dbg_mode)) : "memory");
-                        if (++rs == p.raw_stages) { rs = 0; rph ^= 1; }
-                        const int stage = rg.slot();
-                        mbar_wait(&emptyb[stage], rg.phase ^ 1, p.dbg, 0x800u | (unsigned)stage);
-                        if (p.icoef) {                                             // fp32 product, one rounding: as the pack kernel
-#pragma unroll
-                            for (int j = 0; j < 18; j++) {
-                                const float2 fv = __half22float2(*reinterpret_cast<const __half2*>(&f[j]));
-                                f[j] = pack_tc(fv.x * s0, fv.y * s1, (__half*)nullptr);
-                            }
-                        }
-                        const uint32_t dbase = smem_u32(abase + stage * sbytes) + (mi * 8u + r8) * 128u + (((uint32_t)pw ^ r8) << 4);
-#pragma unroll
-                        for (int g4 = 0; g4 < 4; g4++)
-                            asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};"
-                                         ::"r"(dbase + (uint32_t)(4096 * g4)), "r"(f[4 * g4]), "r"(f[4 * g4 + 1]), "r"(f[4 * g4 + 2]), "r"(f[4 * g4 + 3]) : "memory");
-                        asm volatile("stmatrix.sync.aligned.m8n8.x2.shared.b16 [%0], {%1, %2};" ::"r"(dbase + 16384u), "r"(f[16]), "r"(f[17]) : "memory");
-                        fence_proxy_async();                                       // generic-proxy stores -> visible to tcgen05.mma
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&fullb[stage]);
-                    } else {
-                        int pp = pp0 + 8 * b2 + 2 * m;                                 // flat pixel of this lane's pair in iteration 0 (even)
-                        const uint32_t src = raw_lane + (uint32_t)(rs * TC_RAW_BYTES) - (uint32_t)(2 * a0);
-                        uint32_t v0[NIT], v1[NIT];
-                        {
-                            int y = y0, x = pp - y0 * p.Wp;
-                            if (x >= p.Wp) { x -= p.Wp; y++; }
-    #pragma unroll
-                            for (int it = 0; it < NIT; it++) {
-                                // rows outside the plane / channels >= Ci were zero-filled; pad pixels x >= W are zeros by definition
-                                const bool ok = (unsigned)pp < HWp && x < p.W && (it < NIT - 1 || b2 == 0);
-                                v0[it] = 0u; v1[it] = 0u;
-                                if (ok) {
-                                    const uint32_t a = src + (uint32_t)(2 * (pp - 2 * y));  // element y W + x = pp - 2y of the plane
-                                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v0[it]) : "r"(a) : "memory");
-                                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v1[it]) : "r"(a + (uint32_t)(TC_RAW_PX * 2)) : "memory");
-                                }
-                                pp += 16; x += 16;
-                                if (x >= p.Wp) { x -= p.Wp; y++; }
-                            }
-                        }
-                        // The raw slot may be refilled once the loads have RETURNED, not merely issued: the arrive is handled by the
-                        // barrier unit and overtakes loads still queued behind the tensor core's operand reads in the shared-memory
-                        // pipe (measured: with a 2-deep operand ring the refill then lands under the last loads of a warp -- 16 of
-                        // 16 runs of a 128 -> 128 channel layer wrong in a few dozen pixels).  Hence a data dependency the compiler
-                        // cannot fold: the barrier address gets (OR of every loaded register) & dbg_mode added, and dbg_mode is a
-                        // kernel parameter that is always 0 on this path.
-                        uint32_t loaded = 0u;
-    #pragma unroll
-                        for (int it = 0; it < NIT; it++) loaded |= v0[it] | v1[it];
-                        __syncwarp();
-                        if (lane == 0)
-                            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&rempty[rs]) + (loaded & (uint32_t)p.dbg_mode)) : "memory");
-                        if (++rs == p.raw_stages) { rs = 0; rph ^= 1; }
-                        const int stage = rg.slot();
-                        mbar_wait(&emptyb[stage], rg.phase ^ 1, p.dbg, 0x800u | (unsigned)stage);
-                        const uint32_t dst = smem_u32(abase + stage * sbytes);
-    #pragma unroll
                         for (int it = 0; it < NIT; it++) {
-                            uint32_t te = __byte_perm(v0[it], v1[it], 0x5410), to = __byte_perm(v0[it], v1[it], 0x7632);
-                            if (p.icoef) {                                             // fp32 product, one rounding: as the pack kernel
-                                const float2 fe = __half22float2(*reinterpret_cast<const __half2*>(&te));
-                                const float2 fo = __half22float2(*reinterpret_cast<const __half2*>(&to));
-                                te = pack_tc(fe.x * s0, fe.y * s1, (__half*)nullptr);
-                                to = pack_tc(fo.x * s0, fo.y * s1, (__half*)nullptr);
+                            // rows outside the plane / channels >= Ci were zero-filled; pad pixels x >= W are zeros by definition
+                            const bool ok = (unsigned)pp < HWp && x < p.W && (it < NIT - 1 || b2 == 0);
+                            v0[it] = 0u; v1[it] = 0u;
+                            if (ok) {
+                                const uint32_t a = src + (uint32_t)(2 * (pp - 2 * y));  // element y W + x = pp - 2y of the plane
+                                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v0[it]) : "r"(a) : "memory");
+                                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v1[it]) : "r"(a + (uint32_t)(TC_RAW_PX * 2)) : "memory");
                             }
-                            if (it < NIT - 1 || b2 == 0) {
-                                const uint32_t d = dst + (uint32_t)(it * 2048);
-                                asm volatile("st.shared.b32 [%0], %1;" ::"r"(d + off_first), "r"(b2 ? to : te) : "memory");
-                                asm volatile("st.shared.b32 [%0], %1;" ::"r"(d + off_second), "r"(b2 ? te : to) : "memory");
-                            }
+                            pp += 16; x += 16;
+                            if (x >= p.Wp) { x -= p.Wp; y++; }
                         }
-                        fence_proxy_async();                                           // generic-proxy stores -> visible to tcgen05.mma
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&fullb[stage]);
                     }
+                    // The raw slot may be refilled once the loads have RETURNED, not merely issued: the arrive is handled by the
+                    // barrier unit and overtakes loads still queued behind the tensor core's operand reads in the shared-memory
+                    // pipe (measured: with a 2-deep operand ring the refill then lands under the last loads of a warp -- 16 of
+                    // 16 runs of a 128 -> 128 channel layer wrong in a few dozen pixels).  Hence a data dependency the compiler
+                    // cannot fold: the barrier address gets (OR of every loaded register) & dbg_mode added, and dbg_mode is a
+                    // kernel parameter that is always 0 on this path.
+                    uint32_t loaded = 0u;
+#pragma unroll
+                    for (int it = 0; it < NIT; it++) loaded |= v0[it] | v1[it];
+                    __syncwarp();
+                    if (lane == 0)
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&rempty[rs]) + (loaded & (uint32_t)p.dbg_mode)) : "memory");
+                    if (++rs == p.raw_stages) { rs = 0; rph ^= 1; }
+                    const int stage = rg.slot();
+                    mbar_wait(&emptyb[stage], rg.phase ^ 1, p.dbg, 0x800u | (unsigned)stage);
+                    const uint32_t dst = smem_u32(abase + stage * sbytes);
+#pragma unroll
+                    for (int it = 0; it < NIT; it++) {
+                        uint32_t te = __byte_perm(v0[it], v1[it], 0x5410), to = __byte_perm(v0[it], v1[it], 0x7632);
+                        if (p.icoef) {                                             // fp32 product, one rounding: as the pack kernel
+                            const float2 fe = __half22float2(*reinterpret_cast<const __half2*>(&te));
+                            const float2 fo = __half22float2(*reinterpret_cast<const __half2*>(&to));
+                            te = pack_tc(fe.x * s0, fe.y * s1, (__half*)nullptr);
+                            to = pack_tc(fo.x * s0, fo.y * s1, (__half*)nullptr);
+                        }
+                        if (it < NIT - 1 || b2 == 0) {
+                            const uint32_t d = dst + (uint32_t)(it * 2048);
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(d + off_first), "r"(b2 ? to : te) : "memory");
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(d + off_second), "r"(b2 ? te : to) : "memory");
+                        }
+                    }
+                    fence_proxy_async();                                           // generic-proxy stores -> visible to tcgen05.mma
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&fullb[stage]);
                     rg.next();
                 }
             }
