@@ -137,6 +137,8 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
+        if os.environ.get('AFCM_TC_ISSUERS') and hasattr(L, 'afcm_conv_tc_set_issuers'):       # tuning switch for A/B runs of bench.py
+            L.afcm_conv_tc_set_issuers(int(os.environ['AFCM_TC_ISSUERS']))
         _lib = _DeviceGuarded(L)
     return _lib
 
