@@ -210,6 +210,39 @@ def test_tiny_generator_grads_tc(golden_tiny, golden_tiny_grads):
     assert worst_rel[0] < TC_GRAD_REL and worst_cos[1] > TC_GRAD_COS, (worst_rel, worst_cos)
 
 
+def test_training_step_gradients_are_repeatable(golden_tiny, golden_tiny_grads):
+    """The benchmarked training path (tcgen05 forward / data / weight gradients, tensor-core filtered_lrelu with the sign tensor):
+    two forward + backward passes of the same batch.  Activations, data gradients and the sign tensors are bit-identical; weight
+    and bias gradients are sums over the batch and the plane whose order may depend on the schedule (split-K), so they are
+    compared to rounding."""
+    from afcm_b200.torch_utils.ops import conv2d_gradfix, filtered_lrelu
+    dev = torch.device('cuda:0')
+    g, gg = golden_tiny, golden_tiny_grads
+    conv2d_gradfix.set_conv_impl('tc', torch.bfloat16)
+    filtered_lrelu.set_train_impl('tc')
+    try:
+        G = _tiny(g, dev)
+        runs = []
+        for rep in range(2):
+            for p in G.parameters():
+                p.grad = None
+            y, loss = _grads(G, g, gg, dev)
+            runs.append((y.detach().clone(), {n: p.grad.detach().clone() for n, p in G.named_parameters() if p.grad is not None}))
+        assert torch.equal(runs[0][0], runs[1][0])
+        worst = 0.0
+        for n, a in runs[0][1].items():
+            b = runs[1][1][n]
+            scale = float(a.abs().max())
+            if scale == 0:
+                continue
+            worst = max(worst, float((a - b).abs().max()) / scale)
+        print(f'training step repeatability: worst parameter-gradient difference {worst:.2e} of the maximum')
+        assert worst < 1e-5
+    finally:
+        filtered_lrelu.set_train_impl('exact')
+        conv2d_gradfix.set_conv_impl('f32', torch.float16)
+
+
 def test_trainer_step_single_gpu(golden_tiny, golden_tiny_grads):
     """GeneratorTrainer: flat buffers alias the parameters, the fused Adam step equals torch.optim.Adam."""
     from afcm_b200.training import GeneratorTrainer
