@@ -409,7 +409,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // fp16 planes with even row lengths: neighbouring lanes (an even / odd pixel of the same row) exchange halves, so that
         // every lane stores one 4-byte pixel pair of one channel -- half the store instructions and conversions of the
         // element-wise path below
-        const bool paired = p.y_half && !(p.OW & 1) && !(p.Wp & 1) && !(p.OH * p.OW & 1);
+        const bool paired = p.y_half && !(p.OW & 1) && !(p.Wp & 1) && !(p.OH * p.OW & 1) && !(reinterpret_cast<uintptr_t>(p.y) & 3);
         int coef_key0 = -1, coef_key1 = -1;                          // (sample, channel tile) whose coefficients each buffer holds
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const int nt = tile % p.n_tiles;
