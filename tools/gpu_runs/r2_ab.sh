@@ -1,5 +1,7 @@
 #!/bin/bash
-# A/B of two builds of the library on one box: forward bench, alternating, three rounds
+# A/B of two builds of the library on one box: forward bench, alternating, three rounds.
+# Before the gpurun call: build the other revision (git stash / checkout, python -m afcm_b200.build) and copy its library to
+# afcm_b200/libafcm_b200_prev.so (in-tree .so files travel to the box; AFCM_B200_LIB selects the library).
 mkdir -p gpurun_out
 for r in 1 2 3; do
   for v in prev new; do
